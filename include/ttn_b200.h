@@ -1,0 +1,178 @@
+/*
+ * ttn_b200.h — C ABI of libttn_b200.so: the B200 (sm_100a) implementation of TensorTrainNumerics.jl's
+ * core-contraction hot path.
+ *
+ * The reference (pure Julia, v1.1.3) has no FFI of its own; this header defines the boundary its hot-path
+ * methods bind to through `ccall` (see INTEGRATION.md for the Julia shim).  Every entry point names the
+ * reference function it replaces (file:line relative to the reference repository root).
+ *
+ * Conventions
+ *  - All functions return an int status: 0 = ok, else one of the TTN_E* codes; ttn_last_error() gives the text.
+ *    No C++ exception crosses this boundary.  Status -> reference exception mapping:
+ *      TTN_EDIM      AssertionError("Incompatible dimensions")   src/tt_operations.jl:11,102
+ *      TTN_ECENTER   DimensionMismatch("Impossible orthogonalization")  src/tt_tools.jl:513
+ *      TTN_EARG      AssertionError (sweeps >= 1, k in 1:N-1)     src/tt_tools.jl:744,773
+ *      TTN_ESCHED    AssertionError("Sweep schedule error")       src/solvers/dmrg.jl:513, als.jl:263, mals.jl:347
+ *      TTN_ECUDA     ErrorException(ttn_last_error())
+ *  - dtype: TTN_F64 (Julia Float64) or TTN_C128 (Julia ComplexF64, interleaved re/im = cuDoubleComplex).
+ *  - Host arrays are dense column-major exactly as Julia stores them:
+ *      TT core  X_k[s,a,b]   of size (n_k, r_{k-1}, r_k):        ptr[s + n*(a + r_{k-1}*b)]      src/tt_tools.jl:23-29
+ *      MPO core A_k[i,j,a,b] of size (n_k, n_k, R_{k-1}, R_k):   ptr[i + n*(j + n*(a + R_{k-1}*b))]  src/tt_tools.jl:48-54
+ *  - Host memory stays owned by the caller; the library copies in/out and owns all device memory behind the
+ *    opaque handles, so whole sweeps run without host round trips of tensor data.
+ *  - One calling thread per process; every call is blocking.  One process drives one GPU.
+ *  - There is no CPU fallback: without a CUDA device ttn_init fails with TTN_ECUDA.
+ */
+#ifndef TTN_B200_H
+#define TTN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TTN_OK 0
+#define TTN_EDIM 1
+#define TTN_EARG 2
+#define TTN_ECENTER 3
+#define TTN_ESCHED 4
+#define TTN_ENOTCONV 5
+#define TTN_ECUDA 6
+#define TTN_EINTERNAL 7
+
+#define TTN_F64 0
+#define TTN_C128 1
+
+typedef struct ttn_ttv_s* ttn_ttv; /* device-resident TTvector  (src/tt_tools.jl:23-29)  */
+typedef struct ttn_tto_s* ttn_tto; /* device-resident TToperator (src/tt_tools.jl:48-54) */
+
+/* ---- library lifetime ------------------------------------------------------------------------------ */
+int ttn_init(int device);                 /* selects the device, creates the stream and the memory pool */
+int ttn_shutdown(void);
+const char* ttn_last_error(void);
+int ttn_version(void);
+int ttn_synchronize(void);
+long long ttn_launch_count(void);         /* kernels launched by the library since ttn_reset_launch_count */
+int ttn_reset_launch_count(void);
+void* ttn_stream(void);                   /* cudaStream_t the library launches on (for event timing) */
+
+/* ---- containers -------------------------------------------------------------------------------------- */
+/* TTvector(N, ttv_vec, ttv_dims, ttv_rks, ttv_ot): rks has d+1 entries, ot d entries (may be NULL = zeros).
+ * `batch` > 1 uploads `batch` TTs of identical dims/ranks; cores[k] then points to (n, r_l, r_r, batch). */
+int ttn_ttv_upload(int dtype, int d, const int64_t* dims, const int64_t* rks, const int64_t* ot,
+                   const void* const* cores, int batch, ttn_ttv* out);
+int ttn_ttv_info(ttn_ttv x, int* dtype, int* d, int* batch);
+int ttn_ttv_ranks(ttn_ttv x, int64_t* rks /* d+1 */);
+int ttn_ttv_dims(ttn_ttv x, int64_t* dims /* d */);
+int ttn_ttv_ot(ttn_ttv x, int64_t* ot /* d */);
+int ttn_ttv_download(ttn_ttv x, void* const* cores);
+int ttn_ttv_copy(ttn_ttv x, ttn_ttv* out);                       /* Base.copy, src/tt_tools.jl:172-178 */
+int ttn_ttv_complex(ttn_ttv x, ttn_ttv* out);                    /* Base.complex, src/tt_tools.jl:63-65 */
+int ttn_ttv_free(ttn_ttv x);
+int ttn_tto_upload(int dtype, int d, const int64_t* dims, const int64_t* rks, const void* const* cores, ttn_tto* out);
+int ttn_tto_complex(ttn_tto A, ttn_tto* out);                    /* Base.complex, src/tt_tools.jl:59-61 */
+int ttn_tto_free(ttn_tto A);
+
+/* ---- TT algebra -------------------------------------------------------------------------------------- */
+/* y = A * x                      *(A::TToperator, v::TTvector), src/tt_operations.jl:101-111 */
+int ttn_apply(ttn_tto A, ttn_ttv x, ttn_ttv* y);
+/* dot(a, b) (conj on a), out = {re, im} per batch element     src/tt_operations.jl:239-250 */
+int ttn_dot(ttn_ttv a, ttn_ttv b, double* out);
+/* norm(a) per batch element                                     src/tt_operations.jl:465-470 */
+int ttn_norm(ttn_ttv a, double* out);
+/* z = x + y                                                     src/tt_operations.jl:10-35 */
+int ttn_add(ttn_ttv x, ttn_ttv y, ttn_ttv* z);
+/* y = (re + i*im) * x  (scales the first core with ot == 0)     src/tt_operations.jl:256-266 */
+int ttn_scale(ttn_ttv x, double re, double im, ttn_ttv* y);
+
+/* ---- canonicalisation and rounding ------------------------------------------------------------------- */
+/* y = orthogonalize(x; i = center), center is 1-based          src/tt_tools.jl:511-543 */
+int ttn_orthogonalize(ttn_ttv x, int center, ttn_ttv* y);
+/* tt_compress!(x, max_bond; truncerr, sweeps): in place.       src/tt_tools.jl:772-789 with the `_svdtrunc`
+ * method of src/tt_cross_interpolation.jl:149-166.  The reference's discarded orthogonalize (tt_tools.jl:769)
+ * is not executed.  sigma_out (optional, may be NULL) receives, for batch element 0, the retained singular
+ * values of every bond step, each step padded to `sigma_stride` doubles (2*(d-1)*sweeps steps). */
+int ttn_compress(ttn_ttv x, int64_t max_bond, double truncerr, int sweeps, double* sigma_out, int64_t sigma_stride);
+/* _tt_bond_truncate!(x, k; max_bond, truncerr), k 1-based; mutates x; if y != NULL also returns
+ * orthogonalize(x; i = k) as the reference does.                src/tt_tools.jl:743-770 */
+int ttn_bond_truncate(ttn_ttv x, int k, int64_t max_bond, double truncerr, ttn_ttv* y);
+
+/* ---- alternating solvers ----------------------------------------------------------------------------- */
+typedef struct {
+  int N;                       /* window size for dmrg_* (1 or 2); ignored by als/mals */
+  double tol;                  /* SVD truncation tolerance (mals: sv_trunc, dmrg: cut_off_index) */
+  const int64_t* sweep_schedule; int n_sweep_schedule;
+  const int64_t* rmax_schedule;  int n_rmax_schedule;
+  int64_t rmax;                /* mals_linsolve rmax */
+  int sweep_count;             /* als_linsolve: number of half sweeps (src/solvers/als.jl:198-222) */
+  int it_solver;               /* accepted for signature parity; local problems are always solved matrix-free */
+  int linsolv_maxiter;         /* Krylov iteration cap per local solve */
+  double linsolv_tol;          /* Krylov tolerance per local solve */
+  int itslv_thresh;            /* accepted for signature parity */
+  int krylovdim;               /* Lanczos / GMRES subspace size (KrylovKit default 30) */
+  int symmetrize;              /* dmrg_*: apply 0.5*(K + K^T) like src/solvers/dmrg.jl:241 (1) or K only (0) */
+} ttn_solver_params;
+int ttn_solver_params_default(ttn_solver_params* p);
+
+/* als_linsolve(A, b, x0; sweep_count)            src/solvers/als.jl:161-225;  residual (optional) = ||Ax-b||/||b|| */
+int ttn_als_linsolve(ttn_tto A, ttn_ttv b, ttn_ttv x0, const ttn_solver_params* p, ttn_ttv* x, double* residual);
+/* als_eigsolve(A, x0; sweep_schedule, rmax_schedule)  src/solvers/als.jl:251-321;  E: capacity cap_E, n_E written */
+int ttn_als_eigsolve(ttn_tto A, ttn_ttv x0, const ttn_solver_params* p, ttn_ttv* x, double* E, int cap_E, int* n_E);
+/* mals_linsolve(A, b, x0; tol, rmax)             src/solvers/mals.jl:240-309 */
+int ttn_mals_linsolve(ttn_tto A, ttn_ttv b, ttn_ttv x0, const ttn_solver_params* p, ttn_ttv* x, double* residual);
+/* mals_eigsolve(A, x0; tol, sweep_schedule, rmax_schedule)   src/solvers/mals.jl:335-425 */
+int ttn_mals_eigsolve(ttn_tto A, ttn_ttv x0, const ttn_solver_params* p, ttn_ttv* x, double* E, int64_t* r_hist, int cap_E,
+                      int* n_E);
+/* dmrg_linsolve(A, b, x0; N, tol, sweep_schedule, rmax_schedule)   src/solvers/dmrg.jl:385-473 */
+int ttn_dmrg_linsolve(ttn_tto A, ttn_ttv b, ttn_ttv x0, const ttn_solver_params* p, ttn_ttv* x, double* residual);
+/* dmrg_eigsolve(A, x0; N, tol, sweep_schedule, rmax_schedule)      src/solvers/dmrg.jl:501-578 */
+int ttn_dmrg_eigsolve(ttn_tto A, ttn_ttv x0, const ttn_solver_params* p, ttn_ttv* x, double* E, int64_t* r_hist, int cap_E,
+                      int* n_E);
+
+typedef struct {
+  int two_site;                /* 0: tdvp (src/solvers/tdvp.jl:154-203), 1: tdvp2 (:303-357) */
+  const double* steps; int n_steps;
+  int normalize, sweeps, imaginary_time;
+  int64_t max_bond; double truncerr;      /* tdvp2 only */
+  int krylovdim; double krylov_tol; int krylov_maxiter;   /* KrylovKit.exponentiate stand-in */
+} ttn_tdvp_params;
+int ttn_tdvp_params_default(ttn_tdvp_params* p);
+int ttn_tdvp(ttn_tto H, ttn_ttv u0, const ttn_tdvp_params* p, ttn_ttv* u);
+
+/* ---- kernel-level entry points (parity tests, benchmarks) -------------------------------------------- */
+/* strided-batched GEMM on device pointers: C = alpha*op(A)*op(B) + beta*C  (element strides) */
+int ttn_gemm(int dtype, int M, int N, int K, const void* A, int64_t sAm, int64_t sAk, int conjA, const void* B, int64_t sBk,
+             int64_t sBn, int conjB, void* C, int64_t sCm, int64_t sCn, double alpha, double beta, int batch, int64_t bA,
+             int64_t bB, int64_t bC);
+/* two-site effective-operator matvec  Y[a,b,c] = sum G[y,a,d] Amid[y,b,e,z] V[d,e,f] H[z,c,f]  on HOST arrays in the
+ * reference layouts (src/solvers/dmrg.jl:239-244); symmetrize as in ttn_solver_params. */
+int ttn_matvec2_host(int dtype, int w_l, int w_r, int chi_l, int chi_r, int nn, const void* G, const void* Amid, const void* H,
+                     const void* V, void* Y, int symmetrize);
+/* device-resident matvec for benchmarking: prepare once, apply many times */
+typedef struct ttn_matvec_s* ttn_matvec;
+int ttn_matvec2_create(int dtype, int w_l, int w_r, int chi_l, int chi_r, int nn, const void* G, const void* Amid,
+                       const void* H, ttn_matvec* out);
+int ttn_matvec2_apply(ttn_matvec mv, const void* V_dev, void* Y_dev);   /* device pointers, (chi_l, nn, chi_r) */
+int ttn_matvec2_free(ttn_matvec mv);
+/* environment updates on HOST arrays, reference layouts (src/solvers/dmrg.jl:27-35) */
+int ttn_env_left_host(int dtype, int n, int w_l, int w_r, int r_l, int r_r, const void* G, const void* x, const void* A,
+                      void* Gout);
+int ttn_env_right_host(int dtype, int n, int w_l, int w_r, int r_l, int r_r, const void* H, const void* x, const void* A,
+                       void* Hout);
+/* truncated SVD of a host matrix (column-major m x n): `_svdtrunc` src/tt_cross_interpolation.jl:149-166.
+ * Returns U (m x r), s (r), Vt (r x n) into caller buffers sized for r = min(m,n); *r_out = retained rank. */
+int ttn_svdtrunc_host(int dtype, int m, int n, const void* A, int64_t max_bond, double truncerr, void* U, double* s, void* Vt,
+                      int* r_out);
+/* thin QR of a host matrix (column-major m x n): Q (m x k), R (k x n), k = min(m,n) */
+int ttn_qr_host(int dtype, int m, int n, const void* A, void* Q, void* R);
+/* device memory helpers for benchmarks */
+int ttn_dev_alloc(size_t bytes, void** out);
+int ttn_dev_free(void* p);
+int ttn_h2d(void* dst, const void* src, size_t bytes);
+int ttn_d2h(void* dst, const void* src, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TTN_B200_H */

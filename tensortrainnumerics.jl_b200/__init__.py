@@ -1,0 +1,7 @@
+"""tensortrainnumerics.jl_b200 — B200 (sm_100a) implementation of TensorTrainNumerics.jl's core-contraction
+hot path behind the reference's own API (host-side mirror in Python over the C ABI of libttn_b200.so).
+
+The directory name contains a dot, so import it through the top-level shim:  ``import ttn_b200``.
+"""
+from .api import *  # noqa: F401,F403
+from .api import __all__  # noqa: F401

@@ -1,0 +1,674 @@
+"""Host-side mirror of the reference's operator API for the hot path (same names, argument meaning and
+error behaviour as TensorTrainNumerics.jl; Julia's `f!` is spelled `f_`).
+
+Every function here is a thin marshalling layer over the C ABI (include/ttn_b200.h): host TT cores are
+uploaded, the whole operation (a full sweep, a full solver run) executes on the GPU inside libttn_b200.so,
+and the result is downloaded.  `DeviceTT` / `DeviceTTO` keep trains resident in HBM between calls.
+Nothing in this module computes on the CPU and nothing imports the oracle.
+
+Reference API mirrored (file:line under the reference repo):
+  TTvector / TToperator            src/tt_tools.jl:23-29, 48-54
+  A * x  (apply)                   src/tt_operations.jl:101-111
+  dot, norm, +, scalar *           src/tt_operations.jl:239-250, 465-470, 10-35, 256-266
+  orthogonalize(x; i)              src/tt_tools.jl:511-543
+  tt_compress!(x, max_bond; ...)   src/tt_tools.jl:772-789   (+ _tt_bond_truncate! :743-770)
+  als_linsolve / als_eigsolve      src/solvers/als.jl:161-225, 251-321
+  mals_linsolve / mals_eigsolve    src/solvers/mals.jl:240-309, 335-425
+  dmrg_linsolve / dmrg_eigsolve    src/solvers/dmrg.jl:385-473, 501-578
+  tdvp / tdvp2                     src/solvers/tdvp.jl:154-203, 303-357
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib
+from ._lib import TTN_F64, TTN_C128, SolverParams, TdvpParams, check
+
+__all__ = [
+    "TTvector", "TToperator", "DeviceTT", "DeviceTTO", "apply", "dot", "norm", "add", "scale", "sub",
+    "orthogonalize", "tt_compress_", "tt_bond_truncate_", "als_linsolve", "als_eigsolve", "mals_linsolve",
+    "mals_eigsolve", "dmrg_linsolve", "dmrg_eigsolve", "tdvp", "tdvp2", "matvec2", "env_left", "env_right",
+    "svdtrunc", "qr_thin", "gemm_host", "launch_count", "reset_launch_count", "synchronize", "library_path",
+]
+
+
+def library_path():
+    return _lib.LIB_PATH
+
+
+def launch_count() -> int:
+    return int(_lib.lib().ttn_launch_count())
+
+
+def reset_launch_count():
+    _lib.lib().ttn_reset_launch_count()
+
+
+def synchronize():
+    check(_lib.lib().ttn_synchronize())
+
+
+# ------------------------------------------------------------------------------------------------------
+# host containers (same field names as the reference structs)
+# ------------------------------------------------------------------------------------------------------
+class TTvector:
+    """src/tt_tools.jl:23-29.  ttv_vec[k] is an (n_k, r_{k-1}, r_k) array."""
+
+    def __init__(self, N, ttv_vec, ttv_dims, ttv_rks, ttv_ot=None):
+        self.N = int(N)
+        self.ttv_vec = list(ttv_vec)
+        self.ttv_dims = tuple(int(n) for n in ttv_dims)
+        self.ttv_rks = [int(r) for r in ttv_rks]
+        self.ttv_ot = [0] * self.N if ttv_ot is None else [int(o) for o in ttv_ot]
+
+    @property
+    def dtype(self):
+        return self.ttv_vec[0].dtype
+
+
+class TToperator:
+    """src/tt_tools.jl:48-54.  tto_vec[k] is an (n_k, n_k, R_{k-1}, R_k) array."""
+
+    def __init__(self, N, tto_vec, tto_dims, tto_rks, tto_ot=None):
+        self.N = int(N)
+        self.tto_vec = list(tto_vec)
+        self.tto_dims = tuple(int(n) for n in tto_dims)
+        self.tto_rks = [int(r) for r in tto_rks]
+        self.tto_ot = [0] * self.N if tto_ot is None else [int(o) for o in tto_ot]
+
+    @property
+    def dtype(self):
+        return self.tto_vec[0].dtype
+
+
+def _dtype_code(dt):
+    dt = np.dtype(dt)
+    if dt == np.float64:
+        return TTN_F64
+    if dt == np.complex128:
+        return TTN_C128
+    raise TypeError(f"only Float64 / ComplexF64 are supported on the device path, got {dt}")
+
+
+def _np_dtype(code):
+    return np.float64 if code == TTN_F64 else np.complex128
+
+
+def _i64(seq):
+    return (C.c_int64 * len(seq))(*[int(v) for v in seq])
+
+
+# ------------------------------------------------------------------------------------------------------
+# device-resident handles
+# ------------------------------------------------------------------------------------------------------
+class DeviceTT:
+    """A TTvector (or a batch of identically-shaped TTvectors) resident in HBM behind a `ttn_ttv` handle."""
+
+    def __init__(self, handle):
+        self._h = C.c_void_p(handle) if not isinstance(handle, C.c_void_p) else handle
+
+    @classmethod
+    def upload(cls, x):
+        """`x` is a TTvector-like object (fields N, ttv_vec, ttv_dims, ttv_rks, ttv_ot) or a list of them with
+        identical dims/ranks (uploaded as one batch)."""
+        lib = _lib.lib()
+        xs = list(x) if isinstance(x, (list, tuple)) else [x]
+        x0 = xs[0]
+        d = x0.N
+        dt = np.result_type(*[c.dtype for t in xs for c in t.ttv_vec])
+        code = _dtype_code(dt)
+        for t in xs[1:]:
+            if tuple(t.ttv_dims) != tuple(x0.ttv_dims) or list(t.ttv_rks) != list(x0.ttv_rks):
+                raise AssertionError("Incompatible dimensions")
+        keep, ptrs = [], (C.c_void_p * d)()
+        for k in range(d):
+            shp = (x0.ttv_dims[k], x0.ttv_rks[k], x0.ttv_rks[k + 1])
+            if len(xs) == 1:
+                a = np.asfortranarray(x0.ttv_vec[k], dtype=dt)
+                if a.shape != shp:
+                    raise AssertionError("Incompatible dimensions")
+            else:
+                a = np.empty(shp + (len(xs),), dtype=dt, order="F")
+                for b, t in enumerate(xs):
+                    a[..., b] = t.ttv_vec[k]
+            keep.append(a)
+            ptrs[k] = a.ctypes.data
+        out = C.c_void_p()
+        check(lib.ttn_ttv_upload(code, d, _i64(x0.ttv_dims), _i64(x0.ttv_rks), _i64(x0.ttv_ot), ptrs, len(xs),
+                                 C.byref(out)))
+        return cls(out)
+
+    # -- metadata ---------------------------------------------------------------------------------------
+    def _info(self):
+        dt, d, b = C.c_int(), C.c_int(), C.c_int()
+        check(_lib.lib().ttn_ttv_info(self._h, C.byref(dt), C.byref(d), C.byref(b)))
+        return dt.value, d.value, b.value
+
+    @property
+    def N(self):
+        return self._info()[1]
+
+    @property
+    def batch(self):
+        return self._info()[2]
+
+    @property
+    def dtype(self):
+        return np.dtype(_np_dtype(self._info()[0]))
+
+    def _vec(self, fn, n):
+        buf = (C.c_int64 * n)()
+        check(fn(self._h, buf))
+        return [int(v) for v in buf]
+
+    @property
+    def ttv_rks(self):
+        return self._vec(_lib.lib().ttn_ttv_ranks, self.N + 1)
+
+    @property
+    def ttv_dims(self):
+        return tuple(self._vec(_lib.lib().ttn_ttv_dims, self.N))
+
+    @property
+    def ttv_ot(self):
+        return self._vec(_lib.lib().ttn_ttv_ot, self.N)
+
+    # -- data -------------------------------------------------------------------------------------------
+    def download(self):
+        """Returns a TTvector (batch == 1) or a list of TTvectors."""
+        code, d, batch = self._info()
+        dims, rks, ot = self.ttv_dims, self.ttv_rks, self.ttv_ot
+        arrs, ptrs = [], (C.c_void_p * d)()
+        for k in range(d):
+            shp = (dims[k], rks[k], rks[k + 1]) + ((batch,) if batch > 1 else ())
+            a = np.empty(shp, dtype=_np_dtype(code), order="F")
+            arrs.append(a)
+            ptrs[k] = a.ctypes.data
+        check(_lib.lib().ttn_ttv_download(self._h, ptrs))
+        if batch == 1:
+            return TTvector(d, arrs, dims, rks, ot)
+        return [TTvector(d, [np.asfortranarray(a[..., b]) for a in arrs], dims, rks, ot) for b in range(batch)]
+
+    def copy(self):
+        out = C.c_void_p()
+        check(_lib.lib().ttn_ttv_copy(self._h, C.byref(out)))
+        return DeviceTT(out)
+
+    def complex(self):
+        out = C.c_void_p()
+        check(_lib.lib().ttn_ttv_complex(self._h, C.byref(out)))
+        return DeviceTT(out)
+
+    def free(self):
+        if self._h is not None and self._h.value:
+            _lib.load().ttn_ttv_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class DeviceTTO:
+    """A TToperator resident in HBM behind a `ttn_tto` handle."""
+
+    def __init__(self, handle, dtype_code, N):
+        self._h = handle
+        self._code = dtype_code
+        self.N = N
+
+    @classmethod
+    def upload(cls, A):
+        lib = _lib.lib()
+        d = A.N
+        dt = np.result_type(*[c.dtype for c in A.tto_vec])
+        code = _dtype_code(dt)
+        keep, ptrs = [], (C.c_void_p * d)()
+        for k in range(d):
+            a = np.asfortranarray(A.tto_vec[k], dtype=dt)
+            if a.shape != (A.tto_dims[k], A.tto_dims[k], A.tto_rks[k], A.tto_rks[k + 1]):
+                raise AssertionError("Incompatible dimensions")
+            keep.append(a)
+            ptrs[k] = a.ctypes.data
+        out = C.c_void_p()
+        check(lib.ttn_tto_upload(code, d, _i64(A.tto_dims), _i64(A.tto_rks), ptrs, C.byref(out)))
+        return cls(out, code, d)
+
+    @property
+    def dtype(self):
+        return np.dtype(_np_dtype(self._code))
+
+    def complex(self):
+        out = C.c_void_p()
+        check(_lib.lib().ttn_tto_complex(self._h, C.byref(out)))
+        return DeviceTTO(out, TTN_C128, self.N)
+
+    def free(self):
+        if self._h is not None and self._h.value:
+            _lib.load().ttn_tto_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _dev(x):
+    """(DeviceTT, was_host)"""
+    if isinstance(x, DeviceTT):
+        return x, False
+    return DeviceTT.upload(x), True
+
+
+def _devo(A, want_dtype=None):
+    if isinstance(A, DeviceTTO):
+        d = A
+    else:
+        d = DeviceTTO.upload(A)
+    if want_dtype is not None and np.dtype(want_dtype) == np.complex128 and d.dtype != np.complex128:
+        d = d.complex()
+    return d
+
+
+def _match(*devs):
+    """promote a set of DeviceTT to a common element type (Julia would promote_type)."""
+    if any(v.dtype == np.complex128 for v in devs):
+        return [v if v.dtype == np.complex128 else v.complex() for v in devs]
+    return list(devs)
+
+
+def _ret(dev, host):
+    return dev.download() if host else dev
+
+
+# ------------------------------------------------------------------------------------------------------
+# TT algebra
+# ------------------------------------------------------------------------------------------------------
+def apply(A, x):
+    """`A * x`, src/tt_operations.jl:101-111."""
+    xd, host = _dev(x)
+    Ad = _devo(A, xd.dtype)
+    if Ad.dtype == np.complex128 and xd.dtype != np.complex128:
+        xd = xd.complex()
+    out = C.c_void_p()
+    check(_lib.lib().ttn_apply(Ad._h, xd._h, C.byref(out)))
+    return _ret(DeviceTT(out), host)
+
+
+def dot(a, b):
+    """src/tt_operations.jl:239-250 (conjugates the first argument)."""
+    ad, _ = _dev(a)
+    bd, _ = _dev(b)
+    ad, bd = _match(ad, bd)
+    batch = ad.batch
+    buf = (C.c_double * (2 * batch))()
+    check(_lib.lib().ttn_dot(ad._h, bd._h, buf))
+    vals = np.array(buf[:]).reshape(batch, 2)
+    res = vals[:, 0] + 1j * vals[:, 1] if ad.dtype == np.complex128 else vals[:, 0].copy()
+    return res[0] if batch == 1 else res
+
+
+def norm(a):
+    """src/tt_operations.jl:465-470."""
+    ad, _ = _dev(a)
+    batch = ad.batch
+    buf = (C.c_double * batch)()
+    check(_lib.lib().ttn_norm(ad._h, buf))
+    return float(buf[0]) if batch == 1 else np.array(buf[:])
+
+
+def add(x, y):
+    """`x + y`, src/tt_operations.jl:10-35."""
+    xd, host = _dev(x)
+    yd, _ = _dev(y)
+    xd, yd = _match(xd, yd)
+    out = C.c_void_p()
+    check(_lib.lib().ttn_add(xd._h, yd._h, C.byref(out)))
+    return _ret(DeviceTT(out), host)
+
+
+def scale(a, x):
+    """`a * x`, src/tt_operations.jl:256-266."""
+    xd, host = _dev(x)
+    a = complex(a)
+    if a.imag != 0.0 and xd.dtype != np.complex128:
+        xd = xd.complex()
+    out = C.c_void_p()
+    check(_lib.lib().ttn_scale(xd._h, a.real, a.imag, C.byref(out)))
+    return _ret(DeviceTT(out), host)
+
+
+def sub(x, y):
+    """`x - y` = (-1.0 * y) + x, src/tt_operations.jl:280-282."""
+    xd, host = _dev(x)
+    yd, _ = _dev(y)
+    return _ret(add(scale(-1.0, yd), xd), host)
+
+
+# ------------------------------------------------------------------------------------------------------
+# canonicalisation / rounding
+# ------------------------------------------------------------------------------------------------------
+def orthogonalize(x, i: int = 1):
+    """src/tt_tools.jl:511-543 (pure; centre `i` is 1-based)."""
+    xd, host = _dev(x)
+    out = C.c_void_p()
+    check(_lib.lib().ttn_orthogonalize(xd._h, int(i), C.byref(out)))
+    return _ret(DeviceTT(out), host)
+
+
+def tt_compress_(x, max_bond: int, truncerr: float = 0.0, sweeps: int = 1, verbose: bool = False, return_sigma: bool = False):
+    """`tt_compress!(ψ, max_bond; truncerr, sweeps, verbose)`, src/tt_tools.jl:772-789: mutates and returns `x`.
+    With `return_sigma=True` also returns the retained singular values of every bond step."""
+    lib = _lib.lib()
+    xd, host = _dev(x)
+    sig, stride, nsteps = None, 0, 0
+    if return_sigma:
+        rks = xd.ttv_rks
+        dims = xd.ttv_dims
+        stride = int(max(min(dims[k] * rks[k], dims[k + 1] * rks[k + 2]) for k in range(xd.N - 1))) if xd.N > 1 else 1
+        nsteps = 2 * (xd.N - 1) * max(int(sweeps), 0)
+        sig = (C.c_double * max(1, stride * nsteps))()
+    check(lib.ttn_compress(xd._h, int(max_bond), float(truncerr), int(sweeps), sig, int(stride)))
+    if host:
+        y = xd.download()
+        x.ttv_vec = y.ttv_vec          # same object mutated, `ttv_ot` untouched (test/test_tt_tools.jl:514)
+        x.ttv_rks = y.ttv_rks
+        res = x
+    else:
+        res = xd
+    if return_sigma:
+        s = np.array(sig[:]).reshape(nsteps, stride) if nsteps else np.zeros((0, stride))
+        return res, [row[row > 0] for row in s]
+    return res
+
+
+def tt_bond_truncate_(x, k: int, max_bond: int | None = None, truncerr: float = 0.0):
+    """`_tt_bond_truncate!(ψ, k; max_bond, truncerr)`, src/tt_tools.jl:743-770: mutates `x` and returns
+    `orthogonalize(ψ; i=k)` as the reference does."""
+    xd, host = _dev(x)
+    out = C.c_void_p()
+    mb = (1 << 62) if max_bond is None else int(max_bond)
+    check(_lib.lib().ttn_bond_truncate(xd._h, int(k), mb, float(truncerr), C.byref(out)))
+    y = DeviceTT(out)
+    if host:
+        z = xd.download()
+        x.ttv_vec, x.ttv_rks = z.ttv_vec, z.ttv_rks
+        return y.download()
+    return y
+
+
+# ------------------------------------------------------------------------------------------------------
+# solvers
+# ------------------------------------------------------------------------------------------------------
+def _params(**kw):
+    p = SolverParams()
+    check(_lib.lib().ttn_solver_params_default(C.byref(p)))
+    keep = []
+    for name in ("sweep_schedule", "rmax_schedule"):
+        v = kw.pop(name, None)
+        if v is not None:
+            arr = _i64(list(v))
+            keep.append(arr)
+            setattr(p, name, C.cast(arr, C.POINTER(C.c_int64)))
+            setattr(p, "n_" + name, len(v))
+    for k, v in kw.items():
+        if v is not None:
+            setattr(p, k, v)
+    return p, keep
+
+
+def _isqrt_prod(dims):
+    pr = 1
+    for n in dims:
+        pr *= int(n)
+    return math.isqrt(pr)
+
+
+def _solve_lin(fn, A, b, x0, p):
+    xd, host = _dev(x0)
+    bd, _ = _dev(b)
+    xd, bd = _match(xd, bd)
+    Ad = _devo(A, xd.dtype)
+    if Ad.dtype == np.complex128 and xd.dtype != np.complex128:
+        xd, bd = xd.complex(), bd.complex()
+    out, res = C.c_void_p(), C.c_double()
+    check(fn(Ad._h, bd._h, xd._h, C.byref(p), C.byref(out), C.byref(res)))
+    return DeviceTT(out), host, res.value
+
+
+def als_linsolve(A, b, tt_start, sweep_count=2, it_solver=False, r_itsolver=5000, return_info=False,
+                 linsolv_maxiter=200, krylovdim=30):
+    """src/solvers/als.jl:161-225 (`sweep_count` counts half sweeps, als.jl:198-222)."""
+    p, keep = _params(sweep_count=int(sweep_count), linsolv_maxiter=int(linsolv_maxiter), krylovdim=int(krylovdim))
+    x, host, res = _solve_lin(_lib.lib().ttn_als_linsolve, A, b, tt_start, p)
+    x = _ret(x, host)
+    return (x, {"residual": res}) if return_info else x
+
+
+def als_eigsolve(A, tt_start, sweep_schedule=(2,), rmax_schedule=None, noise_schedule=None, it_solver=False,
+                 itslv_thresh=1024, maxiter=200, linsolv_tol=1e-8, krylovdim=30):
+    """src/solvers/als.jl:251-321 → (E, tt_opt).  Only noise_schedule == 0 is supported on the device path."""
+    if noise_schedule is not None and any(float(v) != 0.0 for v in noise_schedule):
+        raise NotImplementedError("noise_schedule != 0 draws from the host RNG and is not on the device path")
+    xd, host = _dev(tt_start)
+    if rmax_schedule is None:
+        rmax_schedule = [max(xd.ttv_rks)]
+    if len(rmax_schedule) != len(sweep_schedule):
+        raise AssertionError("Sweep schedule error")
+    Ad = _devo(A, xd.dtype)
+    if Ad.dtype == np.complex128 and xd.dtype != np.complex128:
+        xd = xd.complex()
+    p, keep = _params(sweep_schedule=sweep_schedule, rmax_schedule=rmax_schedule, linsolv_maxiter=int(maxiter),
+                      linsolv_tol=float(linsolv_tol), krylovdim=int(krylovdim))
+    cap = 2 * xd.N * (int(sweep_schedule[-1]) + 1) + 8
+    E, nE, out = (C.c_double * cap)(), C.c_int(), C.c_void_p()
+    check(_lib.lib().ttn_als_eigsolve(Ad._h, xd._h, C.byref(p), C.byref(out), E, cap, C.byref(nE)))
+    return np.array(E[:nE.value]), _ret(DeviceTT(out), host)
+
+
+def mals_linsolve(A, b, tt_start, tol=1e-12, rmax=None, return_info=False, linsolv_maxiter=200, krylovdim=30):
+    """src/solvers/mals.jl:240-309 (exactly one forward and one backward sweep)."""
+    dims = tt_start.ttv_dims
+    if rmax is None:
+        rmax = int(round(math.sqrt(float(np.prod([float(n) for n in dims])))))
+    p, keep = _params(tol=float(tol), rmax=int(rmax), linsolv_maxiter=int(linsolv_maxiter), krylovdim=int(krylovdim))
+    x, host, res = _solve_lin(_lib.lib().ttn_mals_linsolve, A, b, tt_start, p)
+    x = _ret(x, host)
+    return (x, {"residual": res}) if return_info else x
+
+
+def _eig_with_hist(fn, A, tt_start, p, cap):
+    xd, host = _dev(tt_start)
+    Ad = _devo(A, xd.dtype)
+    if Ad.dtype == np.complex128 and xd.dtype != np.complex128:
+        xd = xd.complex()
+    E, rh, nE, out = (C.c_double * cap)(), (C.c_int64 * cap)(), C.c_int(), C.c_void_p()
+    check(fn(Ad._h, xd._h, C.byref(p), C.byref(out), E, rh, cap, C.byref(nE)))
+    return np.array(E[:nE.value]), _ret(DeviceTT(out), host), [int(v) for v in rh[:nE.value]]
+
+
+def mals_eigsolve(A, tt_start, tol=1e-12, sweep_schedule=(2,), rmax_schedule=None, it_solver=False, linsolv_maxiter=200,
+                  linsolv_tol=None, itslv_thresh=256, krylovdim=30):
+    """src/solvers/mals.jl:335-425 → (E, tt_opt, r_hist)."""
+    if rmax_schedule is None:
+        rmax_schedule = [int(round(math.sqrt(float(np.prod([float(n) for n in tt_start.ttv_dims])))))]
+    if len(rmax_schedule) != len(sweep_schedule):
+        raise AssertionError("Sweep schedule error")
+    if linsolv_tol is None:
+        linsolv_tol = max(math.sqrt(tol), 1e-8)
+    p, keep = _params(tol=float(tol), sweep_schedule=sweep_schedule, rmax_schedule=rmax_schedule,
+                      linsolv_maxiter=int(linsolv_maxiter), linsolv_tol=float(linsolv_tol), krylovdim=int(krylovdim))
+    cap = 2 * tt_start.N * (int(sweep_schedule[-1]) + 1) + 8
+    return _eig_with_hist(_lib.lib().ttn_mals_eigsolve, A, tt_start, p, cap)
+
+
+def dmrg_linsolve(A, b, tt_start, sweep_count=2, N=2, tol=1e-12, sweep_schedule=(2,), rmax_schedule=None, it_solver=True,
+                  linsolv_maxiter=200, linsolv_tol=None, itslv_thresh=256, return_info=False, krylovdim=30, symmetrize=False):
+    """src/solvers/dmrg.jl:385-473 (`sweep_count` is accepted and ignored, as in the reference :386)."""
+    if rmax_schedule is None:
+        rmax_schedule = [_isqrt_prod(tt_start.ttv_dims)]
+    if linsolv_tol is None:
+        linsolv_tol = max(math.sqrt(tol), 1e-8)
+    p, keep = _params(N=int(N), tol=float(tol), sweep_schedule=sweep_schedule, rmax_schedule=rmax_schedule,
+                      linsolv_maxiter=int(linsolv_maxiter), linsolv_tol=float(linsolv_tol), krylovdim=int(krylovdim),
+                      symmetrize=int(bool(symmetrize)))
+    x, host, res = _solve_lin(_lib.lib().ttn_dmrg_linsolve, A, b, tt_start, p)
+    x = _ret(x, host)
+    return (x, {"residual": res}) if return_info else x
+
+
+def dmrg_eigsolve(A, tt_start, N=2, tol=1e-12, sweep_schedule=(2,), rmax_schedule=None, it_solver=False,
+                  linsolv_maxiter=200, linsolv_tol=None, itslv_thresh=256, krylovdim=30, symmetrize=False):
+    """src/solvers/dmrg.jl:501-578 → (E, tt_opt, r_hist)."""
+    if rmax_schedule is None:
+        rmax_schedule = [_isqrt_prod(tt_start.ttv_dims)]
+    if len(rmax_schedule) != len(sweep_schedule):
+        raise AssertionError("Sweep schedule error")
+    if linsolv_tol is None:
+        linsolv_tol = max(math.sqrt(tol), 1e-8)
+    p, keep = _params(N=int(N), tol=float(tol), sweep_schedule=sweep_schedule, rmax_schedule=rmax_schedule,
+                      linsolv_maxiter=int(linsolv_maxiter), linsolv_tol=float(linsolv_tol), krylovdim=int(krylovdim),
+                      symmetrize=int(bool(symmetrize)))
+    cap = 2 * tt_start.N * (int(sweep_schedule[-1]) + 1) + 8
+    return _eig_with_hist(_lib.lib().ttn_dmrg_eigsolve, A, tt_start, p, cap)
+
+
+def _tdvp(two_site, H, u0, steps, normalize, sweeps, imaginary_time, max_bond, truncerr, krylovdim, tol, maxiter):
+    lib = _lib.lib()
+    ud, host = _dev(u0)
+    Hd = _devo(H, ud.dtype)
+    if Hd.dtype == np.complex128 and ud.dtype != np.complex128:
+        ud = ud.complex()
+    p = TdvpParams()
+    check(lib.ttn_tdvp_params_default(C.byref(p)))
+    st = (C.c_double * len(steps))(*[float(s) for s in steps])
+    p.two_site = int(two_site)
+    p.steps = C.cast(st, C.POINTER(C.c_double))
+    p.n_steps = len(steps)
+    p.normalize, p.sweeps, p.imaginary_time = int(bool(normalize)), int(sweeps), int(bool(imaginary_time))
+    p.max_bond = (1 << 62) if max_bond is None else int(max_bond)
+    p.truncerr = float(truncerr)
+    p.krylovdim, p.krylov_tol, p.krylov_maxiter = int(krylovdim), float(tol), int(maxiter)
+    out = C.c_void_p()
+    check(lib.ttn_tdvp(Hd._h, ud._h, C.byref(p), C.byref(out)))
+    return _ret(DeviceTT(out), host)
+
+
+def tdvp(H, u0, steps, normalize=True, sweeps=1, imaginary_time=False, krylovdim=30, tol=1e-12, maxiter=100):
+    """src/solvers/tdvp.jl:154-203."""
+    return _tdvp(0, H, u0, steps, normalize, sweeps, imaginary_time, None, 0.0, krylovdim, tol, maxiter)
+
+
+def tdvp2(H, u0, steps, normalize=True, sweeps=1, max_bond=None, truncerr=0.0, imaginary_time=False, krylovdim=30,
+          tol=1e-12, maxiter=100):
+    """src/solvers/tdvp.jl:303-357."""
+    return _tdvp(1, H, u0, steps, normalize, sweeps, imaginary_time, max_bond, truncerr, krylovdim, tol, maxiter)
+
+
+# ------------------------------------------------------------------------------------------------------
+# kernel-level entry points (tests / benchmarks), host arrays in the reference layouts
+# ------------------------------------------------------------------------------------------------------
+def _f(a, dt):
+    return np.asfortranarray(a, dtype=dt)
+
+
+def matvec2(G, Amid, H, V, symmetrize=False):
+    """K_matfree of src/solvers/dmrg.jl:239-244 on host arrays: G (w_l,chi_l,chi_l), Amid (w_l,nn,nn,w_r),
+    H (w_r,chi_r,chi_r), V (chi_l,nn,chi_r)."""
+    dt = np.result_type(G.dtype, Amid.dtype, H.dtype, V.dtype)
+    code = _dtype_code(dt)
+    G, Amid, H, V = _f(G, dt), _f(Amid, dt), _f(H, dt), _f(V, dt)
+    Y = np.empty(V.shape, dtype=dt, order="F")
+    check(_lib.lib().ttn_matvec2_host(code, G.shape[0], H.shape[0], G.shape[1], H.shape[1], Amid.shape[1], G.ctypes.data,
+                                      Amid.ctypes.data, H.ctypes.data, V.ctypes.data, Y.ctypes.data, int(bool(symmetrize))))
+    return Y
+
+
+def env_left(G, x, A):
+    """update_G! of src/solvers/dmrg.jl:32-35: G (w_l,r_l,r_l), x (n,r_l,r_r), A (n,n,w_l,w_r) → (w_r,r_r,r_r)."""
+    dt = np.result_type(G.dtype, x.dtype, A.dtype)
+    G, x, A = _f(G, dt), _f(x, dt), _f(A, dt)
+    n, rl, rr = x.shape
+    wl, wr = A.shape[2], A.shape[3]
+    out = np.empty((wr, rr, rr), dtype=dt, order="F")
+    check(_lib.lib().ttn_env_left_host(_dtype_code(dt), n, wl, wr, rl, rr, G.ctypes.data, x.ctypes.data, A.ctypes.data,
+                                       out.ctypes.data))
+    return out
+
+
+def env_right(H, x, A):
+    """update_H! of src/solvers/dmrg.jl:27-30: H (w_r,r_r,r_r), x (n,r_l,r_r), A (n,n,w_l,w_r) → (w_l,r_l,r_l)."""
+    dt = np.result_type(H.dtype, x.dtype, A.dtype)
+    H, x, A = _f(H, dt), _f(x, dt), _f(A, dt)
+    n, rl, rr = x.shape
+    wl, wr = A.shape[2], A.shape[3]
+    out = np.empty((wl, rl, rl), dtype=dt, order="F")
+    check(_lib.lib().ttn_env_right_host(_dtype_code(dt), n, wl, wr, rl, rr, H.ctypes.data, x.ctypes.data, A.ctypes.data,
+                                        out.ctypes.data))
+    return out
+
+
+def svdtrunc(A, max_bond=None, truncerr=0.0):
+    """`_svdtrunc(A; max_bond, truncerr)` (the tail-norm method, src/tt_cross_interpolation.jl:149-166)
+    → (U, s, Vt)."""
+    dt = A.dtype
+    A = _f(A, dt)
+    m, n = A.shape
+    k = min(m, n)
+    U = np.empty((m, k), dtype=dt, order="F")
+    Vt = np.empty((k * n,), dtype=dt)
+    s = (C.c_double * k)()
+    r = C.c_int()
+    mb = (1 << 62) if max_bond is None else int(max_bond)
+    check(_lib.lib().ttn_svdtrunc_host(_dtype_code(dt), m, n, A.ctypes.data, mb, float(truncerr), U.ctypes.data, s,
+                                       Vt.ctypes.data, C.byref(r)))
+    r = r.value
+    return (np.asfortranarray(U.reshape(-1, order="F")[: m * r].reshape(m, r, order="F")), np.array(s[:r]),
+            Vt[: r * n].reshape(r, n, order="F"))
+
+
+def qr_thin(A):
+    """thin Householder QR (LAPACK conventions) of a host matrix → (Q, R)."""
+    dt = A.dtype
+    A = _f(A, dt)
+    m, n = A.shape
+    k = min(m, n)
+    Q = np.empty((m, k), dtype=dt, order="F")
+    R = np.empty((k, n), dtype=dt, order="F")
+    check(_lib.lib().ttn_qr_host(_dtype_code(dt), m, n, A.ctypes.data, Q.ctypes.data, R.ctypes.data))
+    return Q, R
+
+
+def gemm_host(A, B, conjA=False, conjB=False, transA=False, transB=False, alpha=1.0, beta=0.0, C0=None):
+    """C = alpha·op(A)·op(B) + beta·C0 through the DMMA GEMM (device round trip; test helper)."""
+    lib = _lib.lib()
+    dt = np.result_type(A.dtype, B.dtype)
+    code = _dtype_code(dt)
+    A, B = _f(A, dt), _f(B, dt)
+    M = A.shape[1] if transA else A.shape[0]
+    K = A.shape[0] if transA else A.shape[1]
+    N = B.shape[0] if transB else B.shape[1]
+    Cm = np.zeros((M, N), dtype=dt, order="F") if C0 is None else _f(C0, dt).copy(order="F")
+    es = np.dtype(dt).itemsize
+    ptrs = []
+    for arr in (A, B, Cm):
+        p = C.c_void_p()
+        check(lib.ttn_dev_alloc(max(arr.nbytes, es), C.byref(p)))
+        check(lib.ttn_h2d(p, arr.ctypes.data, arr.nbytes))
+        ptrs.append(p)
+    sAm, sAk = (A.shape[0], 1) if transA else (1, A.shape[0])
+    sBk, sBn = (B.shape[0], 1) if transB else (1, B.shape[0])
+    check(lib.ttn_gemm(code, M, N, K, ptrs[0], sAm, sAk, int(conjA), ptrs[1], sBk, sBn, int(conjB), ptrs[2], 1, M,
+                       float(alpha), float(beta), 1, 0, 0, 0))
+    check(lib.ttn_synchronize())
+    check(lib.ttn_d2h(Cm.ctypes.data, ptrs[2], Cm.nbytes))
+    for p in ptrs:
+        check(lib.ttn_dev_free(p))
+    return Cm

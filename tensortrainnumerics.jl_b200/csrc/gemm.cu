@@ -1,0 +1,251 @@
+// Strided-batched FP64 / ComplexF64 GEMM on the sm_100a FP64 tensor pipe (SASS: DMMA.8x8x4).
+//
+// This is kernel family F1/F2/F3 of SURVEY.md §2.1: every contraction on the reference's hot path —
+// the effective-operator matvec L·W·X·R (src/solvers/dmrg.jl:239-244, als.jl:78, mals.jl:193-198,
+// tdvp.jl:30,34,206-207), the environment updates (dmrg.jl:27-35, als.jl:23-55, mals.jl:10-13,
+// tdvp.jl:37-43), the two-site merge (tt_tools.jl:749) and the bond absorbs (als.jl:116,132,
+// dmrg.jl:318,334) — is issued as one or more calls of this kernel.  Operands are addressed through
+// explicit element strides plus two batch dimensions, so the (s,l,r)/(l,s,r) permutes that the reference
+// performs with `permutedims` (tt_tools.jl:746-747, dmrg.jl:39, tdvp.jl:54-55) are folded into the loads.
+//
+// Design (B200): 256-thread CTAs, BK=16 k-slab, register-staged double buffering through padded shared
+// memory (pitch ≡ 4 mod 16 doubles → the m8n8k4 fragment loads are bank-conflict free), each warp owns a
+// WM x WN accumulator block held in registers and issues mma.sync.m8n8k4.f64.  ComplexF64 runs as four
+// real DMMA products on split re/im fragments.  sm_100a has no f64 kind for tcgen05.mma, so DMMA via
+// mma.sync is the FP64 tensor path on this chip (larger f64 shapes decompose to 8x8x4 in SASS).
+#include "ttn_internal.h"
+
+namespace ttn {
+
+namespace {
+
+constexpr int BK = 16;
+constexpr int NT = 256;
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+template <class T> struct Pad { static constexpr int v = 4; };
+template <> struct Pad<zc> { static constexpr int v = 2; };
+
+template <class T> struct Acc;
+template <> struct Acc<double> {
+  double c[2];
+  __device__ __forceinline__ void zero() { c[0] = c[1] = 0.0; }
+  __device__ __forceinline__ void mma(double a, double b) { dmma884(c[0], c[1], a, b); }
+  __device__ __forceinline__ double get(int i) const { return c[i]; }
+};
+template <> struct Acc<zc> {
+  double re[2], im[2];
+  __device__ __forceinline__ void zero() { re[0] = re[1] = im[0] = im[1] = 0.0; }
+  __device__ __forceinline__ void mma(zc a, zc b) {
+    dmma884(re[0], re[1], a.x, b.x);
+    dmma884(re[0], re[1], -a.y, b.y);
+    dmma884(im[0], im[1], a.x, b.y);
+    dmma884(im[0], im[1], a.y, b.x);
+  }
+  __device__ __forceinline__ zc get(int i) const { return make_cuDoubleComplex(re[i], im[i]); }
+};
+
+template <class T, int BM, int BN, int WM, int WN, bool AMAJ, bool BMAJ>
+__global__ void __launch_bounds__(NT) gemm_kernel(const GemmArgs g) {
+  constexpr int PAD = Pad<T>::v;
+  constexpr int PA = BM + PAD, PB = BN + PAD;
+  constexpr int EA = BM * BK / NT, EB = BN * BK / NT;
+  constexpr int MT = WM / 8, NTL = WN / 8;
+  constexpr int WARPS_M = BM / WM;
+  static_assert((BM / WM) * (BN / WN) == NT / 32, "warp layout must cover the CTA tile");
+  static_assert(BM * BK % NT == 0 && BN * BK % NT == 0, "tile loads must divide evenly");
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* As = reinterpret_cast<T*>(smem_raw);            // [2][BK][PA]
+  T* Bs = As + 2 * BK * PA;                          // [2][BK][PB]
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g8 = lane >> 2, t4 = lane & 3;
+  const int wm0 = (warp % WARPS_M) * WM, wn0 = (warp / WARPS_M) * WN;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int b = blockIdx.z, b1 = b % g.batch1, b2 = b / g.batch1;
+
+  const T* __restrict__ A = reinterpret_cast<const T*>(g.A) + b1 * g.bA1 + b2 * g.bA2;
+  const T* __restrict__ B = reinterpret_cast<const T*>(g.B) + b1 * g.bB1 + b2 * g.bB2;
+  T* __restrict__ C = reinterpret_cast<T*>(g.C) + b1 * g.bC1 + b2 * g.bC2;
+
+  Acc<T> acc[MT][NTL];
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < NTL; ++j) acc[i][j].zero();
+
+  T ra[EA], rb[EB];
+  const int nkt = (g.K + BK - 1) / BK;
+
+  auto load_global = [&](int kt) {
+    const int k0 = kt * BK;
+#pragma unroll
+    for (int r = 0; r < EA; ++r) {
+      const int idx = tid + r * NT;
+      const int m = AMAJ ? (idx % BM) : (idx / BK);
+      const int k = AMAJ ? (idx / BM) : (idx % BK);
+      const int gm = m0 + m, gk = k0 + k;
+      T v = t_zero<T>();
+      if (gm < g.M && gk < g.K) v = A[(int64_t)gm * g.sAm + (int64_t)gk * g.sAk];
+      ra[r] = v;
+    }
+#pragma unroll
+    for (int r = 0; r < EB; ++r) {
+      const int idx = tid + r * NT;
+      const int n = BMAJ ? (idx % BN) : (idx / BK);
+      const int k = BMAJ ? (idx / BN) : (idx % BK);
+      const int gn = n0 + n, gk = k0 + k;
+      T v = t_zero<T>();
+      if (gn < g.N && gk < g.K) v = B[(int64_t)gk * g.sBk + (int64_t)gn * g.sBn];
+      rb[r] = v;
+    }
+  };
+  auto store_smem = [&](int buf) {
+    T* as = As + buf * BK * PA;
+    T* bs = Bs + buf * BK * PB;
+#pragma unroll
+    for (int r = 0; r < EA; ++r) {
+      const int idx = tid + r * NT;
+      const int m = AMAJ ? (idx % BM) : (idx / BK);
+      const int k = AMAJ ? (idx / BM) : (idx % BK);
+      as[k * PA + m] = g.conjA ? t_conj(ra[r]) : ra[r];
+    }
+#pragma unroll
+    for (int r = 0; r < EB; ++r) {
+      const int idx = tid + r * NT;
+      const int n = BMAJ ? (idx % BN) : (idx / BK);
+      const int k = BMAJ ? (idx / BN) : (idx % BK);
+      bs[k * PB + n] = g.conjB ? t_conj(rb[r]) : rb[r];
+    }
+  };
+
+  if (nkt > 0) {
+    load_global(0);
+    store_smem(0);
+  }
+  __syncthreads();
+
+  for (int kt = 0; kt < nkt; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nkt) load_global(kt + 1);
+    const T* as = As + buf * BK * PA;
+    const T* bs = Bs + buf * BK * PB;
+#pragma unroll
+    for (int kk = 0; kk < BK; kk += 4) {
+      T af[MT], bf[NTL];
+#pragma unroll
+      for (int i = 0; i < MT; ++i) af[i] = as[(kk + t4) * PA + wm0 + i * 8 + g8];
+#pragma unroll
+      for (int j = 0; j < NTL; ++j) bf[j] = bs[(kk + t4) * PB + wn0 + j * 8 + g8];
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NTL; ++j) acc[i][j].mma(af[i], bf[j]);
+    }
+    if (kt + 1 < nkt) store_smem(buf ^ 1);
+    __syncthreads();
+  }
+
+  // epilogue: C = alpha*acc + beta*C, written straight from the DMMA accumulator layout
+  const bool has_beta = (g.beta != 0.0);
+#pragma unroll
+  for (int i = 0; i < MT; ++i) {
+    const int row = m0 + wm0 + i * 8 + g8;
+    if (row >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < NTL; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int col = n0 + wn0 + j * 8 + 2 * t4 + e;
+        if (col < g.N) {
+          T* p = C + (int64_t)row * g.sCm + (int64_t)col * g.sCn;
+          T v = t_scale(acc[i][j].get(e), g.alpha);
+          if (has_beta) v = t_add(v, t_scale(*p, g.beta));
+          *p = v;
+        }
+      }
+    }
+  }
+}
+
+template <class T, int BM, int BN, int WM, int WN, bool AMAJ, bool BMAJ>
+void launch_cfg(const GemmArgs& g) {
+  constexpr int PAD = Pad<T>::v;
+  const size_t smem = sizeof(T) * 2 * BK * ((BM + PAD) + (BN + PAD));
+  auto kern = gemm_kernel<T, BM, BN, WM, WN, AMAJ, BMAJ>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    TTN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  const int64_t nb = (int64_t)g.batch1 * g.batch2;
+  // grid.z is limited to 65535: split the outer batch dimension if needed
+  const int64_t max_b2 = std::max<int64_t>(1, 65535 / g.batch1);
+  ttn_assert(g.batch1 <= 65535, 2, "gemm: inner batch dimension too large");
+  for (int64_t s = 0; s < g.batch2; s += max_b2) {
+    GemmArgs h = g;
+    const int64_t nb2 = std::min<int64_t>(max_b2, g.batch2 - s);
+    h.batch2 = (int)nb2;
+    const size_t es = sizeof(T);
+    h.A = reinterpret_cast<const char*>(g.A) + es * s * g.bA2;
+    h.B = reinterpret_cast<const char*>(g.B) + es * s * g.bB2;
+    h.C = reinterpret_cast<char*>(g.C) + es * s * g.bC2;
+    dim3 grid((g.M + BM - 1) / BM, (g.N + BN - 1) / BN, (unsigned)(g.batch1 * nb2));
+    ttn_assert(grid.y <= 65535, 2, "gemm: N too large for grid.y");
+    kern<<<grid, NT, smem, ctx().stream>>>(h);
+    TTN_CHECK_LAUNCH();
+    ctx().launches++;
+  }
+  (void)nb;
+}
+
+template <class T, int BM, int BN, int WM, int WN>
+void launch_major(const GemmArgs& g) {
+  const bool amaj = std::llabs(g.sAm) <= std::llabs(g.sAk);   // m is the faster index of A in memory
+  const bool bmaj = std::llabs(g.sBn) < std::llabs(g.sBk);    // n is the faster index of B in memory
+  if (amaj && bmaj) launch_cfg<T, BM, BN, WM, WN, true, true>(g);
+  else if (amaj && !bmaj) launch_cfg<T, BM, BN, WM, WN, true, false>(g);
+  else if (!amaj && bmaj) launch_cfg<T, BM, BN, WM, WN, false, true>(g);
+  else launch_cfg<T, BM, BN, WM, WN, false, false>(g);
+}
+
+template <class T> struct Tiles;
+template <> struct Tiles<double> {
+  static void big(const GemmArgs& g) { launch_major<double, 128, 128, 64, 32>(g); }
+  static void small(const GemmArgs& g) { launch_major<double, 64, 64, 32, 16>(g); }
+  static constexpr int BIGM = 128, BIGN = 128;
+};
+template <> struct Tiles<zc> {
+  static void big(const GemmArgs& g) { launch_major<zc, 64, 128, 32, 32>(g); }
+  static void small(const GemmArgs& g) { launch_major<zc, 64, 64, 32, 16>(g); }
+  static constexpr int BIGM = 64, BIGN = 128;
+};
+
+}  // namespace
+
+template <class T>
+void gemm(const GemmArgs& g) {
+  if (g.M <= 0 || g.N <= 0 || g.batch1 <= 0 || g.batch2 <= 0) return;
+  const int64_t ctas_big = (int64_t)((g.M + Tiles<T>::BIGM - 1) / Tiles<T>::BIGM) *
+                           ((g.N + Tiles<T>::BIGN - 1) / Tiles<T>::BIGN) * g.batch1 * g.batch2;
+  const bool big = g.M >= (Tiles<T>::BIGM * 3) / 4 && g.N >= (Tiles<T>::BIGN * 3) / 4 &&
+                   ctas_big >= (int64_t)(ctx().sm_count * 3) / 4;
+  if (big) Tiles<T>::big(g);
+  else Tiles<T>::small(g);
+}
+
+template void gemm<double>(const GemmArgs&);
+template void gemm<zc>(const GemmArgs&);
+
+double gemm_flops(const GemmArgs& g, bool cplx) {
+  return (cplx ? 8.0 : 2.0) * (double)g.M * (double)g.N * (double)g.K * (double)g.batch1 * (double)g.batch2;
+}
+
+}  // namespace ttn

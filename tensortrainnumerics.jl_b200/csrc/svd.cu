@@ -1,0 +1,79 @@
+// Left singular vectors + singular values of a bond-sized matrix: Householder QR preconditioning followed
+// by one-sided Jacobi on the square triangular factor (SURVEY.md §7.3 "SVD accuracy vs speed").
+//
+//   p <= q (wide / square):  Theta^H = Q~ R   ->  L = R^H (p x p);  Jacobi on the columns of L:  L V = U Sigma
+//   p >  q (tall)         :  Theta   = Q  R   ->  Jacobi on the columns of R: R V = U_R Sigma;  U Sigma = Q [U_R Sigma; 0]
+//
+// Only U·Sigma (orthogonal columns, unsorted) and the sorted singular values are produced; callers obtain the
+// other factor by projection (Sigma·V^H = U^H·Theta, a DMMA GEMM), which is exact for any orthonormal U and needs
+// neither V accumulation nor a division by small singular values.
+#include "ttn_internal.h"
+
+namespace ttn {
+
+template <class T>
+void svd_left(const T* Theta, int p, int q, int64_t rs, int64_t cs, bool conj, SvdLeft& out, int batch, int64_t bT) {
+  ttn_assert(p > 0 && q > 0 && batch > 0, 2, "svd_left: empty matrix");
+  const int k = std::min(p, q);
+  out.p = p; out.q = q; out.k = k;
+  out.norms.alloc(sizeof(double) * (size_t)k * batch);
+  out.X.alloc(sizeof(T) * (size_t)p * k * batch);
+  T* X = out.X.as<T>();
+  const int64_t bX = (int64_t)p * k;
+
+  if (p == q) {
+    Copy4 c; c.n0 = p; c.n1 = q; c.n2 = batch; c.s0 = rs; c.s1 = cs; c.s2 = bT; c.d0 = 1; c.d1 = p; c.d2 = bX; c.conj = conj;
+    copy4<T>(Theta, X, c);
+    out.sweeps = jacobi_orth<T>(X, p, p, p, out.norms.as<double>(), batch, bX, k);
+  } else if (p < q) {
+    // W (q x p) = Theta_eff^H
+    DevBuf W(sizeof(T) * (size_t)q * p * batch), tau(sizeof(T) * (size_t)p * batch);
+    const int64_t bW = (int64_t)q * p;
+    Copy4 c; c.n0 = q; c.n1 = p; c.n2 = batch; c.s0 = cs; c.s1 = rs; c.s2 = bT; c.d0 = 1; c.d1 = q; c.d2 = bW; c.conj = !conj;
+    copy4<T>(Theta, W.as<T>(), c);
+    qr_factor<T>(W.as<T>(), q, p, q, tau.as<T>(), batch, bW, p);
+    // X = R^H (lower triangular p x p): X[i,j] = conj(R[j,i]), j <= i
+    Copy4 t; t.n0 = p; t.n1 = p; t.n2 = batch; t.s0 = 1; t.s1 = q; t.s2 = bW; t.d0 = p; t.d1 = 1; t.d2 = bX; t.conj = true; t.tri = 1;
+    copy4<T>(W.as<T>(), X, t);
+    out.sweeps = jacobi_orth<T>(X, p, p, p, out.norms.as<double>(), batch, bX, k);
+  } else {
+    DevBuf W(sizeof(T) * (size_t)p * q * batch), tau(sizeof(T) * (size_t)q * batch);
+    const int64_t bW = (int64_t)p * q;
+    Copy4 c; c.n0 = p; c.n1 = q; c.n2 = batch; c.s0 = rs; c.s1 = cs; c.s2 = bT; c.d0 = 1; c.d1 = p; c.d2 = bW; c.conj = conj;
+    copy4<T>(Theta, W.as<T>(), c);
+    qr_factor<T>(W.as<T>(), p, q, p, tau.as<T>(), batch, bW, q);
+    // Xr (q x q) = R
+    DevBuf Xr(sizeof(T) * (size_t)q * q * batch);
+    const int64_t bR = (int64_t)q * q;
+    Copy4 t; t.n0 = q; t.n1 = q; t.n2 = batch; t.s0 = 1; t.s1 = p; t.s2 = bW; t.d0 = 1; t.d1 = q; t.d2 = bR; t.tri = 1;
+    copy4<T>(W.as<T>(), Xr.as<T>(), t);
+    out.sweeps = jacobi_orth<T>(Xr.as<T>(), q, q, q, out.norms.as<double>(), batch, bR, k);
+    // X = Q [Xr; 0]
+    fill<T>(X, (int64_t)p * q * batch, t_zero<T>());
+    Copy4 u; u.n0 = q; u.n1 = q; u.n2 = batch; u.s0 = 1; u.s1 = q; u.s2 = bR; u.d0 = 1; u.d1 = p; u.d2 = bX;
+    copy4<T>(Xr.as<T>(), X, u);
+    qr_apply<T>(W.as<T>(), p, q, p, tau.as<T>(), X, q, p, false, batch, bW, q, bX);
+  }
+
+  // singular values to the host, sorted descending per batch element
+  std::vector<double> h((size_t)k * batch);
+  TTN_CUDA(cudaMemcpyAsync(h.data(), out.norms.p, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, ctx().stream));
+  TTN_CUDA(cudaStreamSynchronize(ctx().stream));
+  out.sigma.resize(h.size());
+  out.perm.resize(h.size());
+  std::vector<int> idx(k);
+  for (int b = 0; b < batch; ++b) {
+    const double* hb = h.data() + (size_t)b * k;
+    for (int j = 0; j < k; ++j) idx[j] = j;
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int c2) { return hb[a] > hb[c2]; });
+    for (int j = 0; j < k; ++j) {
+      out.perm[(size_t)b * k + j] = idx[j];
+      out.sigma[(size_t)b * k + j] = hb[idx[j]];
+    }
+  }
+}
+
+template void svd_left<double>(const double*, int, int, int64_t, int64_t, bool, SvdLeft&, int, int64_t);
+template void svd_left<zc>(const zc*, int, int, int64_t, int64_t, bool, SvdLeft&, int, int64_t);
+
+}  // namespace ttn

@@ -1,0 +1,347 @@
+// TT-level operations on device-resident trains: apply, dot, +, scalar *, orthogonalize, tt_compress!.
+// Each function cites the reference lines it reproduces; the arithmetic is carried by the kernels in
+// gemm.cu / apply.cu / qr.cu / jacobi.cu / elementwise.cu, the host code here only sequences launches.
+#include "tt.h"
+
+namespace ttn {
+
+template <class T>
+void tt_copy(const TT<T>& x, TT<T>& y) {
+  y.d = x.d; y.batch = x.batch; y.dims = x.dims; y.rks = x.rks; y.ot = x.ot;
+  y.cores.clear();
+  y.cores.resize(x.d);
+  for (int k = 0; k < x.d; ++k) {
+    y.alloc_core(k);
+    TTN_CUDA(cudaMemcpyAsync(y.cores[k].p, x.cores[k].p, y.cores[k].bytes, cudaMemcpyDeviceToDevice, ctx().stream));
+  }
+}
+
+// src/tt_operations.jl:101-111
+template <class T>
+void tt_apply(const TTO<T>& A, const TT<T>& x, TT<T>& y) {
+  ttn_assert(A.d == x.d && A.dims == x.dims, 1, "Incompatible dimensions");
+  y.d = x.d; y.batch = x.batch; y.dims = x.dims;
+  y.rks.resize(x.d + 1);
+  for (int k = 0; k <= x.d; ++k) y.rks[k] = A.rks[k] * x.rks[k];
+  y.ot.assign(x.d, 0);
+  y.cores.clear();
+  y.cores.resize(x.d);
+  for (int k = 0; k < x.d; ++k) {
+    y.alloc_core(k);
+    apply_core<T>(A.core(k), x.core(k), y.core(k), (int)A.dims[k], (int)A.dims[k], (int)A.rks[k], (int)A.rks[k + 1],
+                  (int)x.rks[k], (int)x.rks[k + 1], x.batch, x.core_elems(k), y.core_elems(k));
+  }
+}
+
+// src/tt_operations.jl:239-250:  M <- A_k^H (B_k M), conj on the first argument
+template <class T>
+void tt_dot(const TT<T>& A, const TT<T>& B, std::vector<T>& out) {
+  ttn_assert(A.d == B.d && A.dims == B.dims && A.batch == B.batch, 1, "TT dimensions are not compatible");
+  const int batch = A.batch;
+  DevBuf M(sizeof(T) * (size_t)A.rks[0] * B.rks[0] * batch);
+  ttn_assert(A.rks[0] == 1 && B.rks[0] == 1, 1, "dot: boundary ranks must be 1");
+  fill<T>(M.as<T>(), batch, t_one<T>());
+  for (int k = 0; k < A.d; ++k) {
+    const int n = (int)A.dims[k];
+    const int ral = (int)A.rks[k], rar = (int)A.rks[k + 1], rbl = (int)B.rks[k], rbr = (int)B.rks[k + 1];
+    DevBuf Tb(sizeof(T) * (size_t)n * ral * rbr * batch);
+    GemmArgs g;  // T[z,alpha,b] = sum_beta M[alpha,beta] B[z,beta,b]
+    g.M = ral; g.N = rbr; g.K = rbl;
+    g.A = M.p; g.sAm = 1; g.sAk = ral; g.bA1 = 0; g.bA2 = (int64_t)ral * rbl;
+    g.B = B.cores[k].p; g.sBk = n; g.sBn = (int64_t)n * rbl; g.bB1 = 1; g.bB2 = B.core_elems(k);
+    g.C = Tb.p; g.sCm = n; g.sCn = (int64_t)n * ral; g.bC1 = 1; g.bC2 = (int64_t)n * ral * rbr;
+    g.batch1 = n; g.batch2 = batch;
+    gemm<T>(g);
+    DevBuf Mn(sizeof(T) * (size_t)rar * rbr * batch);
+    GemmArgs h;  // M'[a,b] = sum_(z,alpha) conj(A[(z,alpha),a]) T[(z,alpha),b]
+    h.M = rar; h.N = rbr; h.K = n * ral;
+    h.A = A.cores[k].p; h.sAm = (int64_t)n * ral; h.sAk = 1; h.conjA = true; h.bA2 = A.core_elems(k);
+    h.B = Tb.p; h.sBk = 1; h.sBn = (int64_t)n * ral; h.bB2 = (int64_t)n * ral * rbr;
+    h.C = Mn.p; h.sCm = 1; h.sCn = rar; h.bC2 = (int64_t)rar * rbr;
+    h.batch1 = 1; h.batch2 = batch;
+    gemm<T>(h);
+    M = std::move(Mn);
+  }
+  ttn_assert(A.rks[A.d] == 1 && B.rks[B.d] == 1, 1, "dot: boundary ranks must be 1");
+  out.resize(batch);
+  TTN_CUDA(cudaMemcpyAsync(out.data(), M.p, sizeof(T) * batch, cudaMemcpyDeviceToHost, ctx().stream));
+  TTN_CUDA(cudaStreamSynchronize(ctx().stream));
+}
+
+// src/tt_operations.jl:10-35 (block-diagonal concatenation)
+template <class T>
+void tt_add(const TT<T>& x, const TT<T>& y, TT<T>& z) {
+  ttn_assert(x.d == y.d && x.dims == y.dims && x.batch == y.batch, 1, "Incompatible dimensions");
+  const int d = x.d, batch = x.batch;
+  z.d = d; z.batch = batch; z.dims = x.dims; z.ot.assign(d, 0);
+  z.rks.resize(d + 1);
+  for (int k = 0; k <= d; ++k) z.rks[k] = x.rks[k] + y.rks[k];
+  z.rks[0] = 1; z.rks[d] = 1;
+  z.cores.clear();
+  z.cores.resize(d);
+  for (int k = 0; k < d; ++k) {
+    z.alloc_core(k);
+    const int64_t n = x.dims[k], zl = z.rks[k], zr = z.rks[k + 1];
+    if (d == 1) {
+      TTN_CUDA(cudaMemcpyAsync(z.cores[k].p, x.cores[k].p, z.cores[k].bytes, cudaMemcpyDeviceToDevice, ctx().stream));
+      axpy<T>(z.core_elems(k) * batch, t_one<T>(), y.core(k), z.core(k));
+      continue;
+    }
+    fill<T>(z.core(k), z.core_elems(k) * batch, t_zero<T>());
+    for (int which = 0; which < 2; ++which) {
+      const TT<T>& s = which == 0 ? x : y;
+      const int64_t sl = s.rks[k], sr = s.rks[k + 1];
+      const int64_t offl = (which == 1 && k > 0) ? x.rks[k] : 0;
+      const int64_t offr = (which == 1 && k < d - 1) ? x.rks[k + 1] : 0;
+      Copy4 c;
+      c.n0 = n * sl; c.n1 = sr; c.n2 = batch;                 // (s,alpha) fused is contiguous in the source
+      c.s0 = 1; c.s1 = n * sl; c.s2 = s.core_elems(k);
+      c.d0 = 1; c.d1 = n * zl; c.d2 = z.core_elems(k);
+      // destination offset: rows start at alpha = offl, columns at beta = offr; the fused (s,alpha) index is only
+      // contiguous when zl == sl, so copy per physical index otherwise
+      if (zl == sl) {
+        copy4<T>(s.core(k), z.core(k) + n * offl + n * zl * offr, c);
+      } else {
+        Copy4 e;
+        e.n0 = n; e.n1 = sl; e.n2 = sr; e.n3 = batch;
+        e.s0 = 1; e.s1 = n; e.s2 = n * sl; e.s3 = s.core_elems(k);
+        e.d0 = 1; e.d1 = n; e.d2 = n * zl; e.d3 = z.core_elems(k);
+        copy4<T>(s.core(k), z.core(k) + n * offl + n * zl * offr, e);
+      }
+    }
+    (void)zr;
+  }
+}
+
+// src/tt_operations.jl:256-266: scales the first core whose ot flag is 0 (core 1 if there is none)
+template <class T>
+void tt_scale(const TT<T>& x, T a, TT<T>& y) {
+  tt_copy(x, y);
+  if (t_abs2(a) == 0.0) {
+    for (int k = 0; k < y.d; ++k) fill<T>(y.core(k), y.core_elems(k) * y.batch, t_zero<T>());
+    y.ot.assign(y.d, 0);
+    return;
+  }
+  int i = 0;
+  for (int k = 0; k < x.d; ++k)
+    if (x.ot[k] == 0) { i = k; break; }
+  scal<T>(y.core_elems(i) * y.batch, a, y.core(i));
+}
+
+// src/tt_tools.jl:511-543
+template <class T>
+void tt_orthogonalize(const TT<T>& x, int center, TT<T>& y) {
+  const int d = x.d, batch = x.batch;
+  ttn_assert(1 <= center && center <= d, 3, "Impossible orthogonalization");
+  ttn_assert(x.rks[0] == 1 && x.rks[d] == 1, 1, "orthogonalize: boundary ranks must be 1");
+  y.d = d; y.batch = batch; y.dims = x.dims; y.rks = x.rks; y.ot.assign(d, 0);
+  y.cores.clear();
+  y.cores.resize(d);
+  const int ci = center - 1;
+
+  // left sweep: QR of (r_{j-1} n) x r_j with row index alpha + r_{j-1} s   (tt_tools.jl:518-525)
+  DevBuf FR(sizeof(T) * batch);
+  fill<T>(FR.as<T>(), batch, t_one<T>());
+  int fr_rows = 1;  // FR is (fr_rows x x.rks[j]) per batch element, ld = fr_rows
+  for (int j = 0; j < ci; ++j) {
+    const int n = (int)x.dims[j], xl = (int)x.rks[j], xr = (int)x.rks[j + 1], yl = fr_rows;
+    const int m = yl * n, k = std::min(m, xr);
+    DevBuf W(sizeof(T) * (size_t)m * xr * batch), tau(sizeof(T) * (size_t)k * batch);
+    GemmArgs g;  // W[(alpha,s), gamma] = sum_beta FR[alpha,beta] x[s,beta,gamma]
+    g.M = yl; g.N = xr; g.K = xl;
+    g.A = FR.p; g.sAm = 1; g.sAk = yl; g.bA1 = 0; g.bA2 = (int64_t)yl * xl;
+    g.B = x.cores[j].p; g.sBk = n; g.sBn = (int64_t)n * xl; g.bB1 = 1; g.bB2 = x.core_elems(j);
+    g.C = W.p; g.sCm = 1; g.sCn = m; g.bC1 = yl; g.bC2 = (int64_t)m * xr;
+    g.batch1 = n; g.batch2 = batch;
+    gemm<T>(g);
+    qr_factor<T>(W.as<T>(), m, xr, m, tau.as<T>(), batch, (int64_t)m * xr, k);
+    DevBuf Q(sizeof(T) * (size_t)m * k * batch);
+    qr_form_q<T>(W.as<T>(), m, k, m, tau.as<T>(), Q.as<T>(), m, batch, (int64_t)m * xr, k, (int64_t)m * k);
+    y.rks[j] = yl; y.rks[j + 1] = k; y.ot[j] = 1;
+    y.alloc_core(j);
+    Copy4 c;  // y[s,alpha,kappa] = Q[alpha + yl*s, kappa]
+    c.n0 = yl; c.n1 = n; c.n2 = k; c.n3 = batch;
+    c.s0 = 1; c.s1 = yl; c.s2 = m; c.s3 = (int64_t)m * k;
+    c.d0 = n; c.d1 = 1; c.d2 = (int64_t)n * yl; c.d3 = y.core_elems(j);
+    copy4<T>(Q.as<T>(), y.core(j), c);
+    DevBuf FRn(sizeof(T) * (size_t)k * xr * batch);
+    Copy4 t;  // FR = R[1:k, :]
+    t.n0 = k; t.n1 = xr; t.n2 = batch; t.s0 = 1; t.s1 = m; t.s2 = (int64_t)m * xr; t.d0 = 1; t.d1 = k; t.d2 = (int64_t)k * xr;
+    t.tri = 1;
+    copy4<T>(W.as<T>(), FRn.as<T>(), t);
+    FR = std::move(FRn);
+    fr_rows = k;
+  }
+
+  // right sweep: LQ of r_{j-1} x (r_j n) with column index beta + r_j s  (tt_tools.jl:528-536), done as the QR of
+  // the conjugate transpose
+  DevBuf FL(sizeof(T) * batch);
+  fill<T>(FL.as<T>(), batch, t_one<T>());
+  int fl_cols = 1;  // FL is (x.rks[j+1] x fl_cols) per batch element, ld = x.rks[j+1]
+  for (int j = d - 1; j > ci; --j) {
+    const int n = (int)x.dims[j], xl = (int)x.rks[j], xr = (int)x.rks[j + 1], yr = fl_cols;
+    const int m = yr * n, k = std::min(m, xl);
+    DevBuf W(sizeof(T) * (size_t)m * xl * batch), tau(sizeof(T) * (size_t)k * batch);
+    GemmArgs g;  // W[(beta,s), alpha] = conj( sum_gamma x[s,alpha,gamma] FL[gamma,beta] )
+    g.M = yr; g.N = xl; g.K = xr;
+    g.A = FL.p; g.sAm = xr; g.sAk = 1; g.conjA = true; g.bA1 = 0; g.bA2 = (int64_t)xr * yr;
+    g.B = x.cores[j].p; g.sBk = (int64_t)n * xl; g.sBn = n; g.conjB = true; g.bB1 = 1; g.bB2 = x.core_elems(j);
+    g.C = W.p; g.sCm = 1; g.sCn = m; g.bC1 = yr; g.bC2 = (int64_t)m * xl;
+    g.batch1 = n; g.batch2 = batch;
+    gemm<T>(g);
+    qr_factor<T>(W.as<T>(), m, xl, m, tau.as<T>(), batch, (int64_t)m * xl, k);
+    DevBuf Q(sizeof(T) * (size_t)m * k * batch);
+    qr_form_q<T>(W.as<T>(), m, k, m, tau.as<T>(), Q.as<T>(), m, batch, (int64_t)m * xl, k, (int64_t)m * k);
+    y.rks[j] = k; y.rks[j + 1] = yr; y.ot[j] = -1;
+    y.alloc_core(j);
+    Copy4 c;  // y[s,kappa,beta] = conj(Q[beta + yr*s, kappa])
+    c.n0 = yr; c.n1 = n; c.n2 = k; c.n3 = batch;
+    c.s0 = 1; c.s1 = yr; c.s2 = m; c.s3 = (int64_t)m * k;
+    c.d0 = (int64_t)n * k; c.d1 = 1; c.d2 = n; c.d3 = y.core_elems(j);
+    c.conj = true;
+    copy4<T>(Q.as<T>(), y.core(j), c);
+    DevBuf FLn(sizeof(T) * (size_t)xl * k * batch);
+    Copy4 t;  // FL[alpha,kappa] = conj(R[kappa,alpha]), kappa <= alpha
+    t.n0 = k; t.n1 = xl; t.n2 = batch; t.s0 = 1; t.s1 = m; t.s2 = (int64_t)m * xl; t.d0 = xl; t.d1 = 1; t.d2 = (int64_t)xl * k;
+    t.tri = 1; t.conj = true;
+    copy4<T>(W.as<T>(), FLn.as<T>(), t);
+    FL = std::move(FLn);
+    fl_cols = k;
+  }
+
+  // centre core: y[s,:,:] = FR x[s,:,:] FL  (tt_tools.jl:538-541)
+  {
+    const int n = (int)x.dims[ci], xl = (int)x.rks[ci], xr = (int)x.rks[ci + 1], yl = fr_rows, yr = fl_cols;
+    DevBuf Tmp(sizeof(T) * (size_t)n * yl * xr * batch);
+    GemmArgs g;  // Tmp[s,alpha,gamma] = sum_beta FR[alpha,beta] x[s,beta,gamma]
+    g.M = yl; g.N = xr; g.K = xl;
+    g.A = FR.p; g.sAm = 1; g.sAk = yl; g.bA2 = (int64_t)yl * xl;
+    g.B = x.cores[ci].p; g.sBk = n; g.sBn = (int64_t)n * xl; g.bB1 = 1; g.bB2 = x.core_elems(ci);
+    g.C = Tmp.p; g.sCm = n; g.sCn = (int64_t)n * yl; g.bC1 = 1; g.bC2 = (int64_t)n * yl * xr;
+    g.batch1 = n; g.batch2 = batch;
+    gemm<T>(g);
+    y.rks[ci] = yl; y.rks[ci + 1] = yr; y.ot[ci] = 0;
+    y.alloc_core(ci);
+    GemmArgs h;  // y[(s,alpha), beta'] = sum_gamma Tmp[(s,alpha),gamma] FL[gamma,beta']
+    h.M = n * yl; h.N = yr; h.K = xr;
+    h.A = Tmp.p; h.sAm = 1; h.sAk = (int64_t)n * yl; h.bA2 = (int64_t)n * yl * xr;
+    h.B = FL.p; h.sBk = 1; h.sBn = xr; h.bB2 = (int64_t)xr * yr;
+    h.C = y.cores[ci].p; h.sCm = 1; h.sCn = (int64_t)n * yl; h.bC2 = y.core_elems(ci);
+    h.batch1 = 1; h.batch2 = batch;
+    gemm<T>(h);
+  }
+}
+
+int rank_tailnorm(const double* s, int len, int64_t max_bond, double truncerr) {
+  int r = len;
+  if (truncerr > 0) {
+    double n2 = 0.0;
+    for (int i = 0; i < len; ++i) n2 += s[i] * s[i];
+    const double nrm = std::sqrt(n2);
+    double cum = 0.0;
+    for (int i = len; i >= 1; --i) {
+      cum += s[i - 1] * s[i - 1];
+      if (std::sqrt(cum) > truncerr * nrm) { r = i; break; }
+    }
+  }
+  if ((int64_t)r > max_bond) r = (int)max_bond;
+  return r;
+}
+
+// src/tt_tools.jl:743-768 (without the discarded orthogonalize of :769)
+template <class T>
+void tt_bond_truncate(TT<T>& x, int k1, int64_t max_bond, double truncerr, double* sigma_out, int64_t sigma_cap) {
+  ttn_assert(1 <= k1 && k1 < x.d, 2, "k must be in 1:(N-1)");
+  ttn_assert(max_bond >= 1, 2, "max_bond must be >= 1");
+  const int k = k1 - 1, batch = x.batch;
+  ttn_assert(batch == 1 || truncerr == 0.0, 2, "batched tt_compress needs truncerr == 0 (uniform ranks)");
+  const int n1 = (int)x.dims[k], n2 = (int)x.dims[k + 1];
+  const int rl = (int)x.rks[k], r = (int)x.rks[k + 1], rr = (int)x.rks[k + 2];
+  const int p = n1 * rl, q = n2 * rr;
+  DevBuf Theta(sizeof(T) * (size_t)p * q * batch);
+  {
+    GemmArgs g;  // Theta[(s1,alpha),(s2,beta)] = sum_gamma A[s1,alpha,gamma] B[s2,gamma,beta]     (tt_tools.jl:749)
+    g.M = p; g.N = rr; g.K = r;
+    g.A = x.cores[k].p; g.sAm = 1; g.sAk = p; g.bA1 = 0; g.bA2 = x.core_elems(k);
+    g.B = x.cores[k + 1].p; g.sBk = n2; g.sBn = (int64_t)n2 * r; g.bB1 = 1; g.bB2 = x.core_elems(k + 1);
+    g.C = Theta.p; g.sCm = 1; g.sCn = (int64_t)p * n2; g.bC1 = p; g.bC2 = (int64_t)p * q;
+    g.batch1 = n2; g.batch2 = batch;
+    gemm<T>(g);
+  }
+  SvdLeft sv;
+  svd_left<T>(Theta.as<T>(), p, q, 1, p, false, sv, batch, (int64_t)p * q);
+  const int kk = sv.k;
+  int rn;
+  if (batch == 1) rn = rank_tailnorm(sv.sigma.data(), kk, max_bond, truncerr);
+  else rn = (int)std::min<int64_t>(kk, max_bond);
+  if (rn < 1) rn = 1;
+  if (sigma_out) {
+    for (int64_t j = 0; j < sigma_cap; ++j) sigma_out[j] = j < rn ? sv.sigma[j] : 0.0;
+  }
+  // scales: core k <- U sqrt(S) = X_j sigma_j^{-1/2};  projection basis G2 = X_j sigma_j^{-3/2}  so that
+  // core k+1 <- sqrt(S) Vt = S^{-1/2} U^H Theta = G2^H Theta                                   (tt_tools.jl:754-757)
+  std::vector<double> s1((size_t)rn * batch), s2((size_t)rn * batch);
+  std::vector<int> perm((size_t)rn * batch);
+  for (int b = 0; b < batch; ++b) {
+    const double smax = sv.sigma[(size_t)b * kk];
+    for (int j = 0; j < rn; ++j) {
+      const double s = sv.sigma[(size_t)b * kk + j];
+      const bool ok = s > 1e-290 && s > smax * 1e-140;
+      s1[(size_t)b * rn + j] = ok ? 1.0 / std::sqrt(s) : 0.0;
+      s2[(size_t)b * rn + j] = ok ? 1.0 / (s * std::sqrt(s)) : 0.0;
+      perm[(size_t)b * rn + j] = sv.perm[(size_t)b * kk + j];
+    }
+  }
+  DevBuf dperm(sizeof(int) * perm.size()), ds1(sizeof(double) * s1.size()), ds2(sizeof(double) * s2.size());
+  TTN_CUDA(cudaMemcpyAsync(dperm.p, perm.data(), dperm.bytes, cudaMemcpyHostToDevice, ctx().stream));
+  TTN_CUDA(cudaMemcpyAsync(ds1.p, s1.data(), ds1.bytes, cudaMemcpyHostToDevice, ctx().stream));
+  TTN_CUDA(cudaMemcpyAsync(ds2.p, s2.data(), ds2.bytes, cudaMemcpyHostToDevice, ctx().stream));
+
+  DevBuf newA(sizeof(T) * (size_t)p * rn * batch), G2(sizeof(T) * (size_t)p * rn * batch);
+  gather_cols<T>(sv.X.as<T>(), p, p, dperm.as<int>(), ds1.as<double>(), rn, newA.as<T>(), 1, p, batch, (int64_t)p * kk, rn,
+                 (int64_t)p * rn);
+  gather_cols<T>(sv.X.as<T>(), p, p, dperm.as<int>(), ds2.as<double>(), rn, G2.as<T>(), 1, p, batch, (int64_t)p * kk, rn,
+                 (int64_t)p * rn);
+  DevBuf newB(sizeof(T) * (size_t)n2 * rn * rr * batch);
+  {
+    GemmArgs g;  // newB[s2,kappa,beta] = sum_row conj(G2[row,kappa]) Theta[row,(s2,beta)]
+    g.M = rn; g.N = rr; g.K = p;
+    g.A = G2.p; g.sAm = p; g.sAk = 1; g.conjA = true; g.bA1 = 0; g.bA2 = (int64_t)p * rn;
+    g.B = Theta.p; g.sBk = 1; g.sBn = (int64_t)p * n2; g.bB1 = p; g.bB2 = (int64_t)p * q;
+    g.C = newB.p; g.sCm = n2; g.sCn = (int64_t)n2 * rn; g.bC1 = 1; g.bC2 = (int64_t)n2 * rn * rr;
+    g.batch1 = n2; g.batch2 = batch;
+    gemm<T>(g);
+  }
+  TTN_CUDA(cudaStreamSynchronize(ctx().stream));
+  x.cores[k] = std::move(newA);
+  x.cores[k + 1] = std::move(newB);
+  x.rks[k + 1] = rn;
+}
+
+// src/tt_tools.jl:772-789
+template <class T>
+void tt_compress(TT<T>& x, int64_t max_bond, double truncerr, int sweeps, double* sigma_out, int64_t sigma_stride) {
+  ttn_assert(sweeps >= 1, 2, "sweeps must be >= 1");
+  int64_t step = 0;
+  for (int sw = 0; sw < sweeps; ++sw) {
+    for (int k = 1; k <= x.d - 1; ++k, ++step)
+      tt_bond_truncate<T>(x, k, max_bond, truncerr, sigma_out ? sigma_out + step * sigma_stride : nullptr, sigma_stride);
+    for (int k = x.d - 1; k >= 1; --k, ++step)
+      tt_bond_truncate<T>(x, k, max_bond, truncerr, sigma_out ? sigma_out + step * sigma_stride : nullptr, sigma_stride);
+  }
+}
+
+#define INST(T)                                                                                   \
+  template void tt_copy<T>(const TT<T>&, TT<T>&);                                                 \
+  template void tt_apply<T>(const TTO<T>&, const TT<T>&, TT<T>&);                                 \
+  template void tt_dot<T>(const TT<T>&, const TT<T>&, std::vector<T>&);                           \
+  template void tt_add<T>(const TT<T>&, const TT<T>&, TT<T>&);                                    \
+  template void tt_scale<T>(const TT<T>&, T, TT<T>&);                                             \
+  template void tt_orthogonalize<T>(const TT<T>&, int, TT<T>&);                                   \
+  template void tt_bond_truncate<T>(TT<T>&, int, int64_t, double, double*, int64_t);              \
+  template void tt_compress<T>(TT<T>&, int64_t, double, int, double*, int64_t);
+INST(double)
+INST(zc)
+#undef INST
+
+}  // namespace ttn

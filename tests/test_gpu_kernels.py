@@ -1,0 +1,155 @@
+"""GPU parity tests of the kernel-level entry points (through the C ABI) against NumPy / the oracle.
+Tolerances: relative 1e-12 for contractions, 1e-10 for singular values / reconstructions."""
+import numpy as np
+import pytest
+
+import ttn_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+
+def rnd(rng, shape, cplx):
+    a = rng.standard_normal(shape)
+    if cplx:
+        a = a + 1j * rng.standard_normal(shape)
+    return np.asfortranarray(a)
+
+
+def relerr(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("shape", [(1, 1, 1), (5, 3, 7), (64, 64, 16), (130, 70, 33), (200, 300, 129), (257, 129, 64), (20, 20, 1000)])
+def test_gemm_shapes(shape, cplx):
+    import ttn_b200 as t
+    M, N, K = shape
+    rng = np.random.default_rng(M * 7 + N * 3 + K)
+    A, B = rnd(rng, (M, K), cplx), rnd(rng, (K, N), cplx)
+    assert relerr(t.gemm_host(A, B), A @ B) < 1e-13
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_gemm_ops_alpha_beta(cplx):
+    import ttn_b200 as t
+    rng = np.random.default_rng(5)
+    M, N, K = 70, 45, 90
+    At, Bt, C0 = rnd(rng, (K, M), cplx), rnd(rng, (N, K), cplx), rnd(rng, (M, N), cplx)
+    got = t.gemm_host(At, Bt, transA=True, transB=True, conjA=True, conjB=False, alpha=0.5, beta=-2.0, C0=C0)
+    ref = 0.5 * (At.conj().T @ Bt.T) - 2.0 * C0
+    assert relerr(got, ref) < 1e-13
+    got = t.gemm_host(At, Bt, transA=True, transB=True, conjA=False, conjB=True)
+    assert relerr(got, At.T @ Bt.conj().T) < 1e-13
+
+
+def test_gemm_large_real_hits_big_tile():
+    import ttn_b200 as t
+    rng = np.random.default_rng(6)
+    A, B = rnd(rng, (1500, 700), False), rnd(rng, (700, 1300), False)
+    assert relerr(t.gemm_host(A, B), A @ B) < 1e-13
+    Ac, Bc = rnd(rng, (900, 300), True), rnd(rng, (300, 1300), True)
+    assert relerr(t.gemm_host(Ac, Bc), Ac @ Bc) < 1e-13
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("shape", [(1, 1), (7, 3), (3, 7), (40, 40), (100, 17), (300, 64), (64, 200), (1024, 96)])
+def test_qr(shape, cplx):
+    import ttn_b200 as t
+    m, n = shape
+    rng = np.random.default_rng(m + 13 * n)
+    A = rnd(rng, (m, n), cplx)
+    Q, R = t.qr_thin(A)
+    k = min(m, n)
+    assert Q.shape == (m, k) and R.shape == (k, n)
+    assert relerr(Q @ R, A) < 1e-13
+    assert np.abs(Q.conj().T @ Q - np.eye(k)).max() < 1e-13
+    assert np.abs(np.tril(R, -1)).max() == 0.0
+
+
+def test_qr_rank_deficient():
+    import ttn_b200 as t
+    rng = np.random.default_rng(3)
+    A = rnd(rng, (50, 4), False) @ rnd(rng, (4, 12), False)
+    A[:, 5] = 0.0
+    Q, R = t.qr_thin(np.asfortranarray(A))
+    assert relerr(Q @ R, A) < 1e-13
+    assert np.abs(Q.T @ Q - np.eye(12)).max() < 1e-12
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("shape", [(6, 4), (4, 6), (5, 5), (64, 64), (32, 200), (200, 32), (128, 128), (128, 1024), (300, 180)])
+def test_svdtrunc_full(shape, cplx):
+    import ttn_b200 as t
+    m, n = shape
+    rng = np.random.default_rng(m * 3 + n)
+    A = rnd(rng, (m, n), cplx)
+    U, s, Vt = t.svdtrunc(A)
+    sref = np.linalg.svd(A, compute_uv=False)
+    assert len(s) == min(m, n)
+    assert np.abs(s - sref).max() / sref[0] < 1e-13          # singular values
+    assert np.all(np.diff(s) <= 0)
+    assert relerr((U * s) @ Vt, A) < 1e-12                   # reconstruction
+    assert np.abs(U.conj().T @ U - np.eye(len(s))).max() < 1e-12
+    assert np.abs(Vt @ Vt.conj().T - np.eye(len(s))).max() < 1e-10
+
+
+def test_svdtrunc_rules_and_relative_accuracy():
+    # test/test_tdvp.jl:28-44 + Appendix B tail-norm rule; small singular values to high relative accuracy
+    import ttn_b200 as t
+    rng = np.random.default_rng(11)
+    A = rnd(rng, (6, 4), False)
+    U, s, Vt = t.svdtrunc(A, max_bond=2)
+    assert len(s) == 2 and np.allclose(s, np.linalg.svd(A, compute_uv=False)[:2], rtol=1e-12)
+    Q1, _ = np.linalg.qr(rng.standard_normal((40, 5)))
+    Q2, _ = np.linalg.qr(rng.standard_normal((30, 5)))
+    sv = np.array([1.0, 1e-3, 1e-6, 1e-9, 1e-12])
+    B = np.asfortranarray(Q1 @ np.diag(sv) @ Q2.T)
+    for te, want in [(1e-4, 2), (1e-7, 3), (0.5, 1), (1e-13, 5)]:
+        assert len(t.svdtrunc(B, truncerr=te)[1]) == len(o.svdtrunc(B, truncerr=te)[1]) == want
+    s5 = t.svdtrunc(B, max_bond=5)[1]
+    assert np.abs(s5[:4] / sv[:4] - 1).max() < 1e-6   # graded spectrum: relative accuracy far below eps*s_max
+    U1, s1, Vt1 = t.svdtrunc(B, max_bond=1)
+    assert U1.shape == (40, 1) and Vt1.shape == (1, 30)
+
+
+def test_svdtrunc_rank_deficient_and_zero():
+    import ttn_b200 as t
+    rng = np.random.default_rng(12)
+    A = np.asfortranarray(rnd(rng, (20, 3), False) @ rnd(rng, (3, 16), False))
+    U, s, Vt = t.svdtrunc(A)
+    assert relerr((U * s) @ Vt, A) < 1e-12
+    assert np.all(np.isfinite(U)) and np.all(np.isfinite(Vt))
+    Z = np.zeros((5, 4), order="F")
+    U, s, Vt = t.svdtrunc(Z)
+    assert np.all(s == 0) and np.all(np.isfinite(U)) and np.all(np.isfinite(Vt))
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("sym", [False, True])
+@pytest.mark.parametrize("dims", [(1, 1, 1, 1, 4), (3, 3, 8, 8, 4), (5, 5, 17, 9, 4), (2, 4, 33, 20, 2), (5, 5, 64, 64, 4)])
+def test_matvec2_vs_oracle(dims, sym, cplx):
+    # K_matfree of src/solvers/dmrg.jl:239-244
+    import ttn_b200 as t
+    wl, wr, cl, cr, nn = dims
+    rng = np.random.default_rng(sum(dims))
+    G, H = rnd(rng, (wl, cl, cl), cplx), rnd(rng, (wr, cr, cr), cplx)
+    Am, V = rnd(rng, (wl, nn, nn, wr), cplx), rnd(rng, (cl, nn, cr), cplx)
+    Y = t.matvec2(G, Am, H, V, symmetrize=sym)
+    assert relerr(Y, o.dmrg_matvec2(G, Am, V, H, symmetrize=sym)) < 1e-13
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_env_updates_vs_oracle(cplx):
+    # update_G! / update_H! of src/solvers/dmrg.jl:27-35
+    import ttn_b200 as t
+    rng = np.random.default_rng(21)
+    n, wl, wr, rl, rr = 2, 3, 4, 7, 5
+    x, A = rnd(rng, (n, rl, rr), cplx), rnd(rng, (n, n, wl, wr), cplx)
+    G, H = rnd(rng, (wl, rl, rl), cplx), rnd(rng, (wr, rr, rr), cplx)
+    assert relerr(t.env_left(G, x, A), o.dmrg_update_G(x, A, G)) < 1e-13
+    assert relerr(t.env_right(H, x, A), o.dmrg_update_H(x, A, H)) < 1e-13
+    n, wl, wr, rl, rr = 3, 5, 5, 40, 33
+    x, A = rnd(rng, (n, rl, rr), cplx), rnd(rng, (n, n, wl, wr), cplx)
+    G, H = rnd(rng, (wl, rl, rl), cplx), rnd(rng, (wr, rr, rr), cplx)
+    assert relerr(t.env_left(G, x, A), o.dmrg_update_G(x, A, G)) < 1e-13
+    assert relerr(t.env_right(H, x, A), o.dmrg_update_H(x, A, H)) < 1e-13

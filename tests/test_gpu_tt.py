@@ -1,0 +1,221 @@
+"""GPU parity tests of the TT-level hot path (apply, dot, +, orthogonalize, tt_compress!) against the oracle and the
+reference's own dense checks.  Gauge-invariant comparisons only (reconstructed tensors, singular values)."""
+import numpy as np
+import pytest
+
+import ttn_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+
+def dv(x):
+    return o.ttv_to_tensor(x).reshape(-1)
+
+
+def relerr(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128])
+def test_apply_vs_dense_and_oracle(dtype):
+    # test/test_tt_tools.jl:345-358 (1e-10), test/test_tt_operations.jl:116-136 (1e-12)
+    import ttn_b200 as t
+    rng = np.random.default_rng(2)
+    dims = (2, 3, 2, 2)
+    A = o.rand_tto(dims, 3, rng=rng, dtype=dtype)
+    x = o.rand_tt(dims, 4, rng=rng, dtype=dtype)
+    y = t.apply(A, x)
+    yo = o.apply(A, x)
+    assert y.ttv_rks == yo.ttv_rks
+    for a, b in zip(y.ttv_vec, yo.ttv_vec):
+        assert relerr(a, b) < 1e-14          # same fused-bond order (MPO index fastest), element by element
+    assert relerr(dv(y), o.tto_to_matrix(A) @ dv(x)) < 1e-12
+
+
+def test_apply_mixed_and_errors():
+    import ttn_b200 as t
+    rng = np.random.default_rng(3)
+    A = o.rand_tto((2, 2, 2), 2, rng=rng, dtype=np.complex128)
+    x = o.rand_tt((2, 2, 2), 2, rng=rng)
+    assert relerr(dv(t.apply(A, x)), o.tto_to_matrix(A) @ dv(x)) < 1e-12
+    with pytest.raises(AssertionError):
+        t.apply(o.rand_tto((2, 2), 2, rng=rng), x)      # tt_operations.jl:102 "Incompatible dimensions"
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128])
+def test_dot_norm_add_scale(dtype):
+    import ttn_b200 as t
+    rng = np.random.default_rng(4)
+    dims = (2, 2, 3, 2)
+    x = o.rand_tt(dims, 3, rng=rng, dtype=dtype)
+    y = o.rand_tt(dims, 2, rng=rng, dtype=dtype)
+    assert abs(t.dot(x, y) - np.vdot(dv(x), dv(y))) < 1e-12 * abs(np.vdot(dv(x), dv(y))) + 1e-13
+    assert abs(t.norm(x) - np.linalg.norm(dv(x))) < 1e-12 * np.linalg.norm(dv(x))
+    z = t.add(x, y)
+    assert z.ttv_rks == o.add(x, y).ttv_rks
+    assert relerr(dv(z), dv(x) + dv(y)) < 1e-13
+    assert relerr(dv(t.scale(2.5, x)), 2.5 * dv(x)) < 1e-14
+    assert relerr(dv(t.sub(x, y)), dv(x) - dv(y)) < 1e-13
+    x.ttv_ot = [1, 0, -1, -1]
+    s = t.scale(-3.0, x)
+    assert relerr(s.ttv_vec[1], -3.0 * x.ttv_vec[1]) < 1e-15 and relerr(s.ttv_vec[0], x.ttv_vec[0]) == 0
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128])
+@pytest.mark.parametrize("center", [1, 2, 3, 5])
+def test_orthogonalize(center, dtype):
+    # test/test_tt_tools.jl:981-1017 — reconstruction + orthonormality ≤ 1e-12, ot flags
+    import ttn_b200 as t
+    rng = np.random.default_rng(5)
+    dims = (2, 3, 2, 2, 2)
+    x = o.rand_tt(dims, 4, rng=rng, dtype=dtype)
+    y = t.orthogonalize(x, i=center)
+    yo = o.orthogonalize(x, i=center)
+    assert y.ttv_rks == yo.ttv_rks and y.ttv_ot == yo.ttv_ot
+    assert relerr(dv(y), dv(x)) < 1e-12
+    for j in range(1, center):
+        G = y.ttv_vec[j - 1]
+        M = np.reshape(np.transpose(G, (1, 0, 2)), (-1, G.shape[2]), order="F")
+        assert np.abs(M.conj().T @ M - np.eye(M.shape[1])).max() < 1e-12
+    for j in range(center + 1, len(dims) + 1):
+        G = y.ttv_vec[j - 1]
+        M = np.reshape(np.transpose(G, (1, 2, 0)), (G.shape[1], -1), order="F")
+        assert np.abs(M @ M.conj().T - np.eye(M.shape[0])).max() < 1e-12
+
+
+def test_orthogonalize_errors_and_overfull_ranks():
+    import ttn_b200 as t
+    x = o.rand_tt((2, 2, 2), 2)
+    with pytest.raises(ValueError):
+        t.orthogonalize(x, i=0)                       # tt_tools.jl:513 DimensionMismatch
+    with pytest.raises(ValueError):
+        t.orthogonalize(x, i=4)
+    rng = np.random.default_rng(6)
+    xo = o.rand_tt((2, 2, 2, 2), [1, 5, 7, 5, 1], rng=rng)   # over-full ranks shrink (tt_tools.jl:522,533)
+    y = t.orthogonalize(xo, i=2)
+    assert y.ttv_rks == o.orthogonalize(xo, i=2).ttv_rks
+    assert relerr(dv(y), dv(xo)) < 1e-12
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128])
+def test_tt_compress_vs_oracle(dtype):
+    import ttn_b200 as t
+    rng = np.random.default_rng(7)
+    x = o.rand_tt((2,) * 10, 16, rng=rng, dtype=dtype, normalise=True)
+    sig_ref = []
+    ref = o.tt_compress(o.copy_tt(x), 6, sigma_out=sig_ref)
+    xc = o.copy_tt(x)
+    got, sig = t.tt_compress_(xc, 6, return_sigma=True)
+    assert got is xc and got.ttv_rks == ref.ttv_rks
+    assert o.rel_distance(got, ref) < 1e-10                      # reconstructed tensor (TT distance)
+    assert relerr(dv(got), dv(ref)) < 1e-10
+    assert len(sig) == len(sig_ref)
+    for a, b in zip(sig, sig_ref):
+        assert len(a) == len(b) and np.abs(a - b).max() / b[0] < 1e-10   # retained singular values per bond step
+
+
+def test_tt_compress_behaviour_kats():
+    # test/test_tt_tools.jl:500-574 and :433-497
+    import ttn_b200 as t
+    rng = np.random.default_rng(8)
+    tt = o.rand_tt((2, 2, 2), [1, 2, 2, 1], rng=rng)
+    ref = dv(tt).copy()
+    before = list(tt.ttv_rks)
+    y = t.tt_compress_(tt, 10, sweeps=1)
+    assert y is tt and tt.ttv_rks == before and relerr(dv(tt), ref) < 1e-13
+    tt4 = o.rand_tt((2, 2, 2, 2), [1, 2, 4, 2, 1], rng=rng)
+    t.tt_compress_(tt4, 2)
+    assert max(tt4.ttv_rks) <= 2
+    for k in range(4):
+        assert tt4.ttv_vec[k].shape == (2, tt4.ttv_rks[k], tt4.ttv_rks[k + 1])
+    with pytest.raises(AssertionError):
+        t.tt_compress_(tt4, 2, sweeps=0)                # tt_tools.jl:773
+    # _tt_bond_truncate!: shapes, returned orthogonalised copy, exact rank-1, bad k
+    tb = o.TTvector(3, [rng.standard_normal((2, 1, 4)), rng.standard_normal((2, 4, 4)), rng.standard_normal((2, 4, 1))],
+                    (2, 2, 2), [1, 4, 4, 1], [0, 0, 0])
+    yb = t.tt_bond_truncate_(tb, 1, max_bond=2)
+    assert tb.ttv_rks[1] <= 2 and tb.ttv_vec[0].shape == (2, 1, tb.ttv_rks[1]) and tb.ttv_vec[1].shape == (2, tb.ttv_rks[1], 4)
+    assert yb.ttv_rks[1] == tb.ttv_rks[1] and relerr(dv(yb), dv(tb)) < 1e-12
+    u, v, p, q = np.array([1.2, -0.5]), np.array([0.7, 0.3]), np.array([2.0, 3.0]), np.array([4.0, 5.0])
+    t2 = o.TTvector(2, [np.einsum("s,g->sg", u, p).reshape(2, 1, 2), np.einsum("s,g->sg", v, q).reshape(2, 2, 1)],
+                    (2, 2), [1, 2, 1], [0, 0])
+    ref2 = dv(t2).copy()
+    t.tt_bond_truncate_(t2, 1, max_bond=1)
+    assert t2.ttv_rks[1] == 1 and relerr(dv(t2), ref2) < 1e-13
+    with pytest.raises(AssertionError):
+        t.tt_bond_truncate_(tb, 0)
+    with pytest.raises(AssertionError):
+        t.tt_bond_truncate_(tb, tb.N)
+
+
+def test_tt_compress_function_qtt_and_truncerr():
+    # test/test_qtt_multidim.jl:577-614 pattern; rank-deficient two-site blocks; tail-norm rule on device == oracle
+    import ttn_b200 as t
+    d = 10
+    s, c = o.qtt_sin(d, lam=1.0), o.qtt_cos(d, lam=2.0)
+    f = o.add(o.add(s, c), s)
+    ref = o.qtt_to_vector(f).copy()
+    g = o.add(o.add(s, c), s)
+    t.tt_compress_(f, 4)
+    assert max(f.ttv_rks) <= 4 and relerr(o.qtt_to_vector(f), ref) < 1e-11
+    go = o.tt_compress(o.add(o.add(s, c), s), 100, truncerr=1e-10)
+    t.tt_compress_(g, 100, truncerr=1e-10)
+    assert g.ttv_rks == go.ttv_rks
+    assert relerr(o.qtt_to_vector(g), ref) < 1e-9
+    rng = np.random.default_rng(9)
+    x = o.rand_tt((2,) * 9, 12, rng=rng, normalise=True)
+    for te in (1e-1, 1e-2, 1e-3):
+        a = o.tt_compress(o.copy_tt(x), 100, truncerr=te)
+        b = t.tt_compress_(o.copy_tt(x), 100, truncerr=te)
+        assert a.ttv_rks == b.ttv_rks and o.rel_distance(b, a) < 1e-10
+
+
+def test_rk4_like_apply_then_compress():
+    # test/test_euler.jl:269-298 — an RK4 stage is `A*x` followed by `tt_compress!`
+    import ttn_b200 as t
+    d = 8
+    A = o.laplace_dd(d)
+    x = o.qtt_sin(d, lam=1.0)
+    y = t.tt_compress_(t.apply(A, x), 4)
+    ref = o.tto_to_matrix(A) @ o.qtt_to_vector(x)
+    assert relerr(o.qtt_to_vector(y), ref) < 1e-10
+
+
+def test_batched_apply_compress_matches_single():
+    # cfg5 shape in miniature: a batch of independent ComplexF64 TTs through apply + tt_compress!
+    import ttn_b200 as t
+    rng = np.random.default_rng(10)
+    d, B = 8, 5
+    A = o.rand_tto((2,) * d, 3, rng=rng, dtype=np.complex128)
+    xs = [o.rand_tt((2,) * d, 4, rng=np.random.default_rng(100 + b), dtype=np.complex128, normalise=True) for b in range(B)]
+    dev = t.DeviceTT.upload(xs)
+    assert dev.batch == B
+    yb = t.tt_compress_(t.apply(A, dev), 6)
+    outs = yb.download()
+    nb = t.norm(yb)
+    for b in range(B):
+        ref = o.tt_compress(o.apply(A, xs[b]), 6)
+        assert outs[b].ttv_rks == ref.ttv_rks
+        assert o.rel_distance(outs[b], ref) < 1e-10
+        assert abs(nb[b] - o.norm(ref)) < 1e-10 * o.norm(ref)
+
+
+def test_cfg2_shape_property_checks():
+    # full-size cfg2 (d=40, rank 512 -> 64): size-independent properties instead of a dense oracle
+    import ttn_b200 as t
+    rng = np.random.default_rng(1)
+    d = 40
+    x = o.rand_tt((2,) * d, 512, rng=rng, normalise=True)
+    xd = t.DeviceTT.upload(x)
+    n0 = t.norm(xd)
+    yd = t.tt_compress_(xd.copy(), 64)
+    assert max(yd.ttv_rks) == 64
+    # idempotence: compressing again at the same bond changes nothing beyond rounding
+    zd = t.tt_compress_(yd.copy(), 64)
+    assert t.norm(t.sub(zd, yd)) / t.norm(yd) < 1e-10
+    # projection property: <x, y> = <y, y> up to the truncation being (quasi-)optimal; error norm consistent
+    err = t.norm(t.sub(xd, yd)) / n0
+    assert 0.0 < err < 1.0
+    # agreement with the CPU oracle on the same input (TT distance, 1e-10)
+    ref = o.tt_compress(o.copy_tt(x), 64)
+    assert o.rel_distance(yd.download(), ref) < 1e-10
