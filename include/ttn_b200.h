@@ -56,6 +56,11 @@ int ttn_synchronize(void);
 long long ttn_launch_count(void);         /* kernels launched by the library since ttn_reset_launch_count */
 int ttn_reset_launch_count(void);
 void* ttn_stream(void);                   /* cudaStream_t the library launches on (for event timing) */
+/* per-kernel-family CUDA-event timing on the library stream (bench.py's roofline pass; adds two event records per launch).
+ * families: 0 gemm, 1 copy/permute, 2 apply, 3 qr panel, 4 qr reflector apply, 5 jacobi, 6 reductions/axpy, 7 gather/norms */
+#define TTN_NFAMILIES 8
+int ttn_profile(int enable);              /* clears the records and switches profiling on/off */
+int ttn_profile_read(double* ms /* 8 */, long long* counts /* 8 */);
 
 /* ---- containers -------------------------------------------------------------------------------------- */
 /* TTvector(N, ttv_vec, ttv_dims, ttv_rks, ttv_ot): rks has d+1 entries, ot d entries (may be NULL = zeros).

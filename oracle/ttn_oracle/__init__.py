@@ -24,7 +24,7 @@ from .generators import (toeplitz_to_qtto, laplace_dd, id_tto, heisenberg_xyz_tt
                          qtt_to_vector, tto_add, tto_scale, laplace2d_interleaved, qtt_sin2d_interleaved,
                          shift_op)
 from .ops import (apply, add, scale, sub, dot, norm, orthogonalize, svdtrunc, svdtrunc_abs,
-                  tt_bond_truncate, tt_compress, euclidean_distance, rel_distance)
+                  tt_bond_truncate, tt_compress, euclidean_distance, rel_distance, norm_stable)
 from .als import als_linsolve, als_eigsolve
 from .mals import mals_linsolve, mals_eigsolve, sv_trunc
 from .dmrg import dmrg_linsolve, dmrg_eigsolve, cut_off_index, dmrg_matvec2, dmrg_update_G, dmrg_update_H, amid

@@ -87,10 +87,17 @@ def euclidean_distance(a: TTvector, b: TTvector) -> float:
     return float(np.sqrt(max(v, 0.0)))
 
 
+def norm_stable(z: TTvector) -> float:
+    """‖z‖ via a right-to-left orthogonalisation sweep: backward stable (error ~ eps·Σ‖terms‖), unlike
+    sqrt(dot(z, z)) of a difference TT, which cancels and bottoms out at sqrt(eps)."""
+    y = orthogonalize(z, i=1)
+    return float(np.linalg.norm(y.ttv_vec[0]))
+
+
 def rel_distance(a: TTvector, b: TTvector) -> float:
-    """‖a-b‖/‖b‖ computed on the (un-rounded) difference TT so that cancellation does not limit it
-    to sqrt(eps) the way the expanded form of euclidean_distance does."""
-    return norm(sub(a, b)) / max(norm(b), np.finfo(float).tiny)
+    """‖a-b‖/‖b‖ on the (un-rounded) difference TT, evaluated with `norm_stable` so that it resolves down to
+    machine precision (the expanded form of euclidean_distance is limited to sqrt(eps) by cancellation)."""
+    return norm_stable(sub(a, b)) / max(norm(b), np.finfo(float).tiny)
 
 
 def orthogonalize(x: TTvector, i: int = 1) -> TTvector:

@@ -31,7 +31,8 @@ __all__ = [
     "TTvector", "TToperator", "DeviceTT", "DeviceTTO", "apply", "dot", "norm", "add", "scale", "sub",
     "orthogonalize", "tt_compress_", "tt_bond_truncate_", "als_linsolve", "als_eigsolve", "mals_linsolve",
     "mals_eigsolve", "dmrg_linsolve", "dmrg_eigsolve", "tdvp", "tdvp2", "matvec2", "env_left", "env_right",
-    "svdtrunc", "qr_thin", "gemm_host", "launch_count", "reset_launch_count", "synchronize", "library_path",
+    "svdtrunc", "qr_thin", "gemm_host", "launch_count", "reset_launch_count", "synchronize", "library_path", "profile", "profile_read", "stream_handle",
+    "KERNEL_FAMILIES",
 ]
 
 
@@ -49,6 +50,26 @@ def reset_launch_count():
 
 def synchronize():
     check(_lib.lib().ttn_synchronize())
+
+
+KERNEL_FAMILIES = ("gemm", "copy", "apply", "qr_panel", "qr_apply", "jacobi", "reduce", "gather")
+
+
+def profile(enable: bool):
+    """switch the per-kernel-family CUDA-event timing on/off (clears previous records)"""
+    check(_lib.lib().ttn_profile(int(bool(enable))))
+
+
+def profile_read():
+    """{family: (total_ms, launches)} accumulated since profile(True)"""
+    ms, cnt = (C.c_double * 8)(), (C.c_longlong * 8)()
+    check(_lib.lib().ttn_profile_read(ms, cnt))
+    return {KERNEL_FAMILIES[i]: (float(ms[i]), int(cnt[i])) for i in range(8)}
+
+
+def stream_handle() -> int:
+    """cudaStream_t the library launches on (for torch.cuda.ExternalStream / event timing)"""
+    return int(_lib.lib().ttn_stream() or 0)
 
 
 # ------------------------------------------------------------------------------------------------------

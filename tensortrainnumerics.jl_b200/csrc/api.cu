@@ -76,6 +76,28 @@ int ttn_synchronize(void) {
 long long ttn_launch_count(void) { return ctx().launches; }
 int ttn_reset_launch_count(void) { ctx().launches = 0; return TTN_OK; }
 void* ttn_stream(void) { return (void*)ctx().stream; }
+int ttn_profile(int enable) {
+  API_BEGIN
+  Context& c = ctx();
+  for (auto& r : c.prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  c.prof.clear();
+  c.prof_on = enable != 0;
+  API_END
+}
+int ttn_profile_read(double* ms, long long* counts) {
+  API_BEGIN
+  need_init();
+  Context& c = ctx();
+  TTN_CUDA(cudaStreamSynchronize(c.stream));
+  for (int i = 0; i < KF_COUNT; ++i) { ms[i] = 0.0; counts[i] = 0; }
+  for (auto& r : c.prof) {
+    float t = 0.f;
+    TTN_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    ms[r.fam] += t;
+    counts[r.fam] += 1;
+  }
+  API_END
+}
 
 // ---------------------------------------------------------------------------------------------------------
 }  // extern "C"

@@ -45,6 +45,7 @@ void apply_core(const T* A, const T* x, T* y, int n_out, int n_in, int Rl, int R
                 int64_t by) {
   const int64_t total = (int64_t)n_out * Rl * rl * Rr * rr;
   if (total <= 0 || batch <= 0) return;
+  ProfScope prof_scope_(KF_APPLY);
   const size_t smem = sizeof(T) * (size_t)n_out * n_in * Rl * Rr;
   ttn_assert(smem <= 48 * 1024, 2, "apply: MPO core does not fit in shared memory");
   int64_t blocks = (total + 255) / 256;

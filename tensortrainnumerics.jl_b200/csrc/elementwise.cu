@@ -193,6 +193,7 @@ template <class T>
 void copy4(const T* src, T* dst, const Copy4& c) {
   const int64_t total = c.n0 * c.n1 * c.n2 * c.n3;
   if (total <= 0) return;
+  ProfScope prof_scope_(KF_COPY);
   copy4_kernel<T><<<grid_for(total, 256), 256, 0, ctx().stream>>>(src, dst, c, total);
   TTN_CHECK_LAUNCH();
   ctx().launches++;
@@ -250,6 +251,7 @@ void scal(int64_t n, T a, T* x) {
 template <class T>
 void multi_dot(int64_t n, int nv, const T* X, int64_t ldx, const T* y, T* host_out) {
   if (nv <= 0) return;
+  ProfScope prof_scope_(KF_REDUCE);
   int nblocks = (int)std::min<int64_t>(std::max<int64_t>(1, (n + RED_T * 4 - 1) / (RED_T * 4)), (int64_t)ctx().sm_count * 4);
   DevBuf partial(sizeof(T) * (size_t)nv * nblocks), out(sizeof(T) * (size_t)nv);
   multi_dot_stage1<T><<<nblocks, RED_T, 0, ctx().stream>>>(n, nv, X, ldx, y, partial.as<T>());
@@ -263,6 +265,7 @@ void multi_dot(int64_t n, int nv, const T* X, int64_t ldx, const T* y, T* host_o
 
 template <class T>
 void multi_axpy(int64_t n, int nv, const T* X, int64_t ldx, const T* h_host, T* y, double sign) {
+  ProfScope prof_scope_(KF_REDUCE);
   for (int j0 = 0; j0 < nv; j0 += MAXV) {
     const int c = std::min(MAXV, nv - j0);
     HVec<T> h;

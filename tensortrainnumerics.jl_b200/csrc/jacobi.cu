@@ -190,7 +190,7 @@ int jacobi_orth(T* X, int m, int n, int64_t ldx, double* norms, int batch, int64
   auto kern = jacobi_kernel<T>;
   static bool attr_done = false;
   if (!attr_done) {
-    TTN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+    TTN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(224 * 1024)));
     attr_done = true;
   }
   int sweeps_used = 0;
@@ -206,6 +206,7 @@ int jacobi_orth(T* X, int m, int n, int64_t ldx, double* norms, int batch, int64
     for (int b0 = 0; b0 < batch; b0 += 65535) {
       const int nb = std::min(65535, batch - b0);
       dim3 grid(1, nb);
+      ProfScope prof_scope_(KF_JACOBI);
       kern<<<grid, threads, (size_t)n * col_bytes, ctx().stream>>>(X + (int64_t)b0 * bX, m, ldx, bX, grp.as<int>(),
                                                                  grp.as<int>() + 1, n, n, 0, 1, 0, tol, nullptr,
                                                                  dsw.as<int>() + b0);
@@ -247,6 +248,7 @@ int jacobi_orth(T* X, int m, int n, int64_t ldx, double* norms, int batch, int64
         if (cnt <= 0) continue;
         dim3 grid(cnt, batch);
         const size_t smem = (size_t)(st == 0 ? 1 : 2) * bsz * col_bytes;
+        ProfScope prof_scope_(KF_JACOBI);
         kern<<<grid, threads, smem, ctx().stream>>>(X, m, ldx, bX, gA.as<int>() + off[st], gB.as<int>() + off[st], bsz, n,
                                                    st == 0 ? 0 : 1, 0, 1, tol, dmax.as<unsigned long long>(), nullptr);
         TTN_CHECK_LAUNCH();
@@ -266,6 +268,7 @@ int jacobi_orth(T* X, int m, int n, int64_t ldx, double* norms, int batch, int64
     for (int b0 = 0; b0 < batch; b0 += 65535) {
       const int nb = std::min(65535, batch - b0);
       dim3 grid((n + wpb - 1) / wpb, nb);
+      ProfScope prof_scope_(KF_GATHER);
       colnorm_kernel<T><<<grid, wpb * 32, 0, ctx().stream>>>(X + (int64_t)b0 * bX, m, n, ldx, bX, norms + (int64_t)b0 * bnorms,
                                                             bnorms);
       TTN_CHECK_LAUNCH();
@@ -284,6 +287,7 @@ void gather_cols(const T* X, int m, int64_t ldx, const int* perm, const double* 
   for (int b0 = 0; b0 < batch; b0 += 65535) {
     const int nb = std::min(65535, batch - b0);
     dim3 grid(blocks, nb);
+    ProfScope prof_scope_(KF_GATHER);
     gather_kernel<T><<<grid, 256, 0, ctx().stream>>>(X + (int64_t)b0 * bX, m, ldx, perm + (int64_t)b0 * bperm,
                                                     scale + (int64_t)b0 * bperm, r, dst + (int64_t)b0 * bdst, rs, cs, bX, bperm,
                                                     bdst);

@@ -218,6 +218,7 @@ template <class T>
 void launch_apply(const T* A, int m, int64_t lda, const T* tau, int jlo, int jhi, T* C, int c0, int nc, int64_t ldc,
                   bool trans, int batch, int64_t bA, int64_t btau, int64_t bC) {
   if (nc <= 0 || jhi <= jlo || batch <= 0) return;
+  ProfScope prof_scope_(KF_QR_APPLY);
   const int L = m - jlo;
   const size_t budget = 200 * 1024;
   const size_t fit = budget / (sizeof(T) * (size_t)L);
@@ -252,6 +253,7 @@ void qr_factor(T* A, int m, int n, int64_t lda, T* tau, int batch, int64_t bA, i
   for (int j0 = 0; j0 < k; j0 += PANEL_NB) {
     for (int b0 = 0; b0 < batch; b0 += 65535) {
       const int nb = std::min(65535, batch - b0);
+      ProfScope prof_scope_(KF_QR_PANEL);
       qr_panel_kernel<T, PANEL_NB><<<nb, PANEL_T, 0, ctx().stream>>>(A + (int64_t)b0 * bA, m, n, lda, tau + (int64_t)b0 * btau,
                                                                      j0, bA, btau);
       TTN_CHECK_LAUNCH();

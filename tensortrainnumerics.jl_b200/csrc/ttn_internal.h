@@ -43,14 +43,36 @@ inline void ttn_assert(bool c, int code, const char* msg) {
 // ---------------------------------------------------------------------------------------------
 // context: one device, one stream, launch counter
 // ---------------------------------------------------------------------------------------------
+enum KernelFamily { KF_GEMM = 0, KF_COPY = 1, KF_APPLY = 2, KF_QR_PANEL = 3, KF_QR_APPLY = 4, KF_JACOBI = 5, KF_REDUCE = 6,
+                    KF_GATHER = 7, KF_COUNT = 8 };
+struct ProfRec { int fam; cudaEvent_t a, b; };
 struct Context {
   int device = 0;
   cudaStream_t stream = nullptr;
   int sm_count = 148;
   long long launches = 0;  // kernels launched by this library since the last reset
   bool inited = false;
+  bool prof_on = false;    // per-kernel-family CUDA-event timing (bench.py roofline pass only)
+  std::vector<ProfRec> prof;
 };
 Context& ctx();
+// brackets the launches of one kernel family with CUDA events on the library stream when profiling is enabled
+struct ProfScope {
+  bool on;
+  ProfRec r;
+  explicit ProfScope(int fam) : on(ctx().prof_on) {
+    if (!on) return;
+    r.fam = fam;
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, ctx().stream);
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(r.b, ctx().stream);
+    ctx().prof.push_back(r);
+  }
+};
 
 // stream-ordered device buffer (cudaMallocAsync pool on the context stream)
 struct DevBuf {
