@@ -59,6 +59,7 @@ void* ttn_stream(void);                   /* cudaStream_t the library launches o
 /* per-kernel-family CUDA-event timing on the library stream (bench.py's roofline pass; adds two event records per launch).
  * families: 0 gemm, 1 copy/permute, 2 apply, 3 qr panel, 4 qr reflector apply, 5 jacobi, 6 reductions/axpy, 7 gather/norms */
 #define TTN_NFAMILIES 8
+int ttn_last_jacobi_sweeps(void);        /* diagnostics: sweeps of the most recent Jacobi SVD */
 int ttn_profile(int enable);              /* clears the records and switches profiling on/off */
 int ttn_profile_read(double* ms /* 8 */, long long* counts /* 8 */);
 

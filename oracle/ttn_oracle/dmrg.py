@@ -54,9 +54,13 @@ def dmrg_matvec2(G, Am, V, H, symmetrize=True):
     """The K_matfree contraction of dmrg.jl:239-244.
     symmetrize=True : 0.5·(G·Amid·V·H + Gᵀ·Amidᵀ·V·Hᵀ)  (what the reference applies)
     symmetrize=False: the single application G·Amid·V·H."""
-    Y = np.einsum("yad,ybez,def,zcf->abc", G, Am, V, H, optimize=True)
+    def chain(Gx, Ax, Hx):   # Σ Gx[y,a,d] Ax[y,b,e,z] V[d,e,f] Hx[z,c,f] as three pairwise contractions
+        t1 = np.einsum("yad,def->yaef", Gx, V)
+        t2 = np.einsum("ybez,yaef->abzf", Ax, t1)
+        return np.einsum("abzf,zcf->abc", t2, Hx)
+    Y = chain(G, Am, H)
     if symmetrize:
-        Y2 = np.einsum("yda,zfc,yebz,def->abc", G, H, Am, V, optimize=True)
+        Y2 = chain(np.transpose(G, (0, 2, 1)), np.transpose(Am, (0, 2, 1, 3)), np.transpose(H, (0, 2, 1)))
         Y = 0.5 * (Y + Y2)
     return Y
 

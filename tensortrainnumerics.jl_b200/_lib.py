@@ -61,7 +61,7 @@ def load():
     vp, i64p, dp, ip = C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_int)
     vpp = C.POINTER(C.c_void_p)
     sig = {
-        "ttn_init": [C.c_int], "ttn_shutdown": [], "ttn_version": [], "ttn_synchronize": [],
+        "ttn_init": [C.c_int], "ttn_shutdown": [], "ttn_version": [], "ttn_synchronize": [], "ttn_last_jacobi_sweeps": [],
         "ttn_reset_launch_count": [], "ttn_profile": [C.c_int],
         "ttn_profile_read": [C.POINTER(C.c_double), C.POINTER(C.c_longlong)],
         "ttn_ttv_upload": [C.c_int, C.c_int, i64p, i64p, i64p, vpp, C.c_int, vpp],

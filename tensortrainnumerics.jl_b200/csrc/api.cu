@@ -76,6 +76,7 @@ int ttn_synchronize(void) {
 long long ttn_launch_count(void) { return ctx().launches; }
 int ttn_reset_launch_count(void) { ctx().launches = 0; return TTN_OK; }
 void* ttn_stream(void) { return (void*)ctx().stream; }
+int ttn_last_jacobi_sweeps(void) { return ctx().last_jacobi_sweeps; }
 int ttn_profile(int enable) {
   API_BEGIN
   Context& c = ctx();

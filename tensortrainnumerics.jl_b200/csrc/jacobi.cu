@@ -27,55 +27,73 @@ __device__ __forceinline__ double wsumd(double v) {
   return v;
 }
 
-// rotate the column pair (xp, xq) of length m (shared memory); returns |c|/sqrt(a b) before the rotation
-template <class T>
-__device__ __forceinline__ double rotate_pair(T* xp, T* xq, int m, int lane, double tol) {
+// Rotates the column pair (xp, xq) of length m (shared memory) with a group of GL lanes (GL = 16: two pairs per
+// warp in flight).  Returns true when a rotation was applied, i.e. |x_p^H x_q| > tol·||x_p||·||x_q||.
+template <class T, int GL>
+__device__ __forceinline__ bool rotate_pair(T* xp, T* xq, int m, int gl, double tol2, bool active) {
+  // every lane of the warp must reach the shuffles below: inactive groups contribute zeros and never rotate
   double a = 0.0, b = 0.0;
   T c = t_zero<T>();
-  for (int i = lane; i < m; i += 32) {
+  if (active)
+  for (int i = gl; i < m; i += GL) {
     const T p = xp[i], q = xq[i];
     a += t_abs2(p);
     b += t_abs2(q);
     t_fma(c, t_conj(p), q);
   }
-  a = wsumd(a);
-  b = wsumd(b);
-  const double cr = wsumd(t_real(c));
-  const double ci = is_cplx<T>::value ? wsumd(t_imag(c)) : 0.0;
-  const double absc = sqrt(cr * cr + ci * ci);
-  const double denom = sqrt(a * b);
-  if (!(denom > 0.0) || !(absc > tol * denom)) return (denom > 0.0) ? absc / denom : 0.0;
-  const double phr = cr / absc, phi = ci / absc;
-  const double zeta = (b - a) / (2.0 * absc);
-  const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-  const double cs = 1.0 / sqrt(1.0 + t * t);
-  const double sn = cs * t;
+  double cr = t_real(c), ci = t_imag(c);
+#pragma unroll
+  for (int o = GL / 2; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+    cr += __shfl_xor_sync(0xffffffffu, cr, o);
+    if (is_cplx<T>::value) ci += __shfl_xor_sync(0xffffffffu, ci, o);
+  }
+  const double c2 = cr * cr + ci * ci;
+  if (!(c2 > tol2 * a * b)) return false;   // also covers zero columns and NaNs
+  double cs, sn, phr = 1.0, phi = 0.0;
+  if (is_cplx<T>::value) {
+    const double inv = rsqrt(c2);           // 1/|c|
+    phr = cr * inv; phi = ci * inv;
+    const double zeta = 0.5 * (b - a) * inv;
+    const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+    cs = rsqrt(1.0 + t * t);
+    sn = cs * t;
+  } else {
+    const double zeta = 0.5 * (b - a) / cr;  // real case: the sign of c is carried by zeta
+    const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+    cs = rsqrt(1.0 + t * t);
+    sn = cs * t;
+  }
   const bool swap = a < b;  // keep the larger column first (de Rijk ordering)
   const T ph = t_from<T>(phr, phi);
   const T phc = t_from<T>(phr, -phi);
-  for (int i = lane; i < m; i += 32) {
+  for (int i = gl; i < m; i += GL) {
     const T p = xp[i], q = xq[i];
     const T np = t_sub(t_scale(p, cs), t_scale(t_mul(phc, q), sn));
     const T nq = t_add(t_scale(t_mul(ph, p), sn), t_scale(q, cs));
     xp[i] = swap ? nq : np;
     xq[i] = swap ? np : nq;
   }
-  return absc / denom;
+  return true;
 }
 
+constexpr int JGL = 16;  // lanes per column pair
+
 // mode 0: all pairs among the na+nb columns; mode 1: cross pairs (one column from each group) only.
-// full != 0: iterate sweeps until converged (single-CTA problem), else run `sweeps` sweeps.
+// full != 0: iterate sweeps until a whole sweep applies no rotation (single-CTA problem), else run `sweeps` sweeps.
 template <class T>
 __global__ void __launch_bounds__(1024) jacobi_kernel(T* __restrict__ X, int m, int64_t ldx, int64_t bX,
                                                       const int* __restrict__ grpA, const int* __restrict__ grpB, int bsz,
                                                       int n, int mode, int full, int sweeps, double tol,
-                                                      unsigned long long* __restrict__ d_maxoff, int* __restrict__ d_sweeps) {
+                                                      unsigned int* __restrict__ d_rotated, int* __restrict__ d_sweeps) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* Xs = reinterpret_cast<T*>(smem_raw);
-  __shared__ double s_max[32];
-  __shared__ int s_done;
+  __shared__ int s_rot;
   T* Xb = X + blockIdx.y * bX;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int grp = tid / JGL, ngrp = blockDim.x / JGL, gl = tid % JGL;
+  const double tol2 = tol * tol;
 
   const int a0 = grpA[blockIdx.x] * bsz;
   const int na = min(bsz, n - a0);
@@ -89,65 +107,57 @@ __global__ void __launch_bounds__(1024) jacobi_kernel(T* __restrict__ X, int m, 
     T* dst = Xs + (size_t)c * m;
     for (int i = lane; i < m; i += 32) dst[i] = src[i];
   }
+  if (tid == 0) s_rot = 0;
   __syncthreads();
 
   int sw = 0;
   const int max_sw = full ? JAC_MAX_SWEEPS : sweeps;
-  double all_max = 0.0;
+  bool any_rot = false;
   for (; sw < max_sw; ++sw) {
-    double mymax = 0.0;
+    bool myrot = false;
     if (mode == 0) {
       const int ne = nc + (nc & 1);          // even number of players (last may be a dummy)
       const int half = ne / 2;
       for (int r = 0; r < ne - 1; ++r) {
-        for (int i = warp; i < half; i += nwarps) {
-          int p, q;
+        for (int i0 = 0; i0 < half; i0 += ngrp) {   // warp-uniform trip count
+          const int i = i0 + grp;
+          int p = 0, q = 0;
           if (i == 0) { p = ne - 1; q = r; }
-          else { p = (r + i) % (ne - 1); q = (r - i + (ne - 1)) % (ne - 1); }
-          if (p < nc && q < nc) {
-            if (p > q) { const int t = p; p = q; q = t; }
-            const double off = rotate_pair<T>(Xs + (size_t)p * m, Xs + (size_t)q * m, m, lane, tol);
-            mymax = fmax(mymax, off);
-          }
+          else if (i < half) { p = (r + i) % (ne - 1); q = (r - i + (ne - 1)) % (ne - 1); }
+          const bool act = i < half && p < nc && q < nc;
+          if (p > q) { const int t = p; p = q; q = t; }
+          myrot |= rotate_pair<T, JGL>(Xs + (size_t)(act ? p : 0) * m, Xs + (size_t)(act ? q : 0) * m, m, gl, tol2, act);
         }
         __syncthreads();
       }
     } else {
       const int bm = max(na, nb);
       for (int r = 0; r < bm; ++r) {
-        for (int i = warp; i < bm; i += nwarps) {
-          const int p = i, q = (i + r) % bm;
-          if (p < na && q < nb) {
-            const double off = rotate_pair<T>(Xs + (size_t)p * m, Xs + (size_t)(na + q) * m, m, lane, tol);
-            mymax = fmax(mymax, off);
-          }
+        for (int i0 = 0; i0 < bm; i0 += ngrp) {     // warp-uniform trip count
+          const int p = i0 + grp, q = (p + r) % bm;
+          const bool act = p < na && q < nb;
+          myrot |= rotate_pair<T, JGL>(Xs + (size_t)(act ? p : 0) * m, Xs + (size_t)(act ? na + q : 0) * m, m, gl, tol2, act);
         }
         __syncthreads();
       }
     }
-    // block max of the off-diagonal measure seen in this sweep
-    if (lane == 0) s_max[warp] = mymax;
+    if (myrot) s_rot = 1;       // benign race: every writer stores the same value
     __syncthreads();
-    if (tid == 0) {
-      double v = 0.0;
-      for (int w = 0; w < nwarps; ++w) v = fmax(v, s_max[w]);
-      s_max[0] = v;
-      s_done = (v <= tol) ? 1 : 0;
-    }
+    const int rot = s_rot;
     __syncthreads();
-    all_max = fmax(all_max, s_max[0]);
-    const int done = s_done;
-    __syncthreads();
-    if (full && done) { ++sw; break; }
+    if (tid == 0) s_rot = 0;
+    any_rot |= (rot != 0);
+    if (full && !rot) { ++sw; break; }
   }
 
+  __syncthreads();
   for (int c = warp; c < nc; c += nwarps) {
     T* dst = Xb + (int64_t)(c < na ? a0 + c : b0 + (c - na)) * ldx;
     const T* src = Xs + (size_t)c * m;
     for (int i = lane; i < m; i += 32) dst[i] = src[i];
   }
   if (tid == 0) {
-    if (d_maxoff) atomicMax(d_maxoff, (unsigned long long)__double_as_longlong(all_max));
+    if (d_rotated && any_rot) atomicOr(d_rotated, 1u);
     if (d_sweeps && full) d_sweeps[blockIdx.y] = sw;
   }
 }
@@ -185,7 +195,8 @@ __global__ void gather_kernel(const T* __restrict__ X, int m, int64_t ldx, const
 template <class T>
 int jacobi_orth(T* X, int m, int n, int64_t ldx, double* norms, int batch, int64_t bX, int64_t bnorms) {
   if (n <= 0 || m <= 0 || batch <= 0) return 0;
-  const double tol = std::sqrt((double)m) * 2.220446049250313e-16;
+  // rotation threshold |x_p^H x_q| <= tol ||x_p|| ||x_q||: m·eps is the rounding level of the computed inner product
+  const double tol = (double)std::max(m, 8) * 1.1102230246251565e-16;
   const size_t budget = 220 * 1024;
   auto kern = jacobi_kernel<T>;
   static bool attr_done = false;
@@ -202,7 +213,7 @@ int jacobi_orth(T* X, int m, int n, int64_t ldx, double* norms, int batch, int64
     DevBuf grp(sizeof(int) * 2), dsw(sizeof(int) * batch);
     TTN_CUDA(cudaMemcpyAsync(grp.p, h_grp, sizeof(h_grp), cudaMemcpyHostToDevice, ctx().stream));
     const int pairs = (n + 1) / 2;
-    int threads = std::min(1024, std::max(64, 32 * pairs));
+    int threads = std::min(1024, std::max(64, ((JGL * pairs + 31) / 32) * 32));
     for (int b0 = 0; b0 < batch; b0 += 65535) {
       const int nb = std::min(65535, batch - b0);
       dim3 grid(1, nb);
@@ -213,14 +224,17 @@ int jacobi_orth(T* X, int m, int n, int64_t ldx, double* norms, int batch, int64
       TTN_CHECK_LAUNCH();
       ctx().launches++;
     }
-    sweeps_used = -1;  // decided on device
+    int hsw = 0;   // sweeps of batch element 0 (diagnostics; one 4-byte D2H, overlapped with the norms read-back sync)
+    TTN_CUDA(cudaMemcpyAsync(&hsw, dsw.p, sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
+    TTN_CUDA(cudaStreamSynchronize(ctx().stream));
+    sweeps_used = hsw;
   } else {
     // block Jacobi: blocks of bsz columns, two blocks per CTA
     int bsz = (int)(budget / (2 * col_bytes));
     if (bsz > 32) bsz = 32;
     const int nblk = (n + bsz - 1) / bsz;
     const int ne = nblk + (nblk & 1);
-    DevBuf dmax(sizeof(unsigned long long));
+    DevBuf dmax(sizeof(unsigned int));
     // pair lists of every round-robin step, uploaded once: step 0 = pairs inside each block,
     // steps 1..ne-1 = block tournament (cross pairs only)
     std::vector<int> hA, hB, off(ne + 1, 0);
@@ -240,9 +254,9 @@ int jacobi_orth(T* X, int m, int n, int64_t ldx, double* norms, int batch, int64
     TTN_CUDA(cudaMemcpyAsync(gB.p, hB.data(), sizeof(int) * hB.size(), cudaMemcpyHostToDevice, ctx().stream));
     TTN_CUDA(cudaStreamSynchronize(ctx().stream));
     ttn_assert(batch <= 65535, 2, "jacobi: batch too large for the block path");
-    const int threads = std::min(1024, std::max(64, 32 * bsz));
+    const int threads = std::min(1024, std::max(64, ((JGL * bsz + 31) / 32) * 32));
     for (int sw = 0; sw < JAC_MAX_SWEEPS; ++sw) {
-      TTN_CUDA(cudaMemsetAsync(dmax.p, 0, sizeof(unsigned long long), ctx().stream));
+      TTN_CUDA(cudaMemsetAsync(dmax.p, 0, sizeof(unsigned int), ctx().stream));
       for (int st = 0; st < ne; ++st) {
         const int cnt = off[st + 1] - off[st];
         if (cnt <= 0) continue;
@@ -250,17 +264,15 @@ int jacobi_orth(T* X, int m, int n, int64_t ldx, double* norms, int batch, int64
         const size_t smem = (size_t)(st == 0 ? 1 : 2) * bsz * col_bytes;
         ProfScope prof_scope_(KF_JACOBI);
         kern<<<grid, threads, smem, ctx().stream>>>(X, m, ldx, bX, gA.as<int>() + off[st], gB.as<int>() + off[st], bsz, n,
-                                                   st == 0 ? 0 : 1, 0, 1, tol, dmax.as<unsigned long long>(), nullptr);
+                                                   st == 0 ? 0 : 1, 0, 1, tol, dmax.as<unsigned int>(), nullptr);
         TTN_CHECK_LAUNCH();
         ctx().launches++;
       }
-      unsigned long long bits = 0;
-      TTN_CUDA(cudaMemcpyAsync(&bits, dmax.p, sizeof(bits), cudaMemcpyDeviceToHost, ctx().stream));
+      unsigned int rotated = 0;
+      TTN_CUDA(cudaMemcpyAsync(&rotated, dmax.p, sizeof(rotated), cudaMemcpyDeviceToHost, ctx().stream));
       TTN_CUDA(cudaStreamSynchronize(ctx().stream));
-      double mx;
-      std::memcpy(&mx, &bits, sizeof(mx));
       sweeps_used = sw + 1;
-      if (mx <= tol) break;
+      if (!rotated) break;
     }
   }
   {
@@ -275,6 +287,7 @@ int jacobi_orth(T* X, int m, int n, int64_t ldx, double* norms, int batch, int64
       ctx().launches++;
     }
   }
+  ctx().last_jacobi_sweeps = sweeps_used;
   return sweeps_used;
 }
 

@@ -54,6 +54,7 @@ struct Context {
   bool inited = false;
   bool prof_on = false;    // per-kernel-family CUDA-event timing (bench.py roofline pass only)
   std::vector<ProfRec> prof;
+  int last_jacobi_sweeps = 0;  // diagnostics: sweeps used by the most recent Jacobi SVD (batch element 0)
 };
 Context& ctx();
 // brackets the launches of one kernel family with CUDA events on the library stream when profiling is enabled

@@ -217,6 +217,20 @@ def test_cfg2_shape_property_checks():
     # projection property: <x, y> = <y, y> up to the truncation being (quasi-)optimal; error norm consistent
     err = t.norm(t.sub(xd, yd)) / n0
     assert 0.0 < err < 1.0
-    # agreement with the CPU oracle on the same input (TT distance, 1e-10)
-    ref = o.tt_compress(o.copy_tt(x), 64)
-    assert o.rel_distance(yd.download(), ref) < 1e-10
+    # agreement with the CPU oracle on the same input.  Truncating a random TT with a flat spectrum is ill conditioned
+    # (the gap sigma_64 - sigma_65 is ~1e-3 sigma_1 at every bond): the oracle itself moves by ~4e-10 when its input is
+    # perturbed by 1e-16, so the comparison is made against that measured sensitivity, the retained singular values of
+    # every bond step are compared to 1e-8, and the truncation error norms (well conditioned) to 1e-10.
+    sig_ref = []
+    ref = o.tt_compress(o.copy_tt(x), 64, sigma_out=sig_ref)
+    pert = o.copy_tt(x)
+    for k in range(d):
+        pert.ttv_vec[k] = pert.ttv_vec[k] * (1 + 1e-16 * rng.standard_normal(pert.ttv_vec[k].shape))
+    sens = o.rel_distance(o.tt_compress(pert, 64), ref)
+    y2, sig = t.tt_compress_(xd.copy(), 64, return_sigma=True)
+    got = y2.download()
+    assert o.rel_distance(got, ref) < max(1e-10, 20 * sens)
+    for a, b in zip(sig, sig_ref):
+        assert len(a) == len(b) and np.abs(a - b).max() / b[0] < 1e-8
+    err_ref = o.rel_distance(ref, x)
+    assert abs(err - err_ref) < 1e-10
