@@ -27,73 +27,61 @@ __device__ __forceinline__ double wsumd(double v) {
   return v;
 }
 
-// Rotates the column pair (xp, xq) of length m (shared memory) with a group of GL lanes (GL = 16: two pairs per
-// warp in flight).  Returns true when a rotation was applied, i.e. |x_p^H x_q| > tol·||x_p||·||x_q||.
-template <class T, int GL>
-__device__ __forceinline__ bool rotate_pair(T* xp, T* xq, int m, int gl, double tol2, bool active) {
-  // every lane of the warp must reach the shuffles below: inactive groups contribute zeros and never rotate
-  double a = 0.0, b = 0.0;
-  T c = t_zero<T>();
-  if (active)
-  for (int i = gl; i < m; i += GL) {
-    const T p = xp[i], q = xq[i];
-    a += t_abs2(p);
-    b += t_abs2(q);
-    t_fma(c, t_conj(p), q);
-  }
-  double cr = t_real(c), ci = t_imag(c);
-#pragma unroll
-  for (int o = GL / 2; o > 0; o >>= 1) {
-    a += __shfl_xor_sync(0xffffffffu, a, o);
-    b += __shfl_xor_sync(0xffffffffu, b, o);
-    cr += __shfl_xor_sync(0xffffffffu, cr, o);
-    if (is_cplx<T>::value) ci += __shfl_xor_sync(0xffffffffu, ci, o);
-  }
-  const double c2 = cr * cr + ci * ci;
-  if (!(c2 > tol2 * a * b)) return false;   // also covers zero columns and NaNs
-  double cs, sn, phr = 1.0, phi = 0.0;
-  if (is_cplx<T>::value) {
-    const double inv = rsqrt(c2);           // 1/|c|
-    phr = cr * inv; phi = ci * inv;
-    const double zeta = 0.5 * (b - a) * inv;
-    const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-    cs = rsqrt(1.0 + t * t);
-    sn = cs * t;
-  } else {
-    const double zeta = 0.5 * (b - a) / cr;  // real case: the sign of c is carried by zeta
-    const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-    cs = rsqrt(1.0 + t * t);
-    sn = cs * t;
-  }
-  const bool swap = a < b;  // keep the larger column first (de Rijk ordering)
-  const T ph = t_from<T>(phr, phi);
-  const T phc = t_from<T>(phr, -phi);
-  for (int i = gl; i < m; i += GL) {
-    const T p = xp[i], q = xq[i];
-    const T np = t_sub(t_scale(p, cs), t_scale(t_mul(phc, q), sn));
-    const T nq = t_add(t_scale(t_mul(ph, p), sn), t_scale(q, cs));
-    xp[i] = swap ? nq : np;
-    xq[i] = swap ? np : nq;
-  }
-  return true;
+// Plane rotation that orthogonalises two columns with squared norms a, b and inner product c = x_p^H x_q
+// (|c| = absc, phase ph = c/|c|):  x_p' = cs x_p - sn conj(ph) x_q,  x_q' = sn ph x_p + cs x_q.
+// With tau = (b-a)/2, h = sqrt(tau^2 + |c|^2), d = tau + sign(tau) h the smaller root is t = |c|/d and
+// cs = |d|/sqrt(d^2+|c|^2), sn = sign(d)|c|/sqrt(d^2+|c|^2): one sqrt and one rsqrt, no division.
+__device__ __forceinline__ void rot_params(double a, double b, double absc, double& cs, double& sn) {
+  const double tau = 0.5 * (b - a);
+  const double h = sqrt(tau * tau + absc * absc);
+  const double d = tau + (tau >= 0.0 ? h : -h);
+  const double rinv = rsqrt(d * d + absc * absc);
+  cs = fabs(d) * rinv;
+  sn = (d >= 0.0 ? absc : -absc) * rinv;
 }
 
-constexpr int JGL = 16;  // lanes per column pair
+constexpr int JAC_T = 256;   // threads per CTA
 
+// slot -> column pair of round r.  mode 0: round-robin tournament over ne = nc (+1 dummy) players, no integer
+// division; mode 1: cross pairs between the two column groups (p from group A, q from group B).
+__device__ __forceinline__ bool pair_of_slot(int mode, int i, int r, int ne, int nc, int na, int nb, int nslots, int& p, int& q) {
+  if (mode == 0) {
+    p = r + i; q = r - i;
+    if (p >= ne - 1) p -= ne - 1;
+    if (q < 0) q += ne - 1;
+    if (i == 0) { p = ne - 1; q = r; }
+    return i < nslots && p < nc && q < nc;
+  }
+  p = i;
+  q = i + r;
+  if (q >= nslots) q -= nslots;
+  const bool act = i < nslots && p < na && q < nb;
+  q += na;
+  return act;
+}
+
+// One-sided Jacobi on a group of columns staged in shared memory (column pitch m+PADC keeps the strided row
+// accesses of neighbouring lane groups on distinct banks).  One block barrier per round.  A group of GL lanes owns a
+// column pair: it loads its rows of both columns into registers (RPL rows per lane; RPL == 0: generic length, rows
+// re-read from shared memory), reduces the inner product with GL-wide shuffles, turns (||x_p||^2, ||x_q||^2, c) into the
+// plane rotation (rot_params: no division) and applies it from the registers.  The squared column norms are
+// maintained in shared memory by the rotation identities and recomputed exactly at the start of every sweep.
+// With GL = 4 a warp carries 8 pairs, so the scalar rotation set-up is amortised over 8 pairs per warp instruction.
 // mode 0: all pairs among the na+nb columns; mode 1: cross pairs (one column from each group) only.
 // full != 0: iterate sweeps until a whole sweep applies no rotation (single-CTA problem), else run `sweeps` sweeps.
-template <class T>
-__global__ void __launch_bounds__(1024) jacobi_kernel(T* __restrict__ X, int m, int64_t ldx, int64_t bX,
-                                                      const int* __restrict__ grpA, const int* __restrict__ grpB, int bsz,
-                                                      int n, int mode, int full, int sweeps, double tol,
-                                                      unsigned int* __restrict__ d_rotated, int* __restrict__ d_sweeps) {
+template <class T, int GL, int RPL, bool FULLM>
+__global__ void __launch_bounds__(JAC_T) jacobi_kernel(T* __restrict__ X, int m, int64_t ldx, int64_t bX,
+                                                       const int* __restrict__ grpA, const int* __restrict__ grpB, int bsz,
+                                                       int n, int mode, int full, int sweeps, double tol,
+                                                       unsigned int* __restrict__ d_rotated, int* __restrict__ d_sweeps) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* Xs = reinterpret_cast<T*>(smem_raw);
   __shared__ int s_rot;
+  constexpr int PADC = is_cplx<T>::value ? 0 : 4;
   T* Xb = X + blockIdx.y * bX;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  const int grp = tid / JGL, ngrp = blockDim.x / JGL, gl = tid % JGL;
+  const int grp = tid / GL, ngrp = blockDim.x / GL, gl = tid % GL;
   const double tol2 = tol * tol;
+  const int pitch = m + PADC;
 
   const int a0 = grpA[blockIdx.x] * bsz;
   const int na = min(bsz, n - a0);
@@ -101,10 +89,16 @@ __global__ void __launch_bounds__(1024) jacobi_kernel(T* __restrict__ X, int m, 
   const int b0 = gb >= 0 ? gb * bsz : 0;
   const int nb = gb >= 0 ? min(bsz, n - b0) : 0;
   const int nc = na + nb;
+  const int ne = nc + (nc & 1);
+  const int nslots = (mode == 0) ? ne / 2 : max(na, nb);
+  const int nrounds = (mode == 0) ? ne - 1 : nslots;
+
+  T* Xs = reinterpret_cast<T*>(smem_raw);                            // [nc][pitch]
+  double* nrm2 = reinterpret_cast<double*>(Xs + (size_t)nc * pitch);   // [nc]
 
   for (int c = warp; c < nc; c += nwarps) {
     const T* src = Xb + (int64_t)(c < na ? a0 + c : b0 + (c - na)) * ldx;
-    T* dst = Xs + (size_t)c * m;
+    T* dst = Xs + (size_t)c * pitch;
     for (int i = lane; i < m; i += 32) dst[i] = src[i];
   }
   if (tid == 0) s_rot = 0;
@@ -114,32 +108,84 @@ __global__ void __launch_bounds__(1024) jacobi_kernel(T* __restrict__ X, int m, 
   const int max_sw = full ? JAC_MAX_SWEEPS : sweeps;
   bool any_rot = false;
   for (; sw < max_sw; ++sw) {
+    for (int c = warp; c < nc; c += nwarps) {       // exact squared norms once per sweep
+      const T* x = Xs + (size_t)c * pitch;
+      double a = 0.0;
+      for (int i = lane; i < m; i += 32) a += t_abs2(x[i]);
+      a = wsumd(a);
+      if (lane == 0) nrm2[c] = a;
+    }
+    __syncthreads();
     bool myrot = false;
-    if (mode == 0) {
-      const int ne = nc + (nc & 1);          // even number of players (last may be a dummy)
-      const int half = ne / 2;
-      for (int r = 0; r < ne - 1; ++r) {
-        for (int i0 = 0; i0 < half; i0 += ngrp) {   // warp-uniform trip count
-          const int i = i0 + grp;
-          int p = 0, q = 0;
-          if (i == 0) { p = ne - 1; q = r; }
-          else if (i < half) { p = (r + i) % (ne - 1); q = (r - i + (ne - 1)) % (ne - 1); }
-          const bool act = i < half && p < nc && q < nc;
-          if (p > q) { const int t = p; p = q; q = t; }
-          myrot |= rotate_pair<T, JGL>(Xs + (size_t)(act ? p : 0) * m, Xs + (size_t)(act ? q : 0) * m, m, gl, tol2, act);
+    for (int r = 0; r < nrounds; ++r) {
+      for (int i0 = 0; i0 < nslots; i0 += ngrp) {   // warp-uniform trip count (the shuffles need every lane)
+        const int i = i0 + grp;
+        int p, q;
+        const bool act = pair_of_slot(mode, i, r, ne, nc, na, nb, nslots, p, q);
+        T* xp = Xs + (act ? p : 0) * pitch;
+        T* xq = Xs + (act ? q : 0) * pitch;
+        T rp[RPL > 0 ? RPL : 1], rq[RPL > 0 ? RPL : 1];
+        T c = t_zero<T>();
+        if (RPL > 0) {
+          // (inactive groups read column 0: harmless, their result is discarded; keeps the loads unpredicated)
+#pragma unroll
+          for (int k = 0; k < RPL; ++k) {
+            const int row = gl + k * GL;
+            const bool ok = FULLM || row < m;
+            rp[k] = ok ? xp[row] : t_zero<T>();
+            rq[k] = ok ? xq[row] : t_zero<T>();
+          }
+          T c4[4] = {t_zero<T>(), t_zero<T>(), t_zero<T>(), t_zero<T>()};   // independent accumulation chains
+#pragma unroll
+          for (int k = 0; k < RPL; ++k) t_fma(c4[k & 3], t_conj(rp[k]), rq[k]);
+          c = t_add(t_add(c4[0], c4[1]), t_add(c4[2], c4[3]));
+        } else if (act) {
+          for (int row = gl; row < m; row += GL) t_fma(c, t_conj(xp[row]), xq[row]);
         }
-        __syncthreads();
-      }
-    } else {
-      const int bm = max(na, nb);
-      for (int r = 0; r < bm; ++r) {
-        for (int i0 = 0; i0 < bm; i0 += ngrp) {     // warp-uniform trip count
-          const int p = i0 + grp, q = (p + r) % bm;
-          const bool act = p < na && q < nb;
-          myrot |= rotate_pair<T, JGL>(Xs + (size_t)(act ? p : 0) * m, Xs + (size_t)(act ? na + q : 0) * m, m, gl, tol2, act);
+        double cr = t_real(c), ci = t_imag(c);
+#pragma unroll
+        for (int o = GL / 2; o > 0; o >>= 1) {
+          cr += __shfl_xor_sync(0xffffffffu, cr, o);
+          if (is_cplx<T>::value) ci += __shfl_xor_sync(0xffffffffu, ci, o);
         }
-        __syncthreads();
+        if (!act) continue;
+        const double a = nrm2[p], b = nrm2[q];
+        const double c2 = cr * cr + ci * ci;
+        if (!(c2 > tol2 * a * b)) continue;        // also skips zero columns and NaNs
+        double cs, sn, absc, phr, phi;
+        if (is_cplx<T>::value) {
+          const double inv = rsqrt(c2);
+          absc = c2 * inv; phr = cr * inv; phi = ci * inv;
+        } else {
+          absc = fabs(cr); phr = cr >= 0.0 ? 1.0 : -1.0; phi = 0.0;
+        }
+        rot_params(a, b, absc, cs, sn);
+        if (gl == 0) {
+          const double x = 2.0 * cs * sn * absc;
+          nrm2[p] = fmax(cs * cs * a - x + sn * sn * b, 0.0);
+          nrm2[q] = fmax(sn * sn * a + x + cs * cs * b, 0.0);
+        }
+        myrot = true;
+        const T ph = t_from<T>(sn * phr, sn * phi);      // sn * phase
+        const T phc = t_from<T>(sn * phr, -sn * phi);    // sn * conj(phase)
+        if (RPL > 0) {
+#pragma unroll
+          for (int k = 0; k < RPL; ++k) {
+            const int row = gl + k * GL;
+            if (FULLM || row < m) {
+              xp[row] = t_sub(t_scale(rp[k], cs), t_mul(phc, rq[k]));
+              xq[row] = t_add(t_mul(ph, rp[k]), t_scale(rq[k], cs));
+            }
+          }
+        } else {
+          for (int row = gl; row < m; row += GL) {
+            const T pv = xp[row], qv = xq[row];
+            xp[row] = t_sub(t_scale(pv, cs), t_mul(phc, qv));
+            xq[row] = t_add(t_mul(ph, pv), t_scale(qv, cs));
+          }
+        }
       }
+      __syncthreads();
     }
     if (myrot) s_rot = 1;       // benign race: every writer stores the same value
     __syncthreads();
@@ -153,7 +199,7 @@ __global__ void __launch_bounds__(1024) jacobi_kernel(T* __restrict__ X, int m, 
   __syncthreads();
   for (int c = warp; c < nc; c += nwarps) {
     T* dst = Xb + (int64_t)(c < na ? a0 + c : b0 + (c - na)) * ldx;
-    const T* src = Xs + (size_t)c * m;
+    const T* src = Xs + (size_t)c * pitch;
     for (int i = lane; i < m; i += 32) dst[i] = src[i];
   }
   if (tid == 0) {
@@ -161,6 +207,10 @@ __global__ void __launch_bounds__(1024) jacobi_kernel(T* __restrict__ X, int m, 
     if (d_sweeps && full) d_sweeps[blockIdx.y] = sw;
   }
 }
+
+template <class T> struct JacCfg;
+template <> struct JacCfg<double> { static constexpr int GL = 4, RPL = 32, GLG = 8; };
+template <> struct JacCfg<zc> { static constexpr int GL = 8, RPL = 16, GLG = 8; };
 
 template <class T>
 __global__ void colnorm_kernel(const T* __restrict__ X, int m, int n, int64_t ldx, int64_t bX, double* __restrict__ norms,
@@ -197,23 +247,30 @@ int jacobi_orth(T* X, int m, int n, int64_t ldx, double* norms, int batch, int64
   if (n <= 0 || m <= 0 || batch <= 0) return 0;
   // rotation threshold |x_p^H x_q| <= tol ||x_p|| ||x_q||: m·eps is the rounding level of the computed inner product
   const double tol = (double)std::max(m, 8) * 1.1102230246251565e-16;
-  const size_t budget = 220 * 1024;
-  auto kern = jacobi_kernel<T>;
+  const size_t budget = 216 * 1024;
+  typedef JacCfg<T> Cfg;
+  // rows-per-lane specialisation: columns of up to GL*RPL = 128 rows live in registers during a rotation
+  const bool regs = m <= Cfg::GL * Cfg::RPL;
+  const bool fullm = m == Cfg::GL * Cfg::RPL;
+  auto kern = regs ? (fullm ? jacobi_kernel<T, Cfg::GL, Cfg::RPL, true> : jacobi_kernel<T, Cfg::GL, Cfg::RPL, false>)
+                   : jacobi_kernel<T, Cfg::GLG, 0, false>;
   static bool attr_done = false;
   if (!attr_done) {
-    TTN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(224 * 1024)));
+    const int mx = 224 * 1024;
+    TTN_CUDA(cudaFuncSetAttribute(jacobi_kernel<T, Cfg::GL, Cfg::RPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    TTN_CUDA(cudaFuncSetAttribute(jacobi_kernel<T, Cfg::GL, Cfg::RPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    TTN_CUDA(cudaFuncSetAttribute(jacobi_kernel<T, Cfg::GLG, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     attr_done = true;
   }
+  const size_t col_bytes = sizeof(T) * (size_t)(m + (is_cplx<T>::value ? 0 : 4)) + sizeof(double);   // column + its norm
+  const int threads = JAC_T;
   int sweeps_used = 0;
-  const size_t col_bytes = sizeof(T) * (size_t)m;
   ttn_assert(2 * col_bytes <= budget, 2, "jacobi: a column pair does not fit in shared memory");
   if ((size_t)n * col_bytes <= budget) {
     // whole matrix in one SM: iterate to convergence inside the kernel
     int h_grp[2] = {0, -1};
     DevBuf grp(sizeof(int) * 2), dsw(sizeof(int) * batch);
     TTN_CUDA(cudaMemcpyAsync(grp.p, h_grp, sizeof(h_grp), cudaMemcpyHostToDevice, ctx().stream));
-    const int pairs = (n + 1) / 2;
-    int threads = std::min(1024, std::max(64, ((JGL * pairs + 31) / 32) * 32));
     for (int b0 = 0; b0 < batch; b0 += 65535) {
       const int nb = std::min(65535, batch - b0);
       dim3 grid(1, nb);
@@ -232,6 +289,7 @@ int jacobi_orth(T* X, int m, int n, int64_t ldx, double* norms, int batch, int64
     // block Jacobi: blocks of bsz columns, two blocks per CTA
     int bsz = (int)(budget / (2 * col_bytes));
     if (bsz > 32) bsz = 32;
+    ttn_assert(bsz >= 1, 2, "jacobi: a column pair does not fit in shared memory");
     const int nblk = (n + bsz - 1) / bsz;
     const int ne = nblk + (nblk & 1);
     DevBuf dmax(sizeof(unsigned int));
@@ -254,7 +312,6 @@ int jacobi_orth(T* X, int m, int n, int64_t ldx, double* norms, int batch, int64
     TTN_CUDA(cudaMemcpyAsync(gB.p, hB.data(), sizeof(int) * hB.size(), cudaMemcpyHostToDevice, ctx().stream));
     TTN_CUDA(cudaStreamSynchronize(ctx().stream));
     ttn_assert(batch <= 65535, 2, "jacobi: batch too large for the block path");
-    const int threads = std::min(1024, std::max(64, ((JGL * bsz + 31) / 32) * 32));
     for (int sw = 0; sw < JAC_MAX_SWEEPS; ++sw) {
       TTN_CUDA(cudaMemsetAsync(dmax.p, 0, sizeof(unsigned int), ctx().stream));
       for (int st = 0; st < ne; ++st) {

@@ -1,0 +1,261 @@
+# TTNB200.jl — thin `ccall` shim that routes TensorTrainNumerics.jl's hot-path methods to libttn_b200.so.
+#
+# Usage (after `using TensorTrainNumerics`):
+#     include("TTNB200.jl"); using .TTNB200; TTNB200.init!(device = 0)
+#     y = TTNB200.apply(A, x)                          # A * x                     src/tt_operations.jl:101
+#     TTNB200.tt_compress!(ψ, 64; truncerr = 0.0)      # tt_compress!              src/tt_tools.jl:772
+#     x = TTNB200.als_linsolve(A, b, x0; sweep_count = 4)                          # src/solvers/als.jl:161
+#     E, ψ, r_hist = TTNB200.dmrg_eigsolve(H, ψ0; sweep_schedule = [2], rmax_schedule = [64])   # dmrg.jl:501
+# `TTNB200.override!()` re-points the exported reference methods (`*`, `orthogonalize`, `tt_compress!`,
+# `als_linsolve`, `mals_linsolve`, `dmrg_*`, `tdvp`, `tdvp2`) at these implementations.
+#
+# This file cannot be exercised in the build container (no Julia binary); it is kept deliberately thin — every call
+# is (1) upload the cores, (2) one C-ABI call, (3) download — and the Python mirror in ../api.py drives the identical
+# ABI under test, so the only untested code here is the marshalling below.
+module TTNB200
+
+using TensorTrainNumerics
+import TensorTrainNumerics: TTvector, TToperator
+
+const LIB = Ref{String}(joinpath(@__DIR__, "..", "libttn_b200.so"))
+const F64, C128 = Cint(0), Cint(1)
+
+struct TTNError <: Exception
+    code::Int
+    msg::String
+end
+
+function check(status::Cint)
+    status == 0 && return nothing
+    msg = unsafe_string(ccall((:ttn_last_error, LIB[]), Cstring, ()))
+    # status -> the exception the reference throws at the same place (include/ttn_b200.h)
+    status == 1 && throw(AssertionError(msg))        # "Incompatible dimensions"      tt_operations.jl:11,102
+    status == 2 && throw(AssertionError(msg))        # sweeps >= 1, k in 1:N-1         tt_tools.jl:744,773
+    status == 3 && throw(DimensionMismatch(msg))     # "Impossible orthogonalization"  tt_tools.jl:513
+    status == 4 && throw(AssertionError(msg))        # "Sweep schedule error"          dmrg.jl:513
+    throw(ErrorException("libttn_b200: $msg (status $status)"))
+end
+
+init!(; device::Integer = 0) = check(ccall((:ttn_init, LIB[]), Cint, (Cint,), device))
+
+dtype_code(::Type{Float64}) = F64
+dtype_code(::Type{ComplexF64}) = C128
+
+# ---- containers ------------------------------------------------------------------------------------------------
+mutable struct DevTT
+    h::Ptr{Cvoid}
+    function DevTT(h)
+        x = new(h)
+        finalizer(y -> ccall((:ttn_ttv_free, LIB[]), Cint, (Ptr{Cvoid},), y.h), x)
+        return x
+    end
+end
+mutable struct DevTTO
+    h::Ptr{Cvoid}
+    function DevTTO(h)
+        x = new(h)
+        finalizer(y -> ccall((:ttn_tto_free, LIB[]), Cint, (Ptr{Cvoid},), y.h), x)
+        return x
+    end
+end
+
+function upload(x::TTvector{T, M}) where {T <: Union{Float64, ComplexF64}, M}
+    d = x.N
+    dims = collect(Int64, x.ttv_dims)
+    rks = collect(Int64, x.ttv_rks)
+    ot = collect(Int64, x.ttv_ot)
+    cores = [pointer(c) for c in x.ttv_vec]            # dense column-major (n, r_l, r_r): src/tt_tools.jl:25
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve x check(ccall((:ttn_ttv_upload, LIB[]), Cint,
+        (Cint, Cint, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Ptr{Cvoid}}, Cint, Ptr{Ptr{Cvoid}}),
+        dtype_code(T), d, dims, rks, ot, cores, 1, out))
+    return DevTT(out[])
+end
+
+function upload(A::TToperator{T, M}) where {T <: Union{Float64, ComplexF64}, M}
+    d = A.N
+    dims = collect(Int64, A.tto_dims)
+    rks = collect(Int64, A.tto_rks)
+    cores = [pointer(c) for c in A.tto_vec]            # (n, n, R_l, R_r): src/tt_tools.jl:50
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve A check(ccall((:ttn_tto_upload, LIB[]), Cint,
+        (Cint, Cint, Ptr{Int64}, Ptr{Int64}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}),
+        dtype_code(T), d, dims, rks, cores, out))
+    return DevTTO(out[])
+end
+
+function download(x::DevTT)
+    dt, d, b = Ref{Cint}(0), Ref{Cint}(0), Ref{Cint}(0)
+    check(ccall((:ttn_ttv_info, LIB[]), Cint, (Ptr{Cvoid}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}), x.h, dt, d, b))
+    N = Int(d[])
+    T = dt[] == F64 ? Float64 : ComplexF64
+    dims, rks, ot = zeros(Int64, N), zeros(Int64, N + 1), zeros(Int64, N)
+    check(ccall((:ttn_ttv_dims, LIB[]), Cint, (Ptr{Cvoid}, Ptr{Int64}), x.h, dims))
+    check(ccall((:ttn_ttv_ranks, LIB[]), Cint, (Ptr{Cvoid}, Ptr{Int64}), x.h, rks))
+    check(ccall((:ttn_ttv_ot, LIB[]), Cint, (Ptr{Cvoid}, Ptr{Int64}), x.h, ot))
+    vec = [Array{T, 3}(undef, dims[k], rks[k], rks[k + 1]) for k in 1:N]
+    ptrs = [pointer(c) for c in vec]
+    GC.@preserve vec check(ccall((:ttn_ttv_download, LIB[]), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), x.h, ptrs))
+    return TTvector{T, N}(N, vec, Tuple(dims), rks, ot)
+end
+
+# ---- TT algebra ------------------------------------------------------------------------------------------------
+function apply(A::TToperator{T}, x::TTvector{T}) where {T}
+    Ad, xd = upload(A), upload(x)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ttn_apply, LIB[]), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), Ad.h, xd.h, out))
+    return download(DevTT(out[]))
+end
+
+function dot(a::TTvector{T}, b::TTvector{T}) where {T}
+    ad, bd = upload(a), upload(b)
+    buf = zeros(Float64, 2)
+    check(ccall((:ttn_dot, LIB[]), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}), ad.h, bd.h, buf))
+    return T <: Real ? buf[1] : complex(buf[1], buf[2])
+end
+
+function orthogonalize(x::TTvector; i::Int = 1)
+    xd = upload(x)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ttn_orthogonalize, LIB[]), Cint, (Ptr{Cvoid}, Cint, Ptr{Ptr{Cvoid}}), xd.h, i, out))
+    return download(DevTT(out[]))
+end
+
+function tt_compress!(ψ::TTvector, max_bond::Int; truncerr::Real = 0.0, sweeps::Int = 1, verbose::Bool = false)
+    xd = upload(ψ)
+    check(ccall((:ttn_compress, LIB[]), Cint, (Ptr{Cvoid}, Int64, Float64, Cint, Ptr{Float64}, Int64),
+                xd.h, max_bond, truncerr, sweeps, C_NULL, 0))
+    y = download(xd)
+    ψ.ttv_vec = y.ttv_vec          # same object mutated, ttv_ot untouched (src/tt_tools.jl:754-767)
+    ψ.ttv_rks = y.ttv_rks
+    return ψ
+end
+
+# ---- solvers ---------------------------------------------------------------------------------------------------
+# mirrors `ttn_solver_params` (include/ttn_b200.h)
+struct SolverParams
+    N::Cint
+    tol::Cdouble
+    sweep_schedule::Ptr{Int64}
+    n_sweep_schedule::Cint
+    rmax_schedule::Ptr{Int64}
+    n_rmax_schedule::Cint
+    rmax::Int64
+    sweep_count::Cint
+    it_solver::Cint
+    linsolv_maxiter::Cint
+    linsolv_tol::Cdouble
+    itslv_thresh::Cint
+    krylovdim::Cint
+    symmetrize::Cint
+end
+
+function params(; N = 2, tol = 1.0e-12, sweep_schedule = Int64[], rmax_schedule = Int64[], rmax = 0, sweep_count = 2,
+                it_solver = false, linsolv_maxiter = 200, linsolv_tol = 1.0e-6, itslv_thresh = 256, krylovdim = 30,
+                symmetrize = false)
+    ss, rs = collect(Int64, sweep_schedule), collect(Int64, rmax_schedule)
+    p = SolverParams(N, tol, pointer(ss), length(ss), pointer(rs), length(rs), rmax, sweep_count, it_solver,
+                     linsolv_maxiter, linsolv_tol, itslv_thresh, krylovdim, symmetrize)
+    return p, (ss, rs)          # keep the schedule vectors alive for the duration of the call
+end
+
+function _linsolve(sym::Symbol, A, b, x0, p, keep; return_info = false)
+    Ad, bd, xd = upload(A), upload(b), upload(x0)
+    out, res = Ref{Ptr{Cvoid}}(C_NULL), Ref{Float64}(0.0)
+    GC.@preserve keep check(ccall((sym, LIB[]), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{SolverParams}, Ptr{Ptr{Cvoid}}, Ptr{Float64}),
+        Ad.h, bd.h, xd.h, Ref(p), out, return_info ? res : C_NULL))
+    x = download(DevTT(out[]))
+    return return_info ? (x, (; residual = res[])) : x
+end
+
+function als_linsolve(A, b, tt_start; sweep_count = 2, it_solver = false, r_itsolver = 5000, return_info = false)
+    p, keep = params(; sweep_count)
+    return _linsolve(:ttn_als_linsolve, A, b, tt_start, p, keep; return_info)
+end
+
+function mals_linsolve(A, b, tt_start; tol = 1.0e-12, rmax = round(Int, sqrt(prod(tt_start.ttv_dims))), return_info = false)
+    p, keep = params(; tol, rmax)
+    return _linsolve(:ttn_mals_linsolve, A, b, tt_start, p, keep; return_info)
+end
+
+function dmrg_linsolve(A, b, tt_start; sweep_count = 2, N = 2, tol = 1.0e-12, sweep_schedule = [2],
+                       rmax_schedule = [isqrt(prod(tt_start.ttv_dims))], it_solver = true, linsolv_maxiter = 200,
+                       linsolv_tol = max(sqrt(tol), 1.0e-8), itslv_thresh = 256, return_info = false)
+    p, keep = params(; N, tol, sweep_schedule, rmax_schedule, linsolv_maxiter, linsolv_tol, itslv_thresh, symmetrize = true)
+    return _linsolve(:ttn_dmrg_linsolve, A, b, tt_start, p, keep; return_info)
+end
+
+function _eigsolve(sym::Symbol, A, x0, p, keep, cap)
+    Ad, xd = upload(A), upload(x0)
+    out, nE = Ref{Ptr{Cvoid}}(C_NULL), Ref{Cint}(0)
+    E, rh = zeros(Float64, cap), zeros(Int64, cap)
+    GC.@preserve keep check(ccall((sym, LIB[]), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Ref{SolverParams}, Ptr{Ptr{Cvoid}}, Ptr{Float64}, Ptr{Int64}, Cint, Ptr{Cint}),
+        Ad.h, xd.h, Ref(p), out, E, rh, cap, nE))
+    return E[1:nE[]], download(DevTT(out[])), rh[1:nE[]]
+end
+
+function dmrg_eigsolve(A, tt_start; N = 2, tol = 1.0e-12, sweep_schedule = [2],
+                       rmax_schedule = [isqrt(prod(tt_start.ttv_dims))], it_solver = false, linsolv_maxiter = 200,
+                       linsolv_tol = max(sqrt(tol), 1.0e-8), itslv_thresh = 256)
+    @assert length(rmax_schedule) == length(sweep_schedule) "Sweep schedule error"
+    p, keep = params(; N, tol, sweep_schedule, rmax_schedule, linsolv_maxiter, linsolv_tol, itslv_thresh, symmetrize = true)
+    return _eigsolve(:ttn_dmrg_eigsolve, A, tt_start, p, keep, 2 * A.N * (sweep_schedule[end] + 1) + 8)
+end
+
+function mals_eigsolve(A, tt_start; tol = 1.0e-12, sweep_schedule = [2],
+                       rmax_schedule = [round(Int, sqrt(prod(tt_start.ttv_dims)))], it_solver = false,
+                       linsolv_maxiter = 200, linsolv_tol = max(sqrt(tol), 1.0e-8), itslv_thresh = 256)
+    @assert length(rmax_schedule) == length(sweep_schedule) "Sweep schedule error"
+    p, keep = params(; tol, sweep_schedule, rmax_schedule, linsolv_maxiter, linsolv_tol, itslv_thresh)
+    return _eigsolve(:ttn_mals_eigsolve, A, tt_start, p, keep, 2 * A.N * (sweep_schedule[end] + 1) + 8)
+end
+
+# mirrors `ttn_tdvp_params`
+struct TdvpParams
+    two_site::Cint
+    steps::Ptr{Float64}
+    n_steps::Cint
+    normalize::Cint
+    sweeps::Cint
+    imaginary_time::Cint
+    max_bond::Int64
+    truncerr::Cdouble
+    krylovdim::Cint
+    krylov_tol::Cdouble
+    krylov_maxiter::Cint
+end
+
+function _tdvp(two_site, H, u0, steps; normalize = true, sweeps = 1, max_bond = typemax(Int) >> 1, truncerr = 0.0,
+               imaginary_time = false, krylovdim = 30, tol = 1.0e-12, maxiter = 100)
+    Hd, ud = upload(H), upload(u0)
+    st = collect(Float64, steps)
+    p = TdvpParams(two_site, pointer(st), length(st), normalize, sweeps, imaginary_time, max_bond, truncerr, krylovdim, tol, maxiter)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve st check(ccall((:ttn_tdvp, LIB[]), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{TdvpParams}, Ptr{Ptr{Cvoid}}),
+                                Hd.h, ud.h, Ref(p), out))
+    return download(DevTT(out[]))
+end
+tdvp(H, u0, steps::Vector{Float64}; kwargs...) = _tdvp(0, H, u0, steps; kwargs...)
+tdvp2(H, u0, steps::Vector{Float64}; kwargs...) = _tdvp(1, H, u0, steps; kwargs...)
+
+"""Re-point the reference's exported hot-path methods at the B200 implementations."""
+function override!()
+    @eval TensorTrainNumerics begin
+        Base.:*(A::TToperator{T, N}, v::TTvector{T, N}) where {T <: Union{Float64, ComplexF64}, N} = $(apply)(A, v)
+        orthogonalize(x::TTvector{T, N}; i = 1::Int) where {T <: Union{Float64, ComplexF64}, N} = $(orthogonalize)(x; i = i)
+        tt_compress!(ψ::TTvector{T, N}, max_bond::Int; kwargs...) where {T <: Union{Float64, ComplexF64}, N} =
+            $(tt_compress!)(ψ, max_bond; kwargs...)
+        als_linsolve(A::TToperator, b::TTvector, x0::TTvector; kwargs...) = $(als_linsolve)(A, b, x0; kwargs...)
+        mals_linsolve(A::TToperator, b::TTvector, x0::TTvector; kwargs...) = $(mals_linsolve)(A, b, x0; kwargs...)
+        dmrg_linsolve(A::TToperator, b::TTvector, x0::TTvector; kwargs...) = $(dmrg_linsolve)(A, b, x0; kwargs...)
+        dmrg_eigsolve(A::TToperator, x0::TTvector; kwargs...) = $(dmrg_eigsolve)(A, x0; kwargs...)
+        mals_eigsolve(A::TToperator, x0::TTvector; kwargs...) = $(mals_eigsolve)(A, x0; kwargs...)
+        tdvp(H::TToperator, u0::TTvector, steps::Vector{Float64}; kwargs...) = $(tdvp)(H, u0, steps; kwargs...)
+        tdvp2(H::TToperator, u0::TTvector, steps::Vector{Float64}; kwargs...) = $(tdvp2)(H, u0, steps; kwargs...)
+    end
+    return nothing
+end
+
+end # module

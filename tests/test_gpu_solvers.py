@@ -46,7 +46,7 @@ def test_als_linsolve_vs_dense_and_oracle():
     x, info = t.als_linsolve(A, b, x0, sweep_count=6, return_info=True)
     ref = np.linalg.solve(o.tto_to_matrix(A), dv(b))
     assert relerr(dv(x), ref) < 1e-10
-    assert info["residual"] < 1e-10
+    assert info["residual"] < 1e-7    # dot-based norm of the residual TT: sqrt(eps) floor, as in the reference
     # reduced rank: same fixed point as the oracle after the same number of half sweeps
     x0r = o.rand_tt((2,) * d, 2, rng=rng)
     xr = t.als_linsolve(A, b, x0r, sweep_count=8)
@@ -109,7 +109,7 @@ def test_dmrg_linsolve_vs_dense(N):
     x0 = o.rand_tt((2,) * d, 2, rng=rng)
     x, info = t.dmrg_linsolve(A, b, x0, N=N, sweep_schedule=[8], rmax_schedule=[4], linsolv_tol=1e-14, return_info=True)
     ref = np.linalg.solve(o.tto_to_matrix(A), dv(b))
-    assert relerr(dv(x), ref) < 1e-9 and info["residual"] < 1e-9
+    assert relerr(dv(x), ref) < 1e-9 and info["residual"] < 1e-7   # norm(A*x-b) via dot() bottoms out at sqrt(eps), as in the reference
 
 
 @pytest.mark.parametrize("sym", [False, True])
