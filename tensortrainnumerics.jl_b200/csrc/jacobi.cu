@@ -40,34 +40,24 @@ __device__ __forceinline__ void rot_params(double a, double b, double absc, doub
   sn = (d >= 0.0 ? absc : -absc) * rinv;
 }
 
-constexpr int JAC_T = 256;   // threads per CTA
-
-// slot -> column pair of round r.  mode 0: round-robin tournament over ne = nc (+1 dummy) players, no integer
-// division; mode 1: cross pairs between the two column groups (p from group A, q from group B).
-__device__ __forceinline__ bool pair_of_slot(int mode, int i, int r, int ne, int nc, int na, int nb, int nslots, int& p, int& q) {
-  if (mode == 0) {
-    p = r + i; q = r - i;
-    if (p >= ne - 1) p -= ne - 1;
-    if (q < 0) q += ne - 1;
-    if (i == 0) { p = ne - 1; q = r; }
-    return i < nslots && p < nc && q < nc;
-  }
-  p = i;
-  q = i + r;
-  if (q >= nslots) q -= nslots;
-  const bool act = i < nslots && p < na && q < nb;
-  q += na;
-  return act;
-}
+constexpr int JAC_T = 256;   // threads per CTA (measured: 256 thr x 4 lanes per pair beats 512 x 8 and 1024 x 16 on B200)
 
 // One-sided Jacobi on a group of columns staged in shared memory (column pitch m+PADC keeps the strided row
-// accesses of neighbouring lane groups on distinct banks).  One block barrier per round.  A group of GL lanes owns a
-// column pair: it loads its rows of both columns into registers (RPL rows per lane; RPL == 0: generic length, rows
-// re-read from shared memory), reduces the inner product with GL-wide shuffles, turns (||x_p||^2, ||x_q||^2, c) into the
-// plane rotation (rot_params: no division) and applies it from the registers.  The squared column norms are
-// maintained in shared memory by the rotation identities and recomputed exactly at the start of every sweep.
+// accesses of neighbouring lane groups on distinct banks).
+//
+// Ordering.  A sweep over nc columns is organised as log2(npad) *levels* of a recursive halving (npad = nc rounded up
+// to a power of two): at the level with half-size h the columns are split into blocks of 2h, and within each block
+// every column a of the first half meets every column q of the second half, h rounds of npad/2 disjoint pairs
+// (a = block + j, q = block + h + (j + r) mod h).  Summed over the levels h = npad/2, ..., 1 this is npad-1 rounds and
+// every pair exactly once — the same count as a round-robin tournament — but the a-column of a lane group is
+// *stationary* for a whole level: it is loaded into registers once per level and only the moving q-column goes
+// through shared memory, which halves the shared-memory traffic that bounds this kernel.
+// mode 1 (block Jacobi across CTAs): a single level of cross pairs between column groups A (stationary) and B.
+//
+// A group of GL lanes owns a pair: RPL rows of both columns per lane in registers (RPL == 0: generic length, rows
+// re-read from shared memory), inner product reduced with GL-wide shuffles, plane rotation by rot_params (no
+// division), squared column norms maintained by the rotation identities and recomputed exactly once per sweep.
 // With GL = 4 a warp carries 8 pairs, so the scalar rotation set-up is amortised over 8 pairs per warp instruction.
-// mode 0: all pairs among the na+nb columns; mode 1: cross pairs (one column from each group) only.
 // full != 0: iterate sweeps until a whole sweep applies no rotation (single-CTA problem), else run `sweeps` sweeps.
 template <class T, int GL, int RPL, bool FULLM>
 __global__ void __launch_bounds__(JAC_T) jacobi_kernel(T* __restrict__ X, int m, int64_t ldx, int64_t bX,
@@ -77,6 +67,7 @@ __global__ void __launch_bounds__(JAC_T) jacobi_kernel(T* __restrict__ X, int m,
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_rot;
   constexpr int PADC = is_cplx<T>::value ? 0 : 4;
+  constexpr int NR = RPL > 0 ? RPL : 1;
   T* Xb = X + blockIdx.y * bX;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int grp = tid / GL, ngrp = blockDim.x / GL, gl = tid % GL;
@@ -89,9 +80,9 @@ __global__ void __launch_bounds__(JAC_T) jacobi_kernel(T* __restrict__ X, int m,
   const int b0 = gb >= 0 ? gb * bsz : 0;
   const int nb = gb >= 0 ? min(bsz, n - b0) : 0;
   const int nc = na + nb;
-  const int ne = nc + (nc & 1);
-  const int nslots = (mode == 0) ? ne / 2 : max(na, nb);
-  const int nrounds = (mode == 0) ? ne - 1 : nslots;
+  int npad = 2;
+  while (npad < nc) npad <<= 1;
+  const int bm = max(na, nb);
 
   T* Xs = reinterpret_cast<T*>(smem_raw);                            // [nc][pitch]
   double* nrm2 = reinterpret_cast<double*>(Xs + (size_t)nc * pitch);   // [nc]
@@ -117,75 +108,103 @@ __global__ void __launch_bounds__(JAC_T) jacobi_kernel(T* __restrict__ X, int m,
     }
     __syncthreads();
     bool myrot = false;
-    for (int r = 0; r < nrounds; ++r) {
-      for (int i0 = 0; i0 < nslots; i0 += ngrp) {   // warp-uniform trip count (the shuffles need every lane)
+    // levels: mode 0 -> h = npad/2, npad/4, ..., 1 ; mode 1 -> the single cross level h = bm
+    for (int h = (mode == 0 ? npad / 2 : bm); h >= 1; h = (mode == 0 ? h >> 1 : 0)) {
+      const int nslots = (mode == 0) ? npad / 2 : bm;
+      for (int i0 = 0; i0 < nslots; i0 += ngrp) {   // passes; warp-uniform trip counts (shuffles + barriers inside)
         const int i = i0 + grp;
-        int p, q;
-        const bool act = pair_of_slot(mode, i, r, ne, nc, na, nb, nslots, p, q);
-        T* xp = Xs + (act ? p : 0) * pitch;
-        T* xq = Xs + (act ? q : 0) * pitch;
-        T rp[RPL > 0 ? RPL : 1], rq[RPL > 0 ? RPL : 1];
-        T c = t_zero<T>();
+        int a, j, qbase;
+        if (mode == 0) { j = i & (h - 1); a = ((i - j) << 1) + j; qbase = a - j + h; }
+        else { j = i; a = i; qbase = na; }
+        const bool actA = i < nslots && a < (mode == 0 ? nc : na);
+        T* xa = Xs + (actA ? a : 0) * pitch;
+        T ra[NR];
+        double an = actA ? nrm2[a] : 0.0;
         if (RPL > 0) {
-          // (inactive groups read column 0: harmless, their result is discarded; keeps the loads unpredicated)
 #pragma unroll
           for (int k = 0; k < RPL; ++k) {
             const int row = gl + k * GL;
-            const bool ok = FULLM || row < m;
-            rp[k] = ok ? xp[row] : t_zero<T>();
-            rq[k] = ok ? xq[row] : t_zero<T>();
+            ra[k] = (FULLM || row < m) ? xa[row] : t_zero<T>();
           }
-          T c4[4] = {t_zero<T>(), t_zero<T>(), t_zero<T>(), t_zero<T>()};   // independent accumulation chains
+        }
+        for (int r = 0; r < h; ++r) {
+          int jq = j + r;
+          if (jq >= h) jq -= h;
+          const int q = qbase + jq;
+          const bool act = actA && q < (mode == 0 ? nc : na + nb);
+          T* xq = Xs + (act ? q : 0) * pitch;
+          T rq[NR];
+          T c = t_zero<T>();
+          if (RPL > 0) {
+            // (inactive groups read column 0: harmless, the result is discarded; keeps the loads unpredicated)
 #pragma unroll
-          for (int k = 0; k < RPL; ++k) t_fma(c4[k & 3], t_conj(rp[k]), rq[k]);
-          c = t_add(t_add(c4[0], c4[1]), t_add(c4[2], c4[3]));
-        } else if (act) {
-          for (int row = gl; row < m; row += GL) t_fma(c, t_conj(xp[row]), xq[row]);
-        }
-        double cr = t_real(c), ci = t_imag(c);
+            for (int k = 0; k < RPL; ++k) {
+              const int row = gl + k * GL;
+              rq[k] = (FULLM || row < m) ? xq[row] : t_zero<T>();
+            }
+            T c4[4] = {t_zero<T>(), t_zero<T>(), t_zero<T>(), t_zero<T>()};   // independent accumulation chains
 #pragma unroll
-        for (int o = GL / 2; o > 0; o >>= 1) {
-          cr += __shfl_xor_sync(0xffffffffu, cr, o);
-          if (is_cplx<T>::value) ci += __shfl_xor_sync(0xffffffffu, ci, o);
-        }
-        if (!act) continue;
-        const double a = nrm2[p], b = nrm2[q];
-        const double c2 = cr * cr + ci * ci;
-        if (!(c2 > tol2 * a * b)) continue;        // also skips zero columns and NaNs
-        double cs, sn, absc, phr, phi;
-        if (is_cplx<T>::value) {
-          const double inv = rsqrt(c2);
-          absc = c2 * inv; phr = cr * inv; phi = ci * inv;
-        } else {
-          absc = fabs(cr); phr = cr >= 0.0 ? 1.0 : -1.0; phi = 0.0;
-        }
-        rot_params(a, b, absc, cs, sn);
-        if (gl == 0) {
-          const double x = 2.0 * cs * sn * absc;
-          nrm2[p] = fmax(cs * cs * a - x + sn * sn * b, 0.0);
-          nrm2[q] = fmax(sn * sn * a + x + cs * cs * b, 0.0);
-        }
-        myrot = true;
-        const T ph = t_from<T>(sn * phr, sn * phi);      // sn * phase
-        const T phc = t_from<T>(sn * phr, -sn * phi);    // sn * conj(phase)
-        if (RPL > 0) {
+            for (int k = 0; k < RPL; ++k) t_fma(c4[k & 3], t_conj(ra[k]), rq[k]);
+            c = t_add(t_add(c4[0], c4[1]), t_add(c4[2], c4[3]));
+          } else if (act) {
+            for (int row = gl; row < m; row += GL) t_fma(c, t_conj(xa[row]), xq[row]);
+          }
+          double cr = t_real(c), ci = t_imag(c);
 #pragma unroll
-          for (int k = 0; k < RPL; ++k) {
-            const int row = gl + k * GL;
-            if (FULLM || row < m) {
-              xp[row] = t_sub(t_scale(rp[k], cs), t_mul(phc, rq[k]));
-              xq[row] = t_add(t_mul(ph, rp[k]), t_scale(rq[k], cs));
+          for (int o = GL / 2; o > 0; o >>= 1) {
+            cr += __shfl_xor_sync(0xffffffffu, cr, o);
+            if (is_cplx<T>::value) ci += __shfl_xor_sync(0xffffffffu, ci, o);
+          }
+          if (act) {
+            const double b = nrm2[q];
+            const double c2 = cr * cr + ci * ci;
+            if (c2 > tol2 * an * b) {              // false for zero columns and NaNs
+              double cs, sn, absc, phr, phi;
+              if (is_cplx<T>::value) {
+                const double inv = rsqrt(c2);
+                absc = c2 * inv; phr = cr * inv; phi = ci * inv;
+              } else {
+                absc = fabs(cr); phr = cr >= 0.0 ? 1.0 : -1.0; phi = 0.0;
+              }
+              rot_params(an, b, absc, cs, sn);
+              const double x = 2.0 * cs * sn * absc;
+              const double an_new = fmax(cs * cs * an - x + sn * sn * b, 0.0);
+              if (gl == 0) nrm2[q] = fmax(sn * sn * an + x + cs * cs * b, 0.0);
+              an = an_new;
+              myrot = true;
+              const T ph = t_from<T>(sn * phr, sn * phi);      // sn * phase
+              const T phc = t_from<T>(sn * phr, -sn * phi);    // sn * conj(phase)
+              if (RPL > 0) {
+#pragma unroll
+                for (int k = 0; k < RPL; ++k) {
+                  const int row = gl + k * GL;
+                  const T pv = ra[k], qv = rq[k];
+                  ra[k] = t_sub(t_scale(pv, cs), t_mul(phc, qv));
+                  if (FULLM || row < m) xq[row] = t_add(t_mul(ph, pv), t_scale(qv, cs));
+                }
+              } else {
+                for (int row = gl; row < m; row += GL) {
+                  const T pv = xa[row], qv = xq[row];
+                  xa[row] = t_sub(t_scale(pv, cs), t_mul(phc, qv));
+                  xq[row] = t_add(t_mul(ph, pv), t_scale(qv, cs));
+                }
+              }
             }
           }
-        } else {
-          for (int row = gl; row < m; row += GL) {
-            const T pv = xp[row], qv = xq[row];
-            xp[row] = t_sub(t_scale(pv, cs), t_mul(phc, qv));
-            xq[row] = t_add(t_mul(ph, pv), t_scale(qv, cs));
-          }
+          __syncthreads();
         }
+        if (actA) {
+          if (RPL > 0) {
+#pragma unroll
+            for (int k = 0; k < RPL; ++k) {
+              const int row = gl + k * GL;
+              if (FULLM || row < m) xa[row] = ra[k];
+            }
+          }
+          if (gl == 0) nrm2[a] = an;
+        }
+        __syncthreads();
       }
-      __syncthreads();
     }
     if (myrot) s_rot = 1;       // benign race: every writer stores the same value
     __syncthreads();
@@ -206,6 +225,119 @@ __global__ void __launch_bounds__(JAC_T) jacobi_kernel(T* __restrict__ X, int m,
     if (d_rotated && any_rot) atomicOr(d_rotated, 1u);
     if (d_sweeps && full) d_sweeps[blockIdx.y] = sw;
   }
+}
+
+// Block Jacobi across CTAs for matrices that do not fit in one SM's shared memory (DMRG / MALS bond matrices of
+// order 512 ... 4096).  One CTA = one pair of column blocks (A, B) and all na*nb cross pairs between them:
+//   - the B block is staged in shared memory together with its maintained squared norms;
+//   - the A block is processed in passes of one column per warp: the warp keeps its whole A column in registers
+//     (RPLA rows per lane, m <= 32*RPLA), so a rotation streams the B column twice (inner product, update) and the A
+//     column never leaves the register file until the pass ends;
+//   - at round r warp w meets B column (w + r) mod R with R = max(nb, #warps): all warps touch distinct columns,
+//     one block barrier per round.
+// Squared norms of both blocks are recomputed exactly when the blocks are loaded.
+template <class T, int RPLA>
+__global__ void __launch_bounds__(JAC_T) jacobi_cross_kernel(T* __restrict__ X, int m, int64_t ldx, int64_t bX,
+                                                             const int* __restrict__ grpA, const int* __restrict__ grpB,
+                                                             int bsz, int n, double tol, unsigned int* __restrict__ d_rotated) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* Xb = X + blockIdx.y * bX;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = JAC_T / 32;
+  const double tol2 = tol * tol;
+  const int a0 = grpA[blockIdx.x] * bsz, na = min(bsz, n - a0);
+  const int b0 = grpB[blockIdx.x] * bsz, nb = min(bsz, n - b0);
+  const int pitch = m + (is_cplx<T>::value ? 0 : 4);
+  T* Bs = reinterpret_cast<T*>(smem_raw);                             // [nb][pitch]
+  double* nrmB = reinterpret_cast<double*>(Bs + (size_t)nb * pitch);    // [nb]
+
+  for (int c = warp; c < nb; c += NW) {
+    const T* src = Xb + (int64_t)(b0 + c) * ldx;
+    T* dst = Bs + (size_t)c * pitch;
+    double s = 0.0;
+    for (int i = lane; i < m; i += 32) { const T v = src[i]; dst[i] = v; s += t_abs2(v); }
+    s = wsumd(s);
+    if (lane == 0) nrmB[c] = s;
+  }
+  __syncthreads();
+
+  bool myrot = false;
+  const int R = max(nb, NW);
+  for (int ap = 0; ap < na; ap += NW) {
+    const int a = ap + warp;
+    const bool actA = a < na;
+    T* ga = Xb + (int64_t)(a0 + (actA ? a : 0)) * ldx;
+    T ra[RPLA];
+    double an = 0.0;
+#pragma unroll
+    for (int k = 0; k < RPLA; ++k) {
+      const int row = lane + 32 * k;
+      ra[k] = (actA && row < m) ? ga[row] : t_zero<T>();
+      an += t_abs2(ra[k]);
+    }
+    an = wsumd(an);
+    for (int r = 0; r < R; ++r) {
+      int bq = warp + r;
+      if (bq >= R) bq -= R;
+      const bool act = actA && bq < nb;
+      T* xq = Bs + (size_t)(act ? bq : 0) * pitch;
+      T c4[4] = {t_zero<T>(), t_zero<T>(), t_zero<T>(), t_zero<T>()};
+      if (act) {
+#pragma unroll
+        for (int k = 0; k < RPLA; ++k) {
+          const int row = lane + 32 * k;
+          if (row < m) t_fma(c4[k & 3], t_conj(ra[k]), xq[row]);
+        }
+      }
+      const T c = t_add(t_add(c4[0], c4[1]), t_add(c4[2], c4[3]));
+      const double cr = wsumd(t_real(c));
+      const double ci = is_cplx<T>::value ? wsumd(t_imag(c)) : 0.0;
+      if (act) {
+        const double b = nrmB[bq];
+        const double c2 = cr * cr + ci * ci;
+        if (c2 > tol2 * an * b) {
+          double cs, sn, absc, phr, phi;
+          if (is_cplx<T>::value) {
+            const double inv = rsqrt(c2);
+            absc = c2 * inv; phr = cr * inv; phi = ci * inv;
+          } else {
+            absc = fabs(cr); phr = cr >= 0.0 ? 1.0 : -1.0; phi = 0.0;
+          }
+          rot_params(an, b, absc, cs, sn);
+          const double x = 2.0 * cs * sn * absc;
+          if (lane == 0) nrmB[bq] = fmax(sn * sn * an + x + cs * cs * b, 0.0);
+          an = fmax(cs * cs * an - x + sn * sn * b, 0.0);
+          myrot = true;
+          const T ph = t_from<T>(sn * phr, sn * phi);
+          const T phc = t_from<T>(sn * phr, -sn * phi);
+#pragma unroll
+          for (int k = 0; k < RPLA; ++k) {
+            const int row = lane + 32 * k;
+            if (row < m) {
+              const T pv = ra[k], qv = xq[row];
+              ra[k] = t_sub(t_scale(pv, cs), t_mul(phc, qv));
+              xq[row] = t_add(t_mul(ph, pv), t_scale(qv, cs));
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+    if (actA) {
+#pragma unroll
+      for (int k = 0; k < RPLA; ++k) {
+        const int row = lane + 32 * k;
+        if (row < m) ga[row] = ra[k];
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = warp; c < nb; c += NW) {
+    T* dst = Xb + (int64_t)(b0 + c) * ldx;
+    const T* src = Bs + (size_t)c * pitch;
+    for (int i = lane; i < m; i += 32) dst[i] = src[i];
+  }
+  if (myrot && lane == 0 && d_rotated) atomicOr(d_rotated, 1u);
 }
 
 template <class T> struct JacCfg;
@@ -286,10 +418,25 @@ int jacobi_orth(T* X, int m, int n, int64_t ldx, double* norms, int batch, int64
     TTN_CUDA(cudaStreamSynchronize(ctx().stream));
     sweeps_used = hsw;
   } else {
-    // block Jacobi: blocks of bsz columns, two blocks per CTA
-    int bsz = (int)(budget / (2 * col_bytes));
+    // block Jacobi across CTAs.  Fast path (m <= 32*RPLA): blocks of #warps columns, cross steps on
+    // jacobi_cross_kernel (A block in registers, B block in shared memory); generic path: two blocks per CTA in
+    // shared memory on jacobi_kernel.
+    constexpr int RPLA_S = is_cplx<T>::value ? 16 : 32, RPLA_L = is_cplx<T>::value ? 32 : 64;
+    const bool fast = m <= 32 * RPLA_L;
+    const bool small_rows = m <= 32 * RPLA_S;
+    int bsz = fast ? JAC_T / 32 : (int)(budget / (2 * col_bytes));
     if (bsz > 32) bsz = 32;
     ttn_assert(bsz >= 1, 2, "jacobi: a column pair does not fit in shared memory");
+    if (fast) {
+      static bool cattr = false;
+      if (!cattr) {
+        const int mx = 224 * 1024;
+        TTN_CUDA(cudaFuncSetAttribute(jacobi_cross_kernel<T, RPLA_S>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        TTN_CUDA(cudaFuncSetAttribute(jacobi_cross_kernel<T, RPLA_L>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        cattr = true;
+      }
+      ttn_assert((size_t)bsz * col_bytes <= budget, 2, "jacobi: block does not fit in shared memory");
+    }
     const int nblk = (n + bsz - 1) / bsz;
     const int ne = nblk + (nblk & 1);
     DevBuf dmax(sizeof(unsigned int));
@@ -312,16 +459,25 @@ int jacobi_orth(T* X, int m, int n, int64_t ldx, double* norms, int batch, int64
     TTN_CUDA(cudaMemcpyAsync(gB.p, hB.data(), sizeof(int) * hB.size(), cudaMemcpyHostToDevice, ctx().stream));
     TTN_CUDA(cudaStreamSynchronize(ctx().stream));
     ttn_assert(batch <= 65535, 2, "jacobi: batch too large for the block path");
+    auto gen = jacobi_kernel<T, Cfg::GLG, 0, false>;
     for (int sw = 0; sw < JAC_MAX_SWEEPS; ++sw) {
       TTN_CUDA(cudaMemsetAsync(dmax.p, 0, sizeof(unsigned int), ctx().stream));
       for (int st = 0; st < ne; ++st) {
         const int cnt = off[st + 1] - off[st];
         if (cnt <= 0) continue;
         dim3 grid(cnt, batch);
-        const size_t smem = (size_t)(st == 0 ? 1 : 2) * bsz * col_bytes;
         ProfScope prof_scope_(KF_JACOBI);
-        kern<<<grid, threads, smem, ctx().stream>>>(X, m, ldx, bX, gA.as<int>() + off[st], gB.as<int>() + off[st], bsz, n,
-                                                   st == 0 ? 0 : 1, 0, 1, tol, dmax.as<unsigned int>(), nullptr);
+        if (st == 0 || !fast) {
+          const size_t smem = (size_t)(st == 0 ? 1 : 2) * bsz * col_bytes;
+          gen<<<grid, threads, smem, ctx().stream>>>(X, m, ldx, bX, gA.as<int>() + off[st], gB.as<int>() + off[st], bsz, n,
+                                                    st == 0 ? 0 : 1, 0, 1, tol, dmax.as<unsigned int>(), nullptr);
+        } else if (small_rows) {
+          jacobi_cross_kernel<T, RPLA_S><<<grid, threads, (size_t)bsz * col_bytes, ctx().stream>>>(
+              X, m, ldx, bX, gA.as<int>() + off[st], gB.as<int>() + off[st], bsz, n, tol, dmax.as<unsigned int>());
+        } else {
+          jacobi_cross_kernel<T, RPLA_L><<<grid, threads, (size_t)bsz * col_bytes, ctx().stream>>>(
+              X, m, ldx, bX, gA.as<int>() + off[st], gB.as<int>() + off[st], bsz, n, tol, dmax.as<unsigned int>());
+        }
         TTN_CHECK_LAUNCH();
         ctx().launches++;
       }
