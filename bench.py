@@ -222,7 +222,18 @@ def run_ours(args, rank, local_rank, world):
     dist = None
     if world > 1:
         import torch.distributed as dist_
-        dist_.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL may print its version banner on stdout: keep stdout clean for the single JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist_.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist_.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
         dist = dist_
     K, W = args.steps, args.warmup
     cores, rks, keep = make_cfg2(pinned=True)
@@ -309,10 +320,21 @@ def run_ours(args, rank, local_rank, world):
                 "note": "cfg2 is a 78-step dependency chain on bond-sized matrices: latency bound, not roofline bound "
                         "(SURVEY.md §8(d)-2)"}
 
-    # ---- extras: two-site effective-operator matvec at cfg4 shapes --------------------------------------------
+    # ---- extras: the other components of BASELINE.json's metric ---------------------------------------------------
     extras = {}
-    if rank == 0 and not args.no_extras:
-        extras["matvec_cfg4"] = bench_matvec(t, torch, stream, peak64)
+    if not args.no_extras:
+        # cfg5 (sharded over the ranks, no collective): batched ComplexF64 apply + tt_compress!
+        bt = bench_batch(t, rank, args.batch_vectors)
+        if dist is not None:
+            tm = torch.tensor([bt["seconds"]], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            bt["seconds"] = float(tm.item())
+        bt["value"] = world * bt["vectors_per_rank"] / bt["seconds"]
+        bt["n_gpus"] = world
+        extras["batch_cfg5"] = bt
+        if rank == 0:
+            extras["matvec_cfg4"] = bench_matvec(t, torch, stream, peak64)
+            extras["dmrg_sweep"] = bench_dmrg(t, args.dmrg_chi)
 
     line = None
     if rank == 0:
@@ -381,6 +403,52 @@ def bench_matvec(t, torch, stream, peak64, chi=1024, w=5, nn=4, reps=10):
             "note": "working set 0.5 GB > L2; back-to-back applications"}
 
 
+def bench_batch(t, rank, nvec, d=30, r=64, W=4):
+    """cfg5: `nvec` independent ComplexF64 QTT vectors per rank (d=30, rank 64) through y = A*x (MPO rank W) and
+    tt_compress!(y, 64); inputs resident in HBM."""
+    rks = [min(2 ** k, 2 ** (d - k), r) for k in range(d + 1)]
+    Rk = [min(4 ** k, 4 ** (d - k), W) for k in range(d + 1)]
+    rng = np.random.default_rng(7)
+    A = t.TToperator(d, [np.asfortranarray((rng.standard_normal((2, 2, Rk[k], Rk[k + 1])) + 1j * rng.standard_normal((2, 2, Rk[k], Rk[k + 1])))
+                                           / math.sqrt(2.0 * Rk[k + 1])) for k in range(d)], (2,) * d, Rk)
+    Ad = t.DeviceTTO.upload(A)
+    g = np.random.default_rng(100 + rank)
+    cores = []
+    for k in range(d):
+        shp = (2, rks[k], rks[k + 1], nvec)
+        cores.append(np.asfortranarray((g.standard_normal(shp) + 1j * g.standard_normal(shp)) / math.sqrt(4.0 * rks[k + 1])))
+    xs = [t.TTvector(d, [c[..., b] for c in cores], (2,) * d, rks) for b in range(nvec)]
+    xd = t.DeviceTT.upload(xs)
+    t.tt_compress_(t.apply(Ad, xd), r)
+    t.synchronize()
+    t0 = time.perf_counter()
+    y = t.tt_compress_(t.apply(Ad, xd), r)
+    t.synchronize()
+    el = time.perf_counter() - t0
+    return {"metric": "batched apply+round vectors/s", "unit": "vectors/s", "vectors_per_rank": nvec, "seconds": el, "d": d,
+            "rank": r, "W": W, "dtype": "c128", "out_max_rank": int(max(y.ttv_rks)),
+            "sharding": "vectors split evenly over the ranks, no data-path collective"}
+
+
+def bench_dmrg(t, chi, L=64, kd=8):
+    """cfg4-style DMRG sweep: Heisenberg XYZ chain L=64 (MPO rank 5), one full two-site sweep from a random TT capped at
+    bond `chi`, fixed Lanczos budget (krylovdim 8 x 1 restart) as in SURVEY.md §8(d)-4."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import dmrg_bench
+    H = t.DeviceTTO.upload(dmrg_bench.heisenberg(L))
+    x0 = t.DeviceTT.upload(dmrg_bench.rand_tt(L, chi))
+    t.synchronize()
+    t.reset_launch_count()
+    t0 = time.perf_counter()
+    E, x, rh = t.dmrg_eigsolve(H, x0, N=2, tol=1e-12, sweep_schedule=[2], rmax_schedule=[chi], linsolv_maxiter=1,
+                               linsolv_tol=1e-10, krylovdim=kd)
+    t.synchronize()
+    el = time.perf_counter() - t0
+    return {"metric": "DMRG sweep s", "value": el, "unit": "s", "L": L, "chi": chi, "krylovdim": kd, "bond_steps": len(E),
+            "max_rank": int(max(rh)), "E_last": float(E[-1]), "gpu_launches": int(t.launch_count()),
+            "note": "BASELINE.json cfg4 is chi=1024; run with --dmrg-chi 1024 for the full-size sweep"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -388,7 +456,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
-    ap.add_argument("--no-extras", action="store_true", help="skip the cfg4 matvec extra")
+    ap.add_argument("--no-extras", action="store_true", help="skip the cfg4 matvec / DMRG sweep / cfg5 batch extras")
+    ap.add_argument("--dmrg-chi", type=int, default=256, help="bond cap of the DMRG sweep extra (cfg4 is 1024)")
+    ap.add_argument("--batch-vectors", type=int, default=128, help="cfg5 vectors per rank in the batch extra")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--rank", type=int, default=64)
     ap.add_argument("--W", type=int, default=4)
     ap.add_argument("--check", action="store_true", help="verify one vector per rank against the oracle")
+    ap.add_argument("--profile", action="store_true", help="per-kernel-family CUDA-event timing")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -71,12 +72,18 @@ def main():
     if dist is not None:
         dist.barrier()
     t.reset_launch_count()
+    if args.profile:
+        t.profile(True)
     t0 = time.perf_counter()
     for c in range(nchunks):
         y = t.tt_compress_(t.apply(Ad, xd), r)
     t.synchronize()
     el = time.perf_counter() - t0
     launches = t.launch_count()
+    fam = None
+    if args.profile:
+        fam = {k: round(v[0], 1) for k, v in t.profile_read().items()}
+        t.profile(False)
     if dist is not None:
         tm = torch.tensor([el], device="cuda", dtype=torch.float64)
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
@@ -93,7 +100,7 @@ def main():
         per_vec_gflop = 13.3 * (d / 30.0)
         print(json.dumps({"metric": "batched apply+round vectors/s", "value": done / el, "unit": "vectors/s", "n_gpus": world,
                           "vectors": done, "chunk": chunk, "seconds": el, "d": d, "rank": r, "W": W, "dtype": "c128",
-                          "gpu_launches": launches, "parity_rel_distance": ok,
+                          "gpu_launches": launches, "parity_rel_distance": ok, "family_ms": fam,
                           "approx_tflops": done * per_vec_gflop / el / 1e3}), flush=True)
     if dist is not None:
         dist.barrier()
