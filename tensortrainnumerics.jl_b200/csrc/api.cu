@@ -48,6 +48,8 @@ int ttn_init(int device) {
     TTN_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t thr = UINT64_MAX;
     TTN_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    c.use_cluster_jacobi = getenv("TTN_NO_CLUSTER_JACOBI") == nullptr;
+    c.use_gram_jacobi = getenv("TTN_NO_GRAM_JACOBI") == nullptr;
     c.inited = true;
   }
   API_END

@@ -398,7 +398,13 @@ int jacobi_orth(T* X, int m, int n, int64_t ldx, double* norms, int batch, int64
   const int threads = JAC_T;
   int sweeps_used = 0;
   ttn_assert(2 * col_bytes <= budget, 2, "jacobi: a column pair does not fit in shared memory");
-  if ((size_t)n * col_bytes <= budget) {
+  DevBuf dsw_cl(sizeof(int) * batch);
+  if (ctx().use_cluster_jacobi && jacobi_cluster<T>(X, m, n, ldx, batch, bX, tol, dsw_cl.as<int>())) {
+    int hsw = 0;
+    TTN_CUDA(cudaMemcpyAsync(&hsw, dsw_cl.p, sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
+    TTN_CUDA(cudaStreamSynchronize(ctx().stream));
+    sweeps_used = hsw;
+  } else if ((size_t)n * col_bytes <= budget) {
     // whole matrix in one SM: iterate to convergence inside the kernel
     int h_grp[2] = {0, -1};
     DevBuf grp(sizeof(int) * 2), dsw(sizeof(int) * batch);

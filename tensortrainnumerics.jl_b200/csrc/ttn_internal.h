@@ -55,6 +55,8 @@ struct Context {
   bool prof_on = false;    // per-kernel-family CUDA-event timing (bench.py roofline pass only)
   std::vector<ProfRec> prof;
   int last_jacobi_sweeps = 0;  // diagnostics: sweeps used by the most recent Jacobi SVD (batch element 0)
+  bool use_cluster_jacobi = true;   // single-matrix SVDs on an 8-SM cluster (TTN_NO_CLUSTER_JACOBI=1 disables; A/B timing)
+  bool use_gram_jacobi = true;      // Gram-block Jacobi (DMMA) for large matrices (TTN_NO_GRAM_JACOBI=1 disables)
 };
 Context& ctx();
 // brackets the launches of one kernel family with CUDA events on the library stream when profiling is enabled
@@ -208,6 +210,8 @@ template <class T> void qr_form_q(const T* A, int m, int k, int64_t lda, const T
 // (unsorted singular values) are written to norms[n] (device).  Returns the number of sweeps used.
 template <class T> int jacobi_orth(T* X, int m, int n, int64_t ldx, double* norms, int batch = 1, int64_t bX = 0,
                                    int64_t bnorms = 0);
+// single-matrix path on an 8-CTA cluster (jacobi_cluster.cu); false if the shape is not served
+template <class T> bool jacobi_cluster(T* X, int m, int n, int64_t ldx, int batch, int64_t bX, double tol, int* d_sweeps);
 // dst (m x r) column j = X[:, perm[j]] * scale[j]   (perm/scale device arrays; per batch strides)
 template <class T> void gather_cols(const T* X, int m, int64_t ldx, const int* perm, const double* scale, int r, T* dst,
                                     int64_t rs, int64_t cs, int batch = 1, int64_t bX = 0, int64_t bperm = 0,
