@@ -23,10 +23,10 @@ namespace cg = cooperative_groups;
 namespace ttn {
 namespace {
 
-constexpr int CL = 8;              // CTAs per cluster (portable maximum)
 constexpr int JC_MAX_SWEEPS = 40;
 
 // destination (cta, slot) of block slot (c, top?) after one block step of the circle method
+template <int CL>
 __device__ __forceinline__ void next_slot(int c, bool top, int& dc, bool& dtop) {
   if (top) {
     if (c == 0) { dc = 0; dtop = true; }
@@ -87,11 +87,11 @@ __device__ __forceinline__ int rotate_pair(T (&rp)[RPL], T (&rq)[RPL], double& a
 }
 
 // writes local column j (registers) into the shared memory of the CTA that owns it in the next block step
-template <class T, int GL, int RPL>
+template <class T, int CL, int GL, int RPL>
 __device__ __forceinline__ void send_column(cg::cluster_group& cluster, T* cols, double* nrm, int crank, int j, int W, int nxt,
                                             int ncl, int pitch, int gl, const T (&rc)[RPL], double nv) {
   int dc; bool dtop;
-  next_slot(crank, j < W, dc, dtop);
+  next_slot<CL>(crank, j < W, dc, dtop);
   const int dj = (dtop ? 0 : W) + (j < W ? j : j - W);
   T* dst = cluster.map_shared_rank(cols, dc) + ((size_t)nxt * ncl + dj) * pitch + gl;
 #pragma unroll
@@ -99,7 +99,10 @@ __device__ __forceinline__ void send_column(cg::cluster_group& cluster, T* cols,
   if (gl == 0) *(cluster.map_shared_rank(nrm, dc) + nxt * ncl + dj) = nv;
 }
 
-template <class T, int GL, int RPL>
+// DB: double-buffered column storage (one cluster barrier per block step; remote stores land in the other buffer) —
+// the latency-optimal form for a single matrix.  !DB: single buffer, an extra cluster barrier separates the last reads
+// of a block step from the remote stores — half the shared memory, used to pack a batch of matrices onto the SMs.
+template <class T, int CL, int GL, int RPL, bool DB>
 __global__ void __launch_bounds__(512) jacobi_cluster_kernel(T* __restrict__ X, int m, int n, int64_t ldx, int64_t bX, int W,
                                                               double tol, int* __restrict__ d_sweeps) {
   cg::cluster_group cluster = cg::this_cluster();
@@ -107,9 +110,10 @@ __global__ void __launch_bounds__(512) jacobi_cluster_kernel(T* __restrict__ X, 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int ncl = 2 * W;                                 // local columns
   const int pitch = GL * RPL;                            // rows padded to the register tile
-  T* cols = reinterpret_cast<T*>(smem_raw);              // [2][ncl][pitch]
-  double* nrm = reinterpret_cast<double*>(cols + (size_t)2 * ncl * pitch);   // [2][ncl]
-  int* flags = reinterpret_cast<int*>(nrm + 2 * ncl);    // [CL]
+  constexpr int NBUF = DB ? 2 : 1;
+  T* cols = reinterpret_cast<T*>(smem_raw);              // [NBUF][ncl][pitch]
+  double* nrm = reinterpret_cast<double*>(cols + (size_t)NBUF * ncl * pitch);   // [NBUF][ncl]
+  int* flags = reinterpret_cast<int*>(nrm + NBUF * ncl);    // [CL]
   __shared__ int s_rot;
 
   const int tid = threadIdx.x;
@@ -146,7 +150,7 @@ __global__ void __launch_bounds__(512) jacobi_cluster_kernel(T* __restrict__ X, 
     for (int bs = 0; bs < 2 * CL - 1; ++bs) {
       T* cb = cols + (size_t)cur * ncl * pitch;
       double* nb = nrm + cur * ncl;
-      const int nxt = cur ^ 1;
+      const int nxt = DB ? cur ^ 1 : cur;
       if (bs == 0) {
         // all pairs among the 2W resident columns: both columns of a pair go through shared memory every step
         const int M1 = ncl - 1;
@@ -167,8 +171,9 @@ __global__ void __launch_bounds__(512) jacobi_cluster_kernel(T* __restrict__ X, 
             if (gl == 0) { nb[p] = an; nb[q] = bn; }
             __syncthreads();
           } else {
-            send_column<T, GL, RPL>(cluster, cols, nrm, crank, p, W, nxt, ncl, pitch, gl, rp, an);
-            send_column<T, GL, RPL>(cluster, cols, nrm, crank, q, W, nxt, ncl, pitch, gl, rq, bn);
+            if (!DB) cluster.sync();   // every CTA has finished reading its columns before any remote store lands
+            send_column<T, CL, GL, RPL>(cluster, cols, nrm, crank, p, W, nxt, ncl, pitch, gl, rp, an);
+            send_column<T, CL, GL, RPL>(cluster, cols, nrm, crank, q, W, nxt, ncl, pitch, gl, rq, bn);
           }
         }
       } else {
@@ -195,11 +200,12 @@ __global__ void __launch_bounds__(512) jacobi_cluster_kernel(T* __restrict__ X, 
             if (gl == 0) nb[q] = bn;
             __syncthreads();
           } else {
-            send_column<T, GL, RPL>(cluster, cols, nrm, crank, q, W, nxt, ncl, pitch, gl, rq, bn);
+            if (!DB) cluster.sync();
+            send_column<T, CL, GL, RPL>(cluster, cols, nrm, crank, q, W, nxt, ncl, pitch, gl, rq, bn);
           }
           if (++qi == W) qi = 0;
         }
-        send_column<T, GL, RPL>(cluster, cols, nrm, crank, grp, W, nxt, ncl, pitch, gl, rp, an);
+        send_column<T, CL, GL, RPL>(cluster, cols, nrm, crank, grp, W, nxt, ncl, pitch, gl, rp, an);
       }
       if (bs == 2 * CL - 2) {
         // end of sweep: publish this CTA's rotation level to every CTA of the cluster
@@ -208,7 +214,7 @@ __global__ void __launch_bounds__(512) jacobi_cluster_kernel(T* __restrict__ X, 
         if (tid < CL) *(cluster.map_shared_rank(flags, tid) + crank) = s_rot;
       }
       cluster.sync();
-      cur ^= 1;
+      if (DB) cur ^= 1;
     }
     int any = 0;
 #pragma unroll
@@ -231,45 +237,66 @@ __global__ void __launch_bounds__(512) jacobi_cluster_kernel(T* __restrict__ X, 
   cluster.sync();   // no CTA may exit while a peer can still address its shared memory
 }
 
-template <class T, int GL, int RPL>
+template <class T, int CL, int GL, int RPL, bool DB>
 bool launch_cluster(T* X, int m, int n, int64_t ldx, int batch, int64_t bX, double tol, int* d_sweeps) {
   const int W = (n + 2 * CL - 1) / (2 * CL);
   const int threads = W * GL;
-  if (threads > 512 || threads < 32) return false;
-  const size_t smem = sizeof(T) * (size_t)2 * 2 * W * GL * RPL + sizeof(double) * 2 * 2 * W + sizeof(int) * CL;
-  if (smem > 200 * 1024) return false;
-  auto kern = jacobi_cluster_kernel<T, GL, RPL>;
+  if (threads > 512 || threads < 32 || (threads & 31)) return false;
+  const size_t smem = sizeof(T) * (size_t)(DB ? 2 : 1) * 2 * W * GL * RPL + sizeof(double) * (DB ? 2 : 1) * 2 * W + sizeof(int) * CL;
+  if (smem > 224 * 1024) return false;
+  auto kern = jacobi_cluster_kernel<T, CL, GL, RPL, DB>;
   static bool attr_done = false;
   if (!attr_done) {
-    TTN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    TTN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     attr_done = true;
   }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(CL * batch, 1, 1);
-  cfg.blockDim = dim3(threads, 1, 1);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = ctx().stream;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = CL;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  ProfScope prof_scope_(KF_JACOBI);
-  TTN_CUDA(cudaLaunchKernelEx(&cfg, kern, X, m, n, ldx, bX, W, tol, d_sweeps));
-  ctx().launches++;
+  for (int b0 = 0; b0 < batch; b0 += 8192) {
+    const int nb = std::min(8192, batch - b0);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CL * nb, 1, 1);
+    cfg.blockDim = dim3(threads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx().stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    ProfScope prof_scope_(KF_JACOBI);
+    TTN_CUDA(cudaLaunchKernelEx(&cfg, kern, X + (int64_t)b0 * bX, m, n, ldx, bX, W, tol, d_sweeps + b0));
+    ctx().launches++;
+  }
   return true;
 }
 
 }  // namespace
 
 // Returns false when the shape is not served by the cluster kernel (caller falls back to the single-SM / block paths).
+//   few matrices  : 8 CTAs per matrix, double-buffered (latency of the single SVD is what matters: TT-rounding chain);
+//   large batches : the smallest cluster whose shared memory holds the matrix (2 or 4 CTAs, single buffer), so that
+//                   sm_count/CL matrices are in flight at once (cfg5: ComplexF64 128 x 128 does not fit in one SM).
 template <class T>
 bool jacobi_cluster(T* X, int m, int n, int64_t ldx, int batch, int64_t bX, double tol, int* d_sweeps) {
-  if (n < 32 || batch > 16) return false;        // tiny problems: one SM is enough; large batches: one SM per matrix
-  if (m <= 128) return launch_cluster<T, 32, 4>(X, m, n, ldx, batch, bX, tol, d_sweeps);
-  if (m <= 256) return launch_cluster<T, 32, 8>(X, m, n, ldx, batch, bX, tol, d_sweeps);
+  if (n < 32) return false;                       // tiny problems: one SM is enough
+  const bool few = batch * 8 <= ctx().sm_count;
+  if (few) {
+    if (m <= 128) return launch_cluster<T, 8, 32, 4, true>(X, m, n, ldx, batch, bX, tol, d_sweeps);
+    if (m <= 256) return launch_cluster<T, 8, 32, 8, true>(X, m, n, ldx, batch, bX, tol, d_sweeps);
+    return false;
+  }
+  const size_t one_sm = (sizeof(T) * (size_t)(m + 4) + 8) * n;   // footprint of the single-SM kernel (jacobi.cu)
+  if (one_sm <= 216 * 1024) return false;         // fits in one SM: one matrix per SM is the throughput-optimal layout
+  if (m <= 128) {
+    if (n <= 128 && launch_cluster<T, 2, 16, 8, false>(X, m, n, ldx, batch, bX, tol, d_sweeps)) return true;
+    if (n <= 256 && launch_cluster<T, 4, 16, 8, false>(X, m, n, ldx, batch, bX, tol, d_sweeps)) return true;
+    return launch_cluster<T, 8, 32, 4, false>(X, m, n, ldx, batch, bX, tol, d_sweeps);
+  }
+  if (m <= 256) {
+    if (launch_cluster<T, 4, 32, 8, false>(X, m, n, ldx, batch, bX, tol, d_sweeps)) return true;
+    return launch_cluster<T, 8, 32, 8, false>(X, m, n, ldx, batch, bX, tol, d_sweeps);
+  }
   return false;
 }
 
