@@ -161,6 +161,27 @@ int ttn_matvec2_create(int dtype, int w_l, int w_r, int chi_l, int chi_r, int nn
                        const void* H, ttn_matvec* out);
 int ttn_matvec2_apply(ttn_matvec mv, const void* V_dev, void* Y_dev);   /* device pointers, (chi_l, nn, chi_r) */
 int ttn_matvec2_free(ttn_matvec mv);
+/* ---- the same matvec sharded over the GPUs of one NVLink node (one process per GPU) ----------
+ * Rank `rank` of `nranks` owns the slice c in [c0, c0+cp) of the right environment's bra index (ttn_shard_range) and
+ * computes Y[:, :, c0:c0+cp] with no reduction; the epilogue of its last GEMM stores the tiles into the result
+ * buffers of every peer (P2P over NVLink), so after ttn_shard_matvec_apply the complete vector is resident on every
+ * rank (stream-ordered).  Peer buffers are exchanged as CUDA IPC handles: each rank calls _handles (192 bytes: two
+ * result buffers + the epoch flags), the host side all-gathers them (MPI.jl / torch.distributed) and calls _bind with
+ * the nranks x 192 bytes in rank order.  Without _bind (or nranks == 1) only the local slice is written.
+ * G, Amid, H are HOST arrays in the reference layouts (dmrg.jl:27-46); every rank passes the full arrays. */
+typedef struct ttn_shard_matvec_s* ttn_shard_matvec;
+int ttn_shard_range(int chi, int rank, int nranks, int* c0, int* cp);
+int ttn_shard_matvec_create(int dtype, int w_l, int w_r, int chi_l, int chi_r, int nn, const void* G, const void* Amid,
+                            const void* H, int rank, int nranks, ttn_shard_matvec* out);
+int ttn_shard_matvec_handles(ttn_shard_matvec mv, void* handles192);
+int ttn_shard_matvec_bind(ttn_shard_matvec mv, const void* all_handles);
+int ttn_shard_matvec_apply(ttn_shard_matvec mv, const void* V_dev, void** Y_dev);   /* *Y_dev: library-owned full vector */
+/* lowest eigenpair of the sharded operator (KrylovKit.eigsolve(..., :SR) stand-in, dmrg.jl:245): x_dev start vector in,
+ * eigenvector out (identical on every rank); the Lanczos recurrence is replicated, only the matvec is distributed */
+int ttn_shard_eigsolve(ttn_shard_matvec mv, void* x_dev, int krylovdim, int maxiter, double tol, double* theta, int* matvecs);
+int ttn_shard_matvec_slice(ttn_shard_matvec mv, int* c0, int* cp);
+int ttn_shard_matvec_error(ttn_shard_matvec mv, int* err);    /* 1 if an epoch wait timed out (a peer died) */
+int ttn_shard_matvec_free(ttn_shard_matvec mv);
 /* environment updates on HOST arrays, reference layouts (src/solvers/dmrg.jl:27-35) */
 int ttn_env_left_host(int dtype, int n, int w_l, int w_r, int r_l, int r_r, const void* G, const void* x, const void* A,
                       void* Gout);

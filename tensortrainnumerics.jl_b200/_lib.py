@@ -86,6 +86,12 @@ def load():
         "ttn_matvec2_host": [C.c_int] * 6 + [vp, vp, vp, vp, vp, C.c_int],
         "ttn_matvec2_create": [C.c_int] * 6 + [vp, vp, vp, vpp],
         "ttn_matvec2_apply": [vp, vp, vp], "ttn_matvec2_free": [vp],
+        "ttn_shard_range": [C.c_int, C.c_int, C.c_int, ip, ip],
+        "ttn_shard_matvec_create": [C.c_int] * 6 + [vp, vp, vp, C.c_int, C.c_int, vpp],
+        "ttn_shard_matvec_handles": [vp, vp], "ttn_shard_matvec_bind": [vp, vp],
+        "ttn_shard_matvec_apply": [vp, vp, vpp],
+        "ttn_shard_eigsolve": [vp, vp, C.c_int, C.c_int, C.c_double, dp, ip],
+        "ttn_shard_matvec_slice": [vp, ip, ip], "ttn_shard_matvec_error": [vp, ip], "ttn_shard_matvec_free": [vp],
         "ttn_env_left_host": [C.c_int] * 6 + [vp, vp, vp, vp],
         "ttn_env_right_host": [C.c_int] * 6 + [vp, vp, vp, vp],
         "ttn_svdtrunc_host": [C.c_int, C.c_int, C.c_int, vp, C.c_int64, C.c_double, vp, dp, vp, ip],

@@ -31,7 +31,7 @@ __all__ = [
     "TTvector", "TToperator", "DeviceTT", "DeviceTTO", "apply", "dot", "norm", "add", "scale", "sub",
     "orthogonalize", "tt_compress_", "tt_bond_truncate_", "als_linsolve", "als_eigsolve", "mals_linsolve",
     "mals_eigsolve", "dmrg_linsolve", "dmrg_eigsolve", "tdvp", "tdvp2", "matvec2", "env_left", "env_right",
-    "svdtrunc", "qr_thin", "gemm_host", "launch_count", "reset_launch_count", "synchronize", "library_path", "profile", "profile_read", "stream_handle",
+    "shard_range", "shard_batch", "assemble_slices", "ShardedMatvec", "svdtrunc", "qr_thin", "gemm_host", "launch_count", "reset_launch_count", "synchronize", "library_path", "profile", "profile_read", "stream_handle",
     "KERNEL_FAMILIES",
 ]
 
@@ -610,6 +610,107 @@ def matvec2(G, Amid, H, V, symmetrize=False):
     check(_lib.lib().ttn_matvec2_host(code, G.shape[0], H.shape[0], G.shape[1], H.shape[1], Amid.shape[1], G.ctypes.data,
                                       Amid.ctypes.data, H.ctypes.data, V.ctypes.data, Y.ctypes.data, int(bool(symmetrize))))
     return Y
+
+
+# ------------------------------------------------------------------------------------------------------
+# multi-GPU partitioning (host logic)
+# ------------------------------------------------------------------------------------------------------
+def shard_range(chi: int, rank: int, nranks: int):
+    """Contiguous slice (c0, cp) of a bond index of size `chi` owned by `rank` — the same rule as the library's
+    ttn_shard_range (the first chi % nranks ranks own one extra index).  Pure host arithmetic (no GPU needed)."""
+    if not (chi >= 1 and nranks >= 1 and 0 <= rank < nranks):
+        raise AssertionError("shard_range: bad arguments")
+    base, rem = divmod(chi, nranks)
+    return rank * base + min(rank, rem), base + (1 if rank < rem else 0)
+
+
+def shard_batch(total: int, rank: int, nranks: int):
+    """Slice (first, count) of a batch of `total` independent TT problems owned by `rank` (cfg5: no collective)."""
+    return shard_range(total, rank, nranks) if total >= 1 else (0, 0)
+
+
+def assemble_slices(slices, axis=-1):
+    """Inverse of the partition: concatenates the per-rank slices (in rank order) along the sharded axis."""
+    return np.concatenate(list(slices), axis=axis)
+
+
+class ShardedMatvec:
+    """Two-site effective operator of src/solvers/dmrg.jl:239-244 sharded over `nranks` GPUs on the bra index of the right
+    environment (one process per GPU).  `exchange` is a callable that all-gathers a bytes object over the ranks
+    (e.g. torch.distributed.all_gather_object); without it (or nranks == 1) only the local slice is produced."""
+
+    def __init__(self, G, Amid, H, rank=0, nranks=1, exchange=None):
+        dt = np.result_type(G.dtype, Amid.dtype, H.dtype)
+        self.dtype, self.code = dt, _dtype_code(dt)
+        G, Amid, H = _f(G, dt), _f(Amid, dt), _f(H, dt)
+        self.shape = (G.shape[1], Amid.shape[1], H.shape[1])
+        self.rank, self.nranks = rank, nranks
+        self.h = C.c_void_p()
+        check(_lib.lib().ttn_shard_matvec_create(self.code, G.shape[0], H.shape[0], G.shape[1], H.shape[1], Amid.shape[1],
+                                                 G.ctypes.data, Amid.ctypes.data, H.ctypes.data, rank, nranks, C.byref(self.h)))
+        c0, cp = C.c_int(), C.c_int()
+        check(_lib.lib().ttn_shard_matvec_slice(self.h, C.byref(c0), C.byref(cp)))
+        self.c0, self.cp = c0.value, cp.value
+        assert (self.c0, self.cp) == shard_range(self.shape[2], rank, nranks)
+        if exchange is not None and nranks > 1:
+            mine = C.create_string_buffer(192)
+            check(_lib.lib().ttn_shard_matvec_handles(self.h, mine))
+            allh = exchange(bytes(mine.raw))
+            assert len(allh) == nranks and all(len(b) == 192 for b in allh)
+            buf = C.create_string_buffer(b"".join(allh), 192 * nranks)
+            check(_lib.lib().ttn_shard_matvec_bind(self.h, buf))
+
+    @property
+    def nbytes(self):
+        return int(np.prod(self.shape)) * np.dtype(self.dtype).itemsize
+
+    def apply_dev(self, V_dev):
+        """device pointer in → device pointer of the library-owned result vector (complete on every bound rank)"""
+        out = C.c_void_p()
+        check(_lib.lib().ttn_shard_matvec_apply(self.h, V_dev, C.byref(out)))
+        return out
+
+    def apply(self, V):
+        """host vector in → host copy of this rank's result buffer (complete if peers are bound, else only the local slice
+        Y[:, :, c0:c0+cp] is meaningful)"""
+        V = _f(V, self.dtype)
+        dV = C.c_void_p()
+        check(_lib.lib().ttn_dev_alloc(V.nbytes, C.byref(dV)))
+        try:
+            check(_lib.lib().ttn_h2d(dV, V.ctypes.data, V.nbytes))
+            dY = self.apply_dev(dV)
+            Y = np.empty(self.shape, dtype=self.dtype, order="F")
+            check(_lib.lib().ttn_d2h(Y.ctypes.data, dY, Y.nbytes))
+        finally:
+            check(_lib.lib().ttn_dev_free(dV))
+        return Y
+
+    def local_slice(self, V):
+        return self.apply(V)[:, :, self.c0:self.c0 + self.cp]
+
+    def eigsolve(self, x0, krylovdim=8, maxiter=1, tol=1e-10):
+        """lowest eigenpair (KrylovKit.eigsolve(..., :SR) stand-in, dmrg.jl:245) → (theta, x, matvecs)"""
+        x = _f(x0, self.dtype).copy(order="F")
+        dx = C.c_void_p()
+        check(_lib.lib().ttn_dev_alloc(x.nbytes, C.byref(dx)))
+        try:
+            check(_lib.lib().ttn_h2d(dx, x.ctypes.data, x.nbytes))
+            th, mv = C.c_double(), C.c_int()
+            check(_lib.lib().ttn_shard_eigsolve(self.h, dx, krylovdim, maxiter, tol, C.byref(th), C.byref(mv)))
+            check(_lib.lib().ttn_d2h(x.ctypes.data, dx, x.nbytes))
+        finally:
+            check(_lib.lib().ttn_dev_free(dx))
+        return th.value, x, mv.value
+
+    def error(self):
+        e = C.c_int()
+        check(_lib.lib().ttn_shard_matvec_error(self.h, C.byref(e)))
+        return e.value
+
+    def free(self):
+        if self.h:
+            check(_lib.lib().ttn_shard_matvec_free(self.h))
+            self.h = C.c_void_p()
 
 
 def env_left(G, x, A):

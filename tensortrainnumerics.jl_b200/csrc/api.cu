@@ -538,6 +538,64 @@ int ttn_matvec2_free(ttn_matvec mv) {
   matvec2_free(mv);
   API_END
 }
+int ttn_shard_range(int chi, int rank, int nranks, int* c0, int* cp) {
+  API_BEGIN
+  ttn_assert(chi >= 1 && nranks >= 1 && rank >= 0 && rank < nranks && c0 && cp, TTN_EARG, "shard_range: bad arguments");
+  shard_range(chi, rank, nranks, c0, cp);
+  API_END
+}
+int ttn_shard_matvec_create(int dtype, int w_l, int w_r, int chi_l, int chi_r, int nn, const void* G, const void* Amid,
+                            const void* H, int rank, int nranks, ttn_shard_matvec* out) {
+  API_BEGIN
+  need_init();
+  ttn_assert(out != nullptr, TTN_EARG, "null argument");
+  *out = shard_create(dtype, w_l, w_r, chi_l, chi_r, nn, G, Amid, H, rank, nranks);
+  API_END
+}
+int ttn_shard_matvec_handles(ttn_shard_matvec mv, void* handles192) {
+  API_BEGIN
+  need_init();
+  shard_handles(mv, handles192);
+  API_END
+}
+int ttn_shard_matvec_bind(ttn_shard_matvec mv, const void* all_handles) {
+  API_BEGIN
+  need_init();
+  shard_bind_handles(mv, all_handles);
+  API_END
+}
+int ttn_shard_matvec_apply(ttn_shard_matvec mv, const void* V_dev, void** Y_dev) {
+  API_BEGIN
+  need_init();
+  ttn_assert(Y_dev != nullptr, TTN_EARG, "null argument");
+  *Y_dev = shard_apply_any(mv, V_dev);
+  API_END
+}
+int ttn_shard_eigsolve(ttn_shard_matvec mv, void* x_dev, int krylovdim, int maxiter, double tol, double* theta, int* matvecs) {
+  API_BEGIN
+  need_init();
+  ttn_assert(theta != nullptr, TTN_EARG, "null argument");
+  *theta = shard_eigsolve(mv, x_dev, krylovdim, maxiter, tol, matvecs);
+  API_END
+}
+int ttn_shard_matvec_slice(ttn_shard_matvec mv, int* c0, int* cp) {
+  API_BEGIN
+  ttn_assert(mv && c0 && cp, TTN_EARG, "null argument");
+  shard_slice(mv, c0, cp);
+  API_END
+}
+int ttn_shard_matvec_error(ttn_shard_matvec mv, int* err) {
+  API_BEGIN
+  need_init();
+  ttn_assert(mv && err, TTN_EARG, "null argument");
+  *err = shard_error(mv);
+  API_END
+}
+int ttn_shard_matvec_free(ttn_shard_matvec mv) {
+  API_BEGIN
+  shard_free(mv);
+  API_END
+}
 int ttn_env_left_host(int dtype, int n, int w_l, int w_r, int r_l, int r_r, const void* G, const void* x, const void* A,
                       void* Gout) {
   API_BEGIN

@@ -169,6 +169,9 @@ __global__ void __launch_bounds__(NT) gemm_kernel(const GemmArgs g) {
           T v = t_scale(acc[i][j].get(e), g.alpha);
           if (has_beta) v = t_add(v, t_scale(*p, g.beta));
           *p = v;
+          // compute -> all-gather fusion: the same element goes straight to the peers' buffers over NVLink (P2P stores)
+          for (int q = 0; q < g.npeer; ++q)
+            (reinterpret_cast<T*>(g.Cpeer[q]) + b1 * g.bC1 + b2 * g.bC2)[(int64_t)row * g.sCm + (int64_t)col * g.sCn] = v;
         }
       }
     }
@@ -189,6 +192,7 @@ void launch_cfg(const GemmArgs& g) {
   // grid.z is limited to 65535: split the outer batch dimension if needed
   const int64_t max_b2 = std::max<int64_t>(1, 65535 / g.batch1);
   ttn_assert(g.batch1 <= 65535, 2, "gemm: inner batch dimension too large");
+  ttn_assert(g.npeer == 0 || g.batch2 <= max_b2, 2, "gemm: peer epilogue needs a single launch");
   for (int64_t s = 0; s < g.batch2; s += max_b2) {
     GemmArgs h = g;
     const int64_t nb2 = std::min<int64_t>(max_b2, g.batch2 - s);

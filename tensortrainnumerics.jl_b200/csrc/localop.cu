@@ -109,6 +109,7 @@ static void localop_pass(LocalOp<T>& op, const T* Lx, const T* Wx, const T* Rx, 
 
 template <class T>
 void LocalOp<T>::apply(const T* V, T* Y) {
+  if (ext_apply) { ext_apply(V, Y); return; }
   if (symmetrize) {
     localop_pass<T>(*this, L, Wp.as<T>(), Rm.as<T>(), V, Y, 0.5, 0.0);
     localop_pass<T>(*this, Lt.as<T>(), Wpt.as<T>(), Rmt.as<T>(), V, Y, 0.5, 1.0);

@@ -2,6 +2,7 @@
 #pragma once
 #include "../../include/ttn_b200.h"
 #include "tt.h"
+#include <functional>
 
 namespace ttn {
 
@@ -25,6 +26,7 @@ struct LocalOp {
   DevBuf Wp;                       // W'[(y,e),(b,z)]
   DevBuf Lt, Rmt, Wpt;             // transposed operator pieces (symmetrize only)
   DevBuf T1, T2;                   // workspaces
+  std::function<void(const T*, T*)> ext_apply;   // sharded operator (shard.cu): replaces the local three-GEMM chain
   int64_t size() const { return (int64_t)chi_l * nn * chi_r; }
   // Wfused: (w_l, nn, nn, w_r) in the reference Amid layout [y, b, e, z]; nullptr for zero_site
   void setup(const T* Lenv, int chil, int wl, const T* Renv, int chir, int wr, const T* Wfused, int nn_, bool sym);
@@ -90,7 +92,19 @@ struct ttn_matvec_s {
   ttn::LocalOp<ttn::zc> c;
   ttn::DevBuf L, R;
 };
+typedef struct ttn_shard_matvec_s* ttn_shard_matvec;
 namespace ttn {
+// sharded effective operator (shard.cu)
+void shard_range(int chi, int rank, int nranks, int* c0, int* cp);
+ttn_shard_matvec shard_create(int dtype, int w_l, int w_r, int chi_l, int chi_r, int nn, const void* G, const void* Amid,
+                              const void* H, int rank, int nranks);
+void shard_handles(ttn_shard_matvec mv, void* out192);
+void shard_bind_handles(ttn_shard_matvec mv, const void* all);
+void* shard_apply_any(ttn_shard_matvec mv, const void* V);
+double shard_eigsolve(ttn_shard_matvec mv, void* x, int krylovdim, int maxiter, double tol, int* matvecs);
+int shard_error(ttn_shard_matvec mv);
+void shard_slice(ttn_shard_matvec mv, int* c0, int* cp);
+void shard_free(ttn_shard_matvec mv);
 ttn_matvec matvec2_create(int dtype, int w_l, int w_r, int chi_l, int chi_r, int nn, const void* G, const void* Amid,
                           const void* H);
 void matvec2_apply(ttn_matvec mv, const void* V, void* Y);

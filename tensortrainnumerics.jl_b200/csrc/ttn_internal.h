@@ -148,6 +148,9 @@ struct GemmArgs {
   double alpha = 1.0, beta = 0.0;
   int batch1 = 1, batch2 = 1;                       // two batch dimensions, b = b1 + batch1*b2
   int64_t bA1 = 0, bA2 = 0, bB1 = 0, bB2 = 0, bC1 = 0, bC2 = 0;
+  // fused all-gather epilogue (shard.cu): the finished C tile is also stored to `npeer` mapped peer buffers (same strides)
+  int npeer = 0;
+  void* Cpeer[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 template <class T> void gemm(const GemmArgs& g);
 double gemm_flops(const GemmArgs& g, bool cplx);
