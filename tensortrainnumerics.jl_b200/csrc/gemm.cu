@@ -14,6 +14,7 @@
 // real DMMA products on split re/im fragments.  sm_100a has no f64 kind for tcgen05.mma, so DMMA via
 // mma.sync is the FP64 tensor path on this chip (larger f64 shapes decompose to 8x8x4 in SASS).
 #include "ttn_internal.h"
+#include "dmma.h"
 
 namespace ttn {
 
@@ -22,33 +23,8 @@ namespace {
 constexpr int BK = 16;
 constexpr int NT = 256;
 
-__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(c0), "+d"(c1)
-               : "d"(a), "d"(b));
-}
-
 template <class T> struct Pad { static constexpr int v = 4; };
 template <> struct Pad<zc> { static constexpr int v = 2; };
-
-template <class T> struct Acc;
-template <> struct Acc<double> {
-  double c[2];
-  __device__ __forceinline__ void zero() { c[0] = c[1] = 0.0; }
-  __device__ __forceinline__ void mma(double a, double b) { dmma884(c[0], c[1], a, b); }
-  __device__ __forceinline__ double get(int i) const { return c[i]; }
-};
-template <> struct Acc<zc> {
-  double re[2], im[2];
-  __device__ __forceinline__ void zero() { re[0] = re[1] = im[0] = im[1] = 0.0; }
-  __device__ __forceinline__ void mma(zc a, zc b) {
-    dmma884(re[0], re[1], a.x, b.x);
-    dmma884(re[0], re[1], -a.y, b.y);
-    dmma884(im[0], im[1], a.x, b.y);
-    dmma884(im[0], im[1], a.y, b.x);
-  }
-  __device__ __forceinline__ zc get(int i) const { return make_cuDoubleComplex(re[i], im[i]); }
-};
 
 template <class T, int BM, int BN, int WM, int WN, bool AMAJ, bool BMAJ>
 __global__ void __launch_bounds__(NT) gemm_kernel(const GemmArgs g) {

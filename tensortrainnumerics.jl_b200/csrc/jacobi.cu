@@ -423,6 +423,13 @@ int jacobi_orth(T* X, int m, int n, int64_t ldx, double* norms, int batch, int64
     TTN_CUDA(cudaMemcpyAsync(&hsw, dsw.p, sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
     TTN_CUDA(cudaStreamSynchronize(ctx().stream));
     sweeps_used = hsw;
+  } else if (ctx().use_gram_jacobi && n >= 128 && m >= 64) {
+    // large matrices: Gram-block Jacobi, O(m n^2) work on the FP64 tensor pipe (jacobi_gram.cu)
+    for (int b = 0; b < batch; ++b) {
+      const int sw = jacobi_gram<T>(X + (int64_t)b * bX, m, n, ldx, tol, JAC_MAX_SWEEPS);
+      ttn_assert(sw >= 0, 7, "jacobi_gram: shape not served");
+      if (b == 0) sweeps_used = sw;
+    }
   } else {
     // block Jacobi across CTAs.  Fast path (m <= 32*RPLA): blocks of #warps columns, cross steps on
     // jacobi_cross_kernel (A block in registers, B block in shared memory); generic path: two blocks per CTA in
