@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(GT) gram_pairs_kernel(const T* __restrict__ X,
 // ---------------------------------------------------------------------------------------------------------------------
 template <class T>
 __global__ void __launch_bounds__(GT) gram_eig_kernel(const T* __restrict__ Gp, int nsplit, int inner_sweeps, double tol,
-                                                      T* __restrict__ Vg, int* __restrict__ skip,
+                                                      const double* __restrict__ d_frob2, double floor_k, T* __restrict__ Vg, int* __restrict__ skip,
                                                       unsigned int* __restrict__ d_rotated) {
   constexpr int P = PW + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(GT) gram_eig_kernel(const T* __restrict__ Gp, 
   __shared__ int s_any, s_step[2];
   const int tid = threadIdx.x;
   const double tol2 = tol * tol;
+  const double floor2 = floor_k * d_frob2[0];   // optional noise floor (jacobi.cu JAC_FLOOR2), 0 = off
   const T* gp = Gp + (size_t)blockIdx.x * nsplit * PW * PW;
   for (int idx = tid; idx < PW * PW; idx += GT) {
     T a = t_zero<T>();
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(GT) gram_eig_kernel(const T* __restrict__ Gp, 
         const double cc = cr * cr + ci * ci;
         double cs = 1.0;
         T sn = t_zero<T>();
-        if (cc > tol2 * fmax(a, 0.0) * fmax(b, 0.0) && cc > 1e-290) {
+        if (cc > tol2 * fmax(a, 0.0) * fmax(b, 0.0) && a > floor2 && b > floor2 && cc > 1e-290) {
           const double tau = 0.5 * (b - a);
           const double z = tau * tau + cc;
           const double h = z * rsqrt(z);
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(GT) update_pairs_kernel(T* __restrict__ X, int
 
 // Orthogonalises the n columns of X (m x n, one matrix); returns the number of sweeps, or -1 if the shape is not served.
 template <class T>
-int jacobi_gram(T* X, int m, int n, int64_t ldx, double tol, int max_sweeps) {
+int jacobi_gram(T* X, int m, int n, int64_t ldx, double tol, const double* frob2, double fk, int max_sweeps) {
   if (n < 2 * PW || m < PW) return -1;
   const int nblk = (n + GB - 1) / GB;
   const int ne = nblk + (nblk & 1);
@@ -330,7 +331,7 @@ int jacobi_gram(T* X, int m, int n, int64_t ldx, double tol, int max_sweeps) {
       }
       {
         ProfScope prof_scope_(KF_JACOBI);
-        gram_eig_kernel<T><<<cnt, GT, smem_e, ctx().stream>>>(Gp.as<T>(), nsplit, inner, tol, Vg.as<T>(), skip.as<int>(),
+        gram_eig_kernel<T><<<cnt, GT, smem_e, ctx().stream>>>(Gp.as<T>(), nsplit, inner, tol, frob2, fk, Vg.as<T>(), skip.as<int>(),
                                                         rot.as<unsigned int>());
         TTN_CHECK_LAUNCH();
       }
@@ -351,7 +352,7 @@ int jacobi_gram(T* X, int m, int n, int64_t ldx, double tol, int max_sweeps) {
   return sweeps;
 }
 
-template int jacobi_gram<double>(double*, int, int, int64_t, double, int);
-template int jacobi_gram<zc>(zc*, int, int, int64_t, double, int);
+template int jacobi_gram<double>(double*, int, int, int64_t, double, const double*, double, int);
+template int jacobi_gram<zc>(zc*, int, int, int64_t, double, const double*, double, int);
 
 }  // namespace ttn

@@ -258,8 +258,15 @@ void tt_bond_truncate(TT<T>& x, int k1, int64_t max_bond, double truncerr, doubl
   const int n1 = (int)x.dims[k], n2 = (int)x.dims[k + 1];
   const int rl = (int)x.rks[k], r = (int)x.rks[k + 1], rr = (int)x.rks[k + 2];
   const int p = n1 * rl, q = n2 * rr;
-  DevBuf Theta(sizeof(T) * (size_t)p * q * batch);
-  {
+  // Rank-deficient bond (inner dimension r well below min(p,q): every R->L step of tt_compress!, and the first sweep after
+  // A*x): Theta = A B has rank <= r, so the SVD is taken of the r x q matrix Theta' = R_A B with A = Q_A R_A (Householder):
+  // same singular values, U = Q_A U'.  The Jacobi problem shrinks from min(p,q) to r columns, and it is full rank
+  // (one-sided Jacobi needs 2-3x more sweeps on a matrix whose trailing singular values are rounding noise).
+  const int kmin = std::min(p, q);
+  const bool factored = (int64_t)r * 4 <= (int64_t)kmin * 3;
+  const int pe = factored ? r : p;                   // rows of the matrix that is actually decomposed
+  DevBuf Theta(sizeof(T) * (size_t)pe * q * batch), QA;
+  if (!factored) {
     GemmArgs g;  // Theta[(s1,alpha),(s2,beta)] = sum_gamma A[s1,alpha,gamma] B[s2,gamma,beta]     (tt_tools.jl:749)
     g.M = p; g.N = rr; g.K = r;
     g.A = x.cores[k].p; g.sAm = 1; g.sAk = p; g.bA1 = 0; g.bA2 = x.core_elems(k);
@@ -267,29 +274,52 @@ void tt_bond_truncate(TT<T>& x, int k1, int64_t max_bond, double truncerr, doubl
     g.C = Theta.p; g.sCm = 1; g.sCn = (int64_t)p * n2; g.bC1 = p; g.bC2 = (int64_t)p * q;
     g.batch1 = n2; g.batch2 = batch;
     gemm<T>(g);
+  } else {
+    const int64_t bA = (int64_t)p * r;
+    DevBuf W(sizeof(T) * (size_t)bA * batch), tau(sizeof(T) * (size_t)r * batch), RA(sizeof(T) * (size_t)r * r * batch);
+    TTN_CUDA(cudaMemcpyAsync(W.p, x.cores[k].p, W.bytes, cudaMemcpyDeviceToDevice, ctx().stream));
+    qr_factor<T>(W.as<T>(), p, r, p, tau.as<T>(), batch, bA, r);
+    QA.alloc(sizeof(T) * (size_t)bA * batch);
+    qr_form_q<T>(W.as<T>(), p, r, p, tau.as<T>(), QA.as<T>(), p, batch, bA, r, bA);
+    Copy4 t; t.n0 = r; t.n1 = r; t.n2 = batch; t.s0 = 1; t.s1 = p; t.s2 = bA; t.d0 = 1; t.d1 = r; t.d2 = (int64_t)r * r; t.tri = 1;
+    copy4<T>(W.as<T>(), RA.as<T>(), t);
+    GemmArgs g;  // Theta'[gamma',(s2,beta)] = sum_gamma R_A[gamma',gamma] B[s2,gamma,beta]
+    g.M = r; g.N = rr; g.K = r;
+    g.A = RA.p; g.sAm = 1; g.sAk = r; g.bA1 = 0; g.bA2 = (int64_t)r * r;
+    g.B = x.cores[k + 1].p; g.sBk = n2; g.sBn = (int64_t)n2 * r; g.bB1 = 1; g.bB2 = x.core_elems(k + 1);
+    g.C = Theta.p; g.sCm = 1; g.sCn = (int64_t)r * n2; g.bC1 = r; g.bC2 = (int64_t)r * q;
+    g.batch1 = n2; g.batch2 = batch;
+    gemm<T>(g);
   }
   SvdLeft sv;
-  svd_left<T>(Theta.as<T>(), p, q, 1, p, false, sv, batch, (int64_t)p * q);
+  svd_left<T>(Theta.as<T>(), pe, q, 1, pe, false, sv, batch, (int64_t)pe * q);
   const int kk = sv.k;
+  // rank rule on the min(p,q) singular values of Theta (the kmin - kk values the factored form does not compute are zero)
   int rn;
-  if (batch == 1) rn = rank_tailnorm(sv.sigma.data(), kk, max_bond, truncerr);
-  else rn = (int)std::min<int64_t>(kk, max_bond);
+  if (batch == 1) {
+    std::vector<double> sig(sv.sigma.begin(), sv.sigma.begin() + kk);
+    sig.resize(kmin, 0.0);
+    rn = rank_tailnorm(sig.data(), kmin, max_bond, truncerr);
+  } else {
+    rn = (int)std::min<int64_t>(kmin, max_bond);
+  }
   if (rn < 1) rn = 1;
+  const int rc = std::min(rn, kk);                   // columns that are actually computed; the rest (sigma = 0) stay zero
   if (sigma_out) {
-    for (int64_t j = 0; j < sigma_cap; ++j) sigma_out[j] = j < rn ? sv.sigma[j] : 0.0;
+    for (int64_t j = 0; j < sigma_cap; ++j) sigma_out[j] = j < rc ? sv.sigma[j] : 0.0;
   }
   // scales: core k <- U sqrt(S) = X_j sigma_j^{-1/2};  projection basis G2 = X_j sigma_j^{-3/2}  so that
   // core k+1 <- sqrt(S) Vt = S^{-1/2} U^H Theta = G2^H Theta                                   (tt_tools.jl:754-757)
-  std::vector<double> s1((size_t)rn * batch), s2((size_t)rn * batch);
-  std::vector<int> perm((size_t)rn * batch);
+  std::vector<double> s1((size_t)rc * batch), s2((size_t)rc * batch);
+  std::vector<int> perm((size_t)rc * batch);
   for (int b = 0; b < batch; ++b) {
     const double smax = sv.sigma[(size_t)b * kk];
-    for (int j = 0; j < rn; ++j) {
+    for (int j = 0; j < rc; ++j) {
       const double s = sv.sigma[(size_t)b * kk + j];
       const bool ok = s > 1e-290 && s > smax * 1e-140;
-      s1[(size_t)b * rn + j] = ok ? 1.0 / std::sqrt(s) : 0.0;
-      s2[(size_t)b * rn + j] = ok ? 1.0 / (s * std::sqrt(s)) : 0.0;
-      perm[(size_t)b * rn + j] = sv.perm[(size_t)b * kk + j];
+      s1[(size_t)b * rc + j] = ok ? 1.0 / std::sqrt(s) : 0.0;
+      s2[(size_t)b * rc + j] = ok ? 1.0 / (s * std::sqrt(s)) : 0.0;
+      perm[(size_t)b * rc + j] = sv.perm[(size_t)b * kk + j];
     }
   }
   DevBuf dperm(sizeof(int) * perm.size()), ds1(sizeof(double) * s1.size()), ds2(sizeof(double) * s2.size());
@@ -297,17 +327,34 @@ void tt_bond_truncate(TT<T>& x, int k1, int64_t max_bond, double truncerr, doubl
   TTN_CUDA(cudaMemcpyAsync(ds1.p, s1.data(), ds1.bytes, cudaMemcpyHostToDevice, ctx().stream));
   TTN_CUDA(cudaMemcpyAsync(ds2.p, s2.data(), ds2.bytes, cudaMemcpyHostToDevice, ctx().stream));
 
-  DevBuf newA(sizeof(T) * (size_t)p * rn * batch), G2(sizeof(T) * (size_t)p * rn * batch);
-  gather_cols<T>(sv.X.as<T>(), p, p, dperm.as<int>(), ds1.as<double>(), rn, newA.as<T>(), 1, p, batch, (int64_t)p * kk, rn,
-                 (int64_t)p * rn);
-  gather_cols<T>(sv.X.as<T>(), p, p, dperm.as<int>(), ds2.as<double>(), rn, G2.as<T>(), 1, p, batch, (int64_t)p * kk, rn,
-                 (int64_t)p * rn);
+  DevBuf newA(sizeof(T) * (size_t)p * rn * batch), G2(sizeof(T) * (size_t)pe * rc * batch);
   DevBuf newB(sizeof(T) * (size_t)n2 * rn * rr * batch);
+  if (rc < rn) {
+    fill<T>(newA.as<T>(), (int64_t)p * rn * batch, t_zero<T>());
+    fill<T>(newB.as<T>(), (int64_t)n2 * rn * rr * batch, t_zero<T>());
+  }
+  if (!factored) {
+    gather_cols<T>(sv.X.as<T>(), p, p, dperm.as<int>(), ds1.as<double>(), rc, newA.as<T>(), 1, p, batch, (int64_t)p * kk, rc,
+                   (int64_t)p * rn);
+  } else {
+    DevBuf Us(sizeof(T) * (size_t)pe * rc * batch);   // U' sqrt(S)^{-1}-scaled columns of the small problem
+    gather_cols<T>(sv.X.as<T>(), pe, pe, dperm.as<int>(), ds1.as<double>(), rc, Us.as<T>(), 1, pe, batch, (int64_t)pe * kk, rc,
+                   (int64_t)pe * rc);
+    GemmArgs g;  // core k <- Q_A (U' S^{-1/2} scaled)
+    g.M = p; g.N = rc; g.K = pe;
+    g.A = QA.p; g.sAm = 1; g.sAk = p; g.bA1 = (int64_t)p * r;
+    g.B = Us.p; g.sBk = 1; g.sBn = pe; g.bB1 = (int64_t)pe * rc;
+    g.C = newA.p; g.sCm = 1; g.sCn = p; g.bC1 = (int64_t)p * rn;
+    g.batch1 = batch;
+    gemm<T>(g);
+  }
+  gather_cols<T>(sv.X.as<T>(), pe, pe, dperm.as<int>(), ds2.as<double>(), rc, G2.as<T>(), 1, pe, batch, (int64_t)pe * kk, rc,
+                 (int64_t)pe * rc);
   {
     GemmArgs g;  // newB[s2,kappa,beta] = sum_row conj(G2[row,kappa]) Theta[row,(s2,beta)]
-    g.M = rn; g.N = rr; g.K = p;
-    g.A = G2.p; g.sAm = p; g.sAk = 1; g.conjA = true; g.bA1 = 0; g.bA2 = (int64_t)p * rn;
-    g.B = Theta.p; g.sBk = 1; g.sBn = (int64_t)p * n2; g.bB1 = p; g.bB2 = (int64_t)p * q;
+    g.M = rc; g.N = rr; g.K = pe;
+    g.A = G2.p; g.sAm = pe; g.sAk = 1; g.conjA = true; g.bA1 = 0; g.bA2 = (int64_t)pe * rc;
+    g.B = Theta.p; g.sBk = 1; g.sBn = (int64_t)pe * n2; g.bB1 = pe; g.bB2 = (int64_t)pe * q;
     g.C = newB.p; g.sCm = n2; g.sCn = (int64_t)n2 * rn; g.bC1 = 1; g.bC2 = (int64_t)n2 * rn * rr;
     g.batch1 = n2; g.batch2 = batch;
     gemm<T>(g);

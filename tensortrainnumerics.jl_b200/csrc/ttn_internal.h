@@ -55,6 +55,7 @@ struct Context {
   bool prof_on = false;    // per-kernel-family CUDA-event timing (bench.py roofline pass only)
   std::vector<ProfRec> prof;
   int last_jacobi_sweeps = 0;  // diagnostics: sweeps used by the most recent Jacobi SVD (batch element 0)
+  bool jacobi_noise_floor = false;  // see JAC_FLOOR2 in jacobi.cu
   bool use_cluster_jacobi = true;   // single-matrix SVDs on an 8-SM cluster (TTN_NO_CLUSTER_JACOBI=1 disables; A/B timing)
   bool use_gram_jacobi = false;     // Gram-block Jacobi (DMMA) for large matrices: opt-in with TTN_GRAM_JACOBI=1
 };
@@ -214,9 +215,10 @@ template <class T> void qr_form_q(const T* A, int m, int k, int64_t lda, const T
 template <class T> int jacobi_orth(T* X, int m, int n, int64_t ldx, double* norms, int batch = 1, int64_t bX = 0,
                                    int64_t bnorms = 0);
 // single-matrix path on an 8-CTA cluster (jacobi_cluster.cu); false if the shape is not served
-template <class T> bool jacobi_cluster(T* X, int m, int n, int64_t ldx, int batch, int64_t bX, double tol, int* d_sweeps);
+template <class T> bool jacobi_cluster(T* X, int m, int n, int64_t ldx, int batch, int64_t bX, double tol, const double* frob2,
+                                       double floor_k, int* d_sweeps);
 // Gram-block Jacobi on the DMMA pipe for one large matrix (jacobi_gram.cu); returns sweeps, or -1 if the shape is not served
-template <class T> int jacobi_gram(T* X, int m, int n, int64_t ldx, double tol, int max_sweeps);
+template <class T> int jacobi_gram(T* X, int m, int n, int64_t ldx, double tol, const double* frob2, double floor_k, int max_sweeps);
 // dst (m x r) column j = X[:, perm[j]] * scale[j]   (perm/scale device arrays; per batch strides)
 template <class T> void gather_cols(const T* X, int m, int64_t ldx, const int* perm, const double* scale, int r, T* dst,
                                     int64_t rs, int64_t cs, int batch = 1, int64_t bX = 0, int64_t bperm = 0,
