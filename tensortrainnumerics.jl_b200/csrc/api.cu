@@ -49,6 +49,7 @@ int ttn_init(int device) {
     uint64_t thr = UINT64_MAX;
     TTN_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
     c.use_cluster_jacobi = getenv("TTN_NO_CLUSTER_JACOBI") == nullptr;
+    c.use_cholqr = getenv("TTN_NO_CHOLQR") == nullptr;
     c.use_gram_jacobi = getenv("TTN_GRAM_JACOBI") != nullptr;   // experimental (slower than the scalar block path in round 1)
     c.inited = true;
   }

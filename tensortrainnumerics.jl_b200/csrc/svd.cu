@@ -27,32 +27,52 @@ void svd_left(const T* Theta, int p, int q, int64_t rs, int64_t cs, bool conj, S
     out.sweeps = jacobi_orth<T>(X, p, p, p, out.norms.as<double>(), batch, bX, k);
   } else if (p < q) {
     // W (q x p) = Theta_eff^H
-    DevBuf W(sizeof(T) * (size_t)q * p * batch), tau(sizeof(T) * (size_t)p * batch);
+    DevBuf W(sizeof(T) * (size_t)q * p * batch);
     const int64_t bW = (int64_t)q * p;
     Copy4 c; c.n0 = q; c.n1 = p; c.n2 = batch; c.s0 = cs; c.s1 = rs; c.s2 = bT; c.d0 = 1; c.d1 = q; c.d2 = bW; c.conj = !conj;
     copy4<T>(Theta, W.as<T>(), c);
-    qr_factor<T>(W.as<T>(), q, p, q, tau.as<T>(), batch, bW, p);
+    DevBuf Rb(sizeof(T) * (size_t)p * p * batch);
+    bool have_r = ctx().use_cholqr && cholqr2<T>(W.as<T>(), q, p, q, bW, Rb.as<T>(), nullptr, 0, 0, batch);
+    if (!have_r) {
+      DevBuf tau(sizeof(T) * (size_t)p * batch);
+      qr_factor<T>(W.as<T>(), q, p, q, tau.as<T>(), batch, bW, p);
+    }
     // X = R^H (lower triangular p x p): X[i,j] = conj(R[j,i]), j <= i
-    Copy4 t; t.n0 = p; t.n1 = p; t.n2 = batch; t.s0 = 1; t.s1 = q; t.s2 = bW; t.d0 = p; t.d1 = 1; t.d2 = bX; t.conj = true; t.tri = 1;
-    copy4<T>(W.as<T>(), X, t);
+    Copy4 t; t.n0 = p; t.n1 = p; t.n2 = batch; t.s0 = 1; t.s1 = have_r ? p : q; t.s2 = have_r ? bX : bW;
+    t.d0 = p; t.d1 = 1; t.d2 = bX; t.conj = true; t.tri = 1;
+    copy4<T>(have_r ? Rb.as<T>() : W.as<T>(), X, t);
     out.sweeps = jacobi_orth<T>(X, p, p, p, out.norms.as<double>(), batch, bX, k);
   } else {
-    DevBuf W(sizeof(T) * (size_t)p * q * batch), tau(sizeof(T) * (size_t)q * batch);
+    DevBuf W(sizeof(T) * (size_t)p * q * batch);
     const int64_t bW = (int64_t)p * q;
     Copy4 c; c.n0 = p; c.n1 = q; c.n2 = batch; c.s0 = rs; c.s1 = cs; c.s2 = bT; c.d0 = 1; c.d1 = p; c.d2 = bW; c.conj = conj;
     copy4<T>(Theta, W.as<T>(), c);
-    qr_factor<T>(W.as<T>(), p, q, p, tau.as<T>(), batch, bW, q);
-    // Xr (q x q) = R
-    DevBuf Xr(sizeof(T) * (size_t)q * q * batch);
+    DevBuf Xr(sizeof(T) * (size_t)q * q * batch), Qe(sizeof(T) * (size_t)p * q * batch);
     const int64_t bR = (int64_t)q * q;
-    Copy4 t; t.n0 = q; t.n1 = q; t.n2 = batch; t.s0 = 1; t.s1 = p; t.s2 = bW; t.d0 = 1; t.d1 = q; t.d2 = bR; t.tri = 1;
-    copy4<T>(W.as<T>(), Xr.as<T>(), t);
-    out.sweeps = jacobi_orth<T>(Xr.as<T>(), q, q, q, out.norms.as<double>(), batch, bR, k);
-    // X = Q [Xr; 0]
-    fill<T>(X, (int64_t)p * q * batch, t_zero<T>());
-    Copy4 u; u.n0 = q; u.n1 = q; u.n2 = batch; u.s0 = 1; u.s1 = q; u.s2 = bR; u.d0 = 1; u.d1 = p; u.d2 = bX;
-    copy4<T>(Xr.as<T>(), X, u);
-    qr_apply<T>(W.as<T>(), p, q, p, tau.as<T>(), X, q, p, false, batch, bW, q, bX);
+    const bool have_q = ctx().use_cholqr && cholqr2<T>(W.as<T>(), p, q, p, bW, Xr.as<T>(), Qe.as<T>(), p, bW, batch);
+    if (have_q) {
+      out.sweeps = jacobi_orth<T>(Xr.as<T>(), q, q, q, out.norms.as<double>(), batch, bR, k);
+      GemmArgs g;   // X = Q (R V) = Q * Xr
+      g.M = p; g.N = q; g.K = q;
+      g.A = Qe.p; g.sAm = 1; g.sAk = p; g.bA1 = bW;
+      g.B = Xr.p; g.sBk = 1; g.sBn = q; g.bB1 = bR;
+      g.C = X; g.sCm = 1; g.sCn = p; g.bC1 = bX;
+      g.batch1 = batch;
+      gemm<T>(g);
+    } else {
+      Qe.release();
+      DevBuf tau(sizeof(T) * (size_t)q * batch);
+      qr_factor<T>(W.as<T>(), p, q, p, tau.as<T>(), batch, bW, q);
+      // Xr (q x q) = R
+      Copy4 t; t.n0 = q; t.n1 = q; t.n2 = batch; t.s0 = 1; t.s1 = p; t.s2 = bW; t.d0 = 1; t.d1 = q; t.d2 = bR; t.tri = 1;
+      copy4<T>(W.as<T>(), Xr.as<T>(), t);
+      out.sweeps = jacobi_orth<T>(Xr.as<T>(), q, q, q, out.norms.as<double>(), batch, bR, k);
+      // X = Q [Xr; 0]
+      fill<T>(X, (int64_t)p * q * batch, t_zero<T>());
+      Copy4 u; u.n0 = q; u.n1 = q; u.n2 = batch; u.s0 = 1; u.s1 = q; u.s2 = bR; u.d0 = 1; u.d1 = p; u.d2 = bX;
+      copy4<T>(Xr.as<T>(), X, u);
+      qr_apply<T>(W.as<T>(), p, q, p, tau.as<T>(), X, q, p, false, batch, bW, q, bX);
+    }
   }
 
   // singular values to the host, sorted descending per batch element

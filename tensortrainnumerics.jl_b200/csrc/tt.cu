@@ -276,13 +276,16 @@ void tt_bond_truncate(TT<T>& x, int k1, int64_t max_bond, double truncerr, doubl
     gemm<T>(g);
   } else {
     const int64_t bA = (int64_t)p * r;
-    DevBuf W(sizeof(T) * (size_t)bA * batch), tau(sizeof(T) * (size_t)r * batch), RA(sizeof(T) * (size_t)r * r * batch);
-    TTN_CUDA(cudaMemcpyAsync(W.p, x.cores[k].p, W.bytes, cudaMemcpyDeviceToDevice, ctx().stream));
-    qr_factor<T>(W.as<T>(), p, r, p, tau.as<T>(), batch, bA, r);
+    DevBuf RA(sizeof(T) * (size_t)r * r * batch);
     QA.alloc(sizeof(T) * (size_t)bA * batch);
-    qr_form_q<T>(W.as<T>(), p, r, p, tau.as<T>(), QA.as<T>(), p, batch, bA, r, bA);
-    Copy4 t; t.n0 = r; t.n1 = r; t.n2 = batch; t.s0 = 1; t.s1 = p; t.s2 = bA; t.d0 = 1; t.d1 = r; t.d2 = (int64_t)r * r; t.tri = 1;
-    copy4<T>(W.as<T>(), RA.as<T>(), t);
+    if (!(ctx().use_cholqr && cholqr2<T>(x.core(k), p, r, p, bA, RA.as<T>(), QA.as<T>(), p, bA, batch))) {
+      DevBuf W(sizeof(T) * (size_t)bA * batch), tau(sizeof(T) * (size_t)r * batch);
+      TTN_CUDA(cudaMemcpyAsync(W.p, x.cores[k].p, W.bytes, cudaMemcpyDeviceToDevice, ctx().stream));
+      qr_factor<T>(W.as<T>(), p, r, p, tau.as<T>(), batch, bA, r);
+      qr_form_q<T>(W.as<T>(), p, r, p, tau.as<T>(), QA.as<T>(), p, batch, bA, r, bA);
+      Copy4 t; t.n0 = r; t.n1 = r; t.n2 = batch; t.s0 = 1; t.s1 = p; t.s2 = bA; t.d0 = 1; t.d1 = r; t.d2 = (int64_t)r * r; t.tri = 1;
+      copy4<T>(W.as<T>(), RA.as<T>(), t);
+    }
     GemmArgs g;  // Theta'[gamma',(s2,beta)] = sum_gamma R_A[gamma',gamma] B[s2,gamma,beta]
     g.M = r; g.N = rr; g.K = r;
     g.A = RA.p; g.sAm = 1; g.sAk = r; g.bA1 = 0; g.bA2 = (int64_t)r * r;

@@ -55,6 +55,7 @@ struct Context {
   bool prof_on = false;    // per-kernel-family CUDA-event timing (bench.py roofline pass only)
   std::vector<ProfRec> prof;
   int last_jacobi_sweeps = 0;  // diagnostics: sweeps used by the most recent Jacobi SVD (batch element 0)
+  bool use_cholqr = true;           // CholeskyQR2 fast path for tall-skinny QR (TTN_NO_CHOLQR=1 disables)
   bool jacobi_noise_floor = false;  // see JAC_FLOOR2 in jacobi.cu
   bool use_cluster_jacobi = true;   // single-matrix SVDs on an 8-SM cluster (TTN_NO_CLUSTER_JACOBI=1 disables; A/B timing)
   bool use_gram_jacobi = false;     // Gram-block Jacobi (DMMA) for large matrices: opt-in with TTN_GRAM_JACOBI=1
@@ -203,6 +204,11 @@ template <class T> void qr_factor(T* A, int m, int n, int64_t lda, T* tau, int b
 // where Q = H_0 ... H_{k-1} is held in (A, tau) as produced by qr_factor;  col0: only columns >= col0 of C
 template <class T> void qr_apply(const T* A, int m, int k, int64_t lda, const T* tau, T* C, int nc, int64_t ldc, bool trans,
                                  int batch = 1, int64_t bA = 0, int64_t btau = 0, int64_t bC = 0);
+// CholeskyQR2 on the DMMA pipe for tall-skinny, well-conditioned matrices (cholqr.cu).  R: k x k upper (ld k, batch stride
+// k*k); Q optional.  Returns false when the shape is not served or a matrix is rejected as ill conditioned: the caller
+// then uses the Householder path above.
+template <class T> bool cholqr2_fits(int m, int k);
+template <class T> bool cholqr2(const T* A, int m, int k, int64_t lda, int64_t bA, T* R, T* Q, int64_t ldq, int64_t bQ, int batch);
 // thin Q (m x k) explicitly
 template <class T> void qr_form_q(const T* A, int m, int k, int64_t lda, const T* tau, T* Q, int64_t ldq,
                                   int batch = 1, int64_t bA = 0, int64_t btau = 0, int64_t bQ = 0);
