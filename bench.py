@@ -332,6 +332,11 @@ def run_ours(args, rank, local_rank, world):
         bt["value"] = world * bt["vectors_per_rank"] / bt["seconds"]
         bt["n_gpus"] = world
         extras["batch_cfg5"] = bt
+        if world > 1:
+            # cfg4 matvec sharded on the spectator bond, all-gather fused into the last GEMM
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import shard_bench
+            extras["matvec_cfg4_sharded"] = shard_bench.run(torch, dist, rank, world, chi=1024, w=5, reps=10, krylovdim=8)
         if rank == 0:
             extras["matvec_cfg4"] = bench_matvec(t, torch, stream, peak64)
             extras["dmrg_sweep"] = bench_dmrg(t, args.dmrg_chi)

@@ -198,3 +198,24 @@ def test_sharded_eigsolve_single_rank_matches_dense():
     op.free()
     ev = np.linalg.eigvalsh(K)
     assert abs(th - ev[0]) < 1e-9 * max(1.0, abs(ev[0]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cond", [1e2, 1e6, 1e12])
+@pytest.mark.parametrize("shape", [(1024, 128), (128, 1024), (300, 64), (96, 96)])
+def test_svdtrunc_across_condition_numbers(shape, cond):
+    """`_svdtrunc` (tt_cross_interpolation.jl:149-166) on prescribed spectra: the CholeskyQR2 preconditioner is taken for
+    well-conditioned tall/wide inputs and must hand over to Householder QR as the conditioning degrades; singular values to
+    1e-12 of sigma_1 (gesdd's absolute accuracy), reconstruction to 1e-12."""
+    import ttn_b200 as t
+    rng = np.random.default_rng(int(np.log10(cond)) + shape[0])
+    m, n = shape
+    k = min(m, n)
+    U, _ = np.linalg.qr(rng.standard_normal((m, k)))
+    V, _ = np.linalg.qr(rng.standard_normal((n, k)))
+    s = np.logspace(0, -np.log10(cond), k)
+    A = np.asfortranarray((U * s) @ V.T)
+    Ug, sg, Vtg = t.svdtrunc(A)
+    assert np.abs(sg - s).max() < 1e-12
+    assert relerr((Ug * sg) @ Vtg, A) < 1e-12
+    assert np.abs(Ug.T @ Ug - np.eye(k)).max() < 1e-11

@@ -4,7 +4,7 @@
 
 Times (CUDA events on the library stream, max over ranks) the fused matvec + all-gather (tile stores to peer memory in
 the GEMM epilogue, epoch-flag handshake) and, for comparison, the same local slice followed by an NCCL all-gather
-(torch.distributed.all_gather_into_tensor).  Checks the gathered vector against the NumPy oracle at a small size first.
+(torch.distributed.all_gather_into_tensor).  Checks the gathered vector against a dense NumPy contraction at a small size first.
 Prints one JSON line on rank 0.
 """
 import argparse
@@ -17,29 +17,15 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--chi", type=int, default=1024)
-    ap.add_argument("--w", type=int, default=5)
-    ap.add_argument("--reps", type=int, default=20)
-    ap.add_argument("--krylovdim", type=int, default=8)
-    args = ap.parse_args()
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    import torch
-    import torch.distributed as dist
-    torch.cuda.set_device(local)
-    if world > 1:
-        sys.stdout.flush()
-        saved = os.dup(1); os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-            dist.barrier(); torch.cuda.synchronize()
-        finally:
-            sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
+def run(torch, dist, rank, world, chi=1024, w=5, reps=20, krylovdim=8, with_nccl=True):
+    """Sharded cfg4 matvec on an initialised process group (dist may be None for world == 1); returns the result dict
+    (identical on every rank)."""
+    class A:  # argument holder so the body below reads like the script
+        pass
+    args = A()
+    args.chi, args.w, args.reps, args.krylovdim = chi, w, reps, krylovdim
     import ttn_b200 as t
     from ttn_b200 import _lib
     lib = _lib.lib()
@@ -57,8 +43,7 @@ def main():
         if world > 1:
             dist.barrier()
 
-    # ---- parity at a small size against the oracle (every rank checks its complete gathered vector) ------------
-    import ttn_oracle as o
+    # ---- parity at a small size against a dense NumPy contraction (every rank checks its complete gathered vector) ------------
     rng = np.random.default_rng(4)
     w, nn, cs = 3, 4, 40
     G = rng.standard_normal((w, cs, cs)); H = rng.standard_normal((w, cs, cs)); Am = rng.standard_normal((w, nn, nn, w))
@@ -66,7 +51,7 @@ def main():
     op = t.ShardedMatvec(G, Am, H, rank, world, exchange)
     Y = op.apply(V)
     barrier()
-    Yref = o.dmrg_matvec2(G, Am, V, H, symmetrize=False)
+    Yref = np.einsum("yad,ybez,def,zcf->abc", G, Am, V, H, optimize=True)   # K_matfree, dmrg.jl:239-244 (one application)
     err = float(np.linalg.norm(Y - Yref) / np.linalg.norm(Yref))
     werr = op.error()
     barrier()
@@ -111,7 +96,7 @@ def main():
     # NCCL variant: unbound operator (local slice only) + all_gather_into_tensor on torch's stream
     plain = t.ShardedMatvec(G, Am, H, rank, world, None)
     ms_nccl = None
-    if world > 1 and chi % world == 0:
+    if with_nccl and world > 1 and chi % world == 0:
         n_el = chi * nn * chi
         full = torch.empty(n_el, dtype=torch.float64, device="cuda")
         lib_stream = stream
@@ -141,19 +126,45 @@ def main():
         dist.all_gather_object(thetas, theta)
     else:
         thetas = [theta]
-    if rank == 0:
-        print(json.dumps({
-            "metric": "sharded local-matvec FP64 TFLOP/s", "n_gpus": world, "chi": chi, "w": w, "gflop": flops / 1e9,
-            "fused_ms": ms_fused, "fused_tflops": flops / ms_fused / 1e9,
-            "nccl_allgather_ms": ms_nccl, "nccl_tflops": (flops / ms_nccl / 1e9) if ms_nccl else None,
-            "local_slice_only_ms": ms_local,
-            "lanczos_bond_solve_ms": ms_eig, "krylovdim": args.krylovdim,
-            "theta_identical_on_all_ranks": bool(all(x == thetas[0] for x in thetas)),
-            "parity_small_rel_err_per_rank": [e[0] for e in errs], "wait_timeouts": [e[1] for e in errs] + [werr2],
-            "exchange": "GEMM epilogue stores to peer buffers over NVLink (CUDA IPC), epoch flags; %d bytes per rank per matvec"
-                        % (V.nbytes // world * (world - 1))}), flush=True)
+    res = {
+        "metric": "sharded local-matvec FP64 TFLOP/s", "n_gpus": world, "chi": chi, "w": w, "gflop": flops / 1e9,
+        "fused_ms": ms_fused, "fused_tflops": flops / ms_fused / 1e9,
+        "nccl_allgather_ms": ms_nccl, "nccl_tflops": (flops / ms_nccl / 1e9) if ms_nccl else None,
+        "local_slice_only_ms": ms_local,
+        "lanczos_bond_solve_ms": ms_eig, "krylovdim": args.krylovdim,
+        "theta_identical_on_all_ranks": bool(all(x == thetas[0] for x in thetas)),
+        "parity_small_rel_err_per_rank": [e[0] for e in errs], "wait_timeouts": [e[1] for e in errs] + [werr2],
+        "exchange": "GEMM epilogue stores to peer buffers over NVLink (CUDA IPC), epoch flags; %d bytes per rank per matvec"
+                    % (V.nbytes // world * (world - 1))}
     barrier()
     fused.free(); plain.free()
+    _lib.check(lib.ttn_dev_free(dV)); _lib.check(lib.ttn_dev_free(dx))
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--chi", type=int, default=1024)
+    ap.add_argument("--w", type=int, default=5)
+    ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--krylovdim", type=int, default=8)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    if world > 1:
+        sys.stdout.flush()
+        saved = os.dup(1); os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier(); torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
+    res = run(torch, dist if world > 1 else None, rank, world, args.chi, args.w, args.reps, args.krylovdim)
+    if rank == 0:
+        print(json.dumps(res), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
