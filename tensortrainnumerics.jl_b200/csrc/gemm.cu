@@ -8,7 +8,7 @@
 // explicit element strides plus two batch dimensions, so the (s,l,r)/(l,s,r) permutes that the reference
 // performs with `permutedims` (tt_tools.jl:746-747, dmrg.jl:39, tdvp.jl:54-55) are folded into the loads.
 //
-// Design (B200): 256-thread CTAs, BK=16 k-slab, register-staged double buffering through padded shared
+// Design (B200): 256-thread CTAs, BK=16 k-slabs streamed by a 4-stage cp.async (LDGSTS) pipeline into padded shared
 // memory (pitch ≡ 4 mod 16 doubles → the m8n8k4 fragment loads are bank-conflict free), each warp owns a
 // WM x WN accumulator block held in registers and issues mma.sync.m8n8k4.f64.  ComplexF64 runs as four
 // real DMMA products on split re/im fragments.  sm_100a has no f64 kind for tcgen05.mma, so DMMA via
@@ -22,9 +22,21 @@ namespace {
 
 constexpr int BK = 16;
 constexpr int NT = 256;
+constexpr int NSTAGE = 4;       // cp.async pipeline depth (k-slabs in flight)
 
 template <class T> struct Pad { static constexpr int v = 4; };
 template <> struct Pad<zc> { static constexpr int v = 2; };
+
+// 8 / 16-byte asynchronous global -> shared copy (LDGSTS); src_bytes = 0 zero-fills the destination (out-of-range elements)
+template <class T>
+__device__ __forceinline__ void cp_async_elem(T* smem_dst, const T* gsrc, bool valid) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? (int)sizeof(T) : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;\n" ::"r"(dst), "l"(gsrc), "n"(sizeof(T)), "r"(n));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 template <class T, int BM, int BN, int WM, int WN, bool AMAJ, bool BMAJ>
 __global__ void __launch_bounds__(NT) gemm_kernel(const GemmArgs g) {
@@ -33,12 +45,12 @@ __global__ void __launch_bounds__(NT) gemm_kernel(const GemmArgs g) {
   constexpr int EA = BM * BK / NT, EB = BN * BK / NT;
   constexpr int MT = WM / 8, NTL = WN / 8;
   constexpr int WARPS_M = BM / WM;
+  constexpr int STAGE = BK * (PA + PB);              // elements per pipeline stage
   static_assert((BM / WM) * (BN / WN) == NT / 32, "warp layout must cover the CTA tile");
   static_assert(BM * BK % NT == 0 && BN * BK % NT == 0, "tile loads must divide evenly");
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* As = reinterpret_cast<T*>(smem_raw);            // [2][BK][PA]
-  T* Bs = As + 2 * BK * PA;                          // [2][BK][PB]
+  T* Sm = reinterpret_cast<T*>(smem_raw);            // [NSTAGE][ A: [BK][PA] | B: [BK][PB] ]
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -57,77 +69,77 @@ __global__ void __launch_bounds__(NT) gemm_kernel(const GemmArgs g) {
 #pragma unroll
     for (int j = 0; j < NTL; ++j) acc[i][j].zero();
 
-  T ra[EA], rb[EB];
   const int nkt = (g.K + BK - 1) / BK;
 
-  auto load_global = [&](int kt) {
-    const int k0 = kt * BK;
+  // per-thread element coordinates inside a k-slab are fixed; only the k offset advances
+  int am[EA], ak[EA], bn[EB], bk[EB];
+  int64_t aoff[EA], boff[EB];
+  bool aok[EA], bok[EB];
 #pragma unroll
-    for (int r = 0; r < EA; ++r) {
-      const int idx = tid + r * NT;
-      const int m = AMAJ ? (idx % BM) : (idx / BK);
-      const int k = AMAJ ? (idx / BM) : (idx % BK);
-      const int gm = m0 + m, gk = k0 + k;
-      T v = t_zero<T>();
-      if (gm < g.M && gk < g.K) v = A[(int64_t)gm * g.sAm + (int64_t)gk * g.sAk];
-      ra[r] = v;
-    }
-#pragma unroll
-    for (int r = 0; r < EB; ++r) {
-      const int idx = tid + r * NT;
-      const int n = BMAJ ? (idx % BN) : (idx / BK);
-      const int k = BMAJ ? (idx / BN) : (idx % BK);
-      const int gn = n0 + n, gk = k0 + k;
-      T v = t_zero<T>();
-      if (gn < g.N && gk < g.K) v = B[(int64_t)gk * g.sBk + (int64_t)gn * g.sBn];
-      rb[r] = v;
-    }
-  };
-  auto store_smem = [&](int buf) {
-    T* as = As + buf * BK * PA;
-    T* bs = Bs + buf * BK * PB;
-#pragma unroll
-    for (int r = 0; r < EA; ++r) {
-      const int idx = tid + r * NT;
-      const int m = AMAJ ? (idx % BM) : (idx / BK);
-      const int k = AMAJ ? (idx / BM) : (idx % BK);
-      as[k * PA + m] = g.conjA ? t_conj(ra[r]) : ra[r];
-    }
-#pragma unroll
-    for (int r = 0; r < EB; ++r) {
-      const int idx = tid + r * NT;
-      const int n = BMAJ ? (idx % BN) : (idx / BK);
-      const int k = BMAJ ? (idx / BN) : (idx % BK);
-      bs[k * PB + n] = g.conjB ? t_conj(rb[r]) : rb[r];
-    }
-  };
-
-  if (nkt > 0) {
-    load_global(0);
-    store_smem(0);
+  for (int r = 0; r < EA; ++r) {
+    const int idx = tid + r * NT;
+    am[r] = AMAJ ? (idx % BM) : (idx / BK);
+    ak[r] = AMAJ ? (idx / BM) : (idx % BK);
+    aok[r] = m0 + am[r] < g.M;
+    aoff[r] = (int64_t)(m0 + am[r]) * g.sAm + (int64_t)ak[r] * g.sAk;
   }
-  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < EB; ++r) {
+    const int idx = tid + r * NT;
+    bn[r] = BMAJ ? (idx % BN) : (idx / BK);
+    bk[r] = BMAJ ? (idx / BN) : (idx % BK);
+    bok[r] = n0 + bn[r] < g.N;
+    boff[r] = (int64_t)bk[r] * g.sBk + (int64_t)(n0 + bn[r]) * g.sBn;
+  }
+  auto issue = [&](int kt) {
+    if (kt < nkt) {
+      T* as = Sm + (size_t)(kt % NSTAGE) * STAGE;
+      T* bs = as + BK * PA;
+      const int k0 = kt * BK;
+#pragma unroll
+      for (int r = 0; r < EA; ++r) {
+        const bool ok = aok[r] && k0 + ak[r] < g.K;
+        cp_async_elem<T>(as + ak[r] * PA + am[r], ok ? A + aoff[r] + (int64_t)k0 * g.sAk : A, ok);
+      }
+#pragma unroll
+      for (int r = 0; r < EB; ++r) {
+        const bool ok = bok[r] && k0 + bk[r] < g.K;
+        cp_async_elem<T>(bs + bk[r] * PB + bn[r], ok ? B + boff[r] + (int64_t)k0 * g.sBk : B, ok);
+      }
+    }
+    cp_async_commit();     // one group per slab, empty past the end, so that wait_group counts stay uniform
+  };
 
+#pragma unroll
+  for (int s = 0; s < NSTAGE - 1; ++s) issue(s);
+
+  const bool cja = g.conjA, cjb = g.conjB;
   for (int kt = 0; kt < nkt; ++kt) {
-    const int buf = kt & 1;
-    if (kt + 1 < nkt) load_global(kt + 1);
-    const T* as = As + buf * BK * PA;
-    const T* bs = Bs + buf * BK * PB;
+    cp_async_wait<NSTAGE - 2>();      // slab kt has landed (for this thread's copies) ...
+    __syncthreads();                  // ... and for everyone; slab kt-1 is no longer being read
+    issue(kt + NSTAGE - 1);           // refills the buffer of slab kt-1
+    const T* as = Sm + (size_t)(kt % NSTAGE) * STAGE;
+    const T* bs = as + BK * PA;
 #pragma unroll
     for (int kk = 0; kk < BK; kk += 4) {
       T af[MT], bf[NTL];
 #pragma unroll
-      for (int i = 0; i < MT; ++i) af[i] = as[(kk + t4) * PA + wm0 + i * 8 + g8];
+      for (int i = 0; i < MT; ++i) {
+        const T v = as[(kk + t4) * PA + wm0 + i * 8 + g8];
+        af[i] = (is_cplx<T>::value && cja) ? t_conj(v) : v;
+      }
 #pragma unroll
-      for (int j = 0; j < NTL; ++j) bf[j] = bs[(kk + t4) * PB + wn0 + j * 8 + g8];
+      for (int j = 0; j < NTL; ++j) {
+        const T v = bs[(kk + t4) * PB + wn0 + j * 8 + g8];
+        bf[j] = (is_cplx<T>::value && cjb) ? t_conj(v) : v;
+      }
 #pragma unroll
       for (int i = 0; i < MT; ++i)
 #pragma unroll
         for (int j = 0; j < NTL; ++j) acc[i][j].mma(af[i], bf[j]);
     }
-    if (kt + 1 < nkt) store_smem(buf ^ 1);
-    __syncthreads();
   }
+  cp_async_wait<0>();
 
   // epilogue: C = alpha*acc + beta*C, written straight from the DMMA accumulator layout
   const bool has_beta = (g.beta != 0.0);
@@ -157,7 +169,7 @@ __global__ void __launch_bounds__(NT) gemm_kernel(const GemmArgs g) {
 template <class T, int BM, int BN, int WM, int WN, bool AMAJ, bool BMAJ>
 void launch_cfg(const GemmArgs& g) {
   constexpr int PAD = Pad<T>::v;
-  const size_t smem = sizeof(T) * 2 * BK * ((BM + PAD) + (BN + PAD));
+  const size_t smem = sizeof(T) * NSTAGE * BK * ((BM + PAD) + (BN + PAD));
   auto kern = gemm_kernel<T, BM, BN, WM, WN, AMAJ, BMAJ>;
   static bool attr_done = false;
   if (!attr_done) {
