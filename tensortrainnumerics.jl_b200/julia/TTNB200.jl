@@ -241,6 +241,34 @@ tdvp(H, u0, steps::Vector{Float64}; kwargs...) = _tdvp(0, H, u0, steps; kwargs..
 tdvp2(H, u0, steps::Vector{Float64}; kwargs...) = _tdvp(1, H, u0, steps; kwargs...)
 
 """Re-point the reference's exported hot-path methods at the B200 implementations."""
+# ---- one bond problem sharded over the GPUs of a node (SURVEY.md section 8(e)); `allgather` is e.g. b -> MPI.Allgather(b, comm) ----
+mutable struct ShardedMatvec
+    h::Ptr{Cvoid}
+    function ShardedMatvec(G::Array{T, 3}, Amid::Array{T, 4}, H::Array{T, 3}, rank::Int, nranks::Int, allgather) where {T <: Union{Float64, ComplexF64}}
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        GC.@preserve G Amid H check(ccall((:ttn_shard_matvec_create, LIB), Cint,
+            (Cint, Cint, Cint, Cint, Cint, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Ptr{Ptr{Cvoid}}),
+            T === Float64 ? 0 : 1, size(G, 1), size(H, 1), size(G, 2), size(H, 2), size(Amid, 2), G, Amid, H, rank, nranks, out))
+        mv = new(out[])
+        finalizer(m -> ccall((:ttn_shard_matvec_free, LIB), Cint, (Ptr{Cvoid},), m.h), mv)
+        if nranks > 1
+            mine = Vector{UInt8}(undef, 192)
+            check(ccall((:ttn_shard_matvec_handles, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}), mv.h, mine))
+            all = allgather(mine)::Vector{UInt8}                  # nranks * 192 bytes in rank order
+            check(ccall((:ttn_shard_matvec_bind, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}), mv.h, all))
+        end
+        return mv
+    end
+end
+
+"lowest eigenpair of the sharded effective operator; `x_dev` is a device pointer (start vector in, eigenvector out)"
+function shard_eigsolve(mv::ShardedMatvec, x_dev::Ptr{Cvoid}; krylovdim = 8, maxiter = 1, tol = 1.0e-10)
+    theta = Ref{Cdouble}(0.0); nmv = Ref{Cint}(0)
+    check(ccall((:ttn_shard_eigsolve, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Cdouble, Ptr{Cdouble}, Ptr{Cint}),
+                mv.h, x_dev, krylovdim, maxiter, tol, theta, nmv))
+    return theta[], Int(nmv[])
+end
+
 function override!()
     @eval TensorTrainNumerics begin
         Base.:*(A::TToperator{T, N}, v::TTvector{T, N}) where {T <: Union{Float64, ComplexF64}, N} = $(apply)(A, v)
