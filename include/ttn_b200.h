@@ -112,10 +112,11 @@ typedef struct {
   const int64_t* rmax_schedule;  int n_rmax_schedule;
   int64_t rmax;                /* mals_linsolve rmax */
   int sweep_count;             /* als_linsolve: number of half sweeps (src/solvers/als.jl:198-222) */
-  int it_solver;               /* accepted for signature parity; local problems are always solved matrix-free */
+  int it_solver;               /* linear local problems: 0 = dense direct solve (K_full + `\`, as the reference) while the
+                                * window has at most max(itslv_thresh, 2048) unknowns, matrix-free GMRES beyond; 1 = always GMRES */
   int linsolv_maxiter;         /* Krylov iteration cap per local solve */
   double linsolv_tol;          /* Krylov tolerance per local solve */
-  int itslv_thresh;            /* accepted for signature parity */
+  int itslv_thresh;            /* see it_solver (dmrg.jl:92-177); eigen problems are always solved by Lanczos */
   int krylovdim;               /* Lanczos / GMRES subspace size (KrylovKit default 30) */
   int symmetrize;              /* dmrg_*: apply 0.5*(K + K^T) like src/solvers/dmrg.jl:241 (1) or K only (0) */
 } ttn_solver_params;

@@ -467,7 +467,8 @@ def _solve_lin(fn, A, b, x0, p):
 def als_linsolve(A, b, tt_start, sweep_count=2, it_solver=False, r_itsolver=5000, return_info=False,
                  linsolv_maxiter=200, krylovdim=30):
     """src/solvers/als.jl:161-225 (`sweep_count` counts half sweeps, als.jl:198-222)."""
-    p, keep = _params(sweep_count=int(sweep_count), linsolv_maxiter=int(linsolv_maxiter), krylovdim=int(krylovdim))
+    p, keep = _params(sweep_count=int(sweep_count), linsolv_maxiter=int(linsolv_maxiter), krylovdim=int(krylovdim),
+                      it_solver=int(bool(it_solver)))
     x, host, res = _solve_lin(_lib.lib().ttn_als_linsolve, A, b, tt_start, p)
     x = _ret(x, host)
     return (x, {"residual": res}) if return_info else x
@@ -539,7 +540,7 @@ def dmrg_linsolve(A, b, tt_start, sweep_count=2, N=2, tol=1e-12, sweep_schedule=
         linsolv_tol = max(math.sqrt(tol), 1e-8)
     p, keep = _params(N=int(N), tol=float(tol), sweep_schedule=sweep_schedule, rmax_schedule=rmax_schedule,
                       linsolv_maxiter=int(linsolv_maxiter), linsolv_tol=float(linsolv_tol), krylovdim=int(krylovdim),
-                      symmetrize=int(bool(symmetrize)))
+                      symmetrize=int(bool(symmetrize)), it_solver=int(bool(it_solver)), itslv_thresh=int(itslv_thresh))
     x, host, res = _solve_lin(_lib.lib().ttn_dmrg_linsolve, A, b, tt_start, p)
     x = _ret(x, host)
     return (x, {"residual": res}) if return_info else x

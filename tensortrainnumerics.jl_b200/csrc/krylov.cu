@@ -144,6 +144,66 @@ double lanczos_lowest(LocalOp<T>& op, T* x, int krylovdim, int maxiter, double t
   return theta;
 }
 
+namespace {
+// back substitution R x = y for the upper triangle of a column-major N x N matrix; one CTA, x staged in shared memory
+template <class T>
+__global__ void __launch_bounds__(256) trsv_upper_kernel(const T* __restrict__ R, int N, int64_t ld, T* __restrict__ y) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* x = reinterpret_cast<T*>(smem_raw);
+  __shared__ T s_xj;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < N; i += 256) x[i] = y[i];
+  __syncthreads();
+  for (int j = N - 1; j >= 0; --j) {
+    if (tid == 0) {
+      const T d = R[j + (int64_t)j * ld];
+      const double den = t_abs2(d);
+      const T v = x[j];
+      // x_j = v / d (complex-safe); a zero pivot propagates inf/nan exactly like LAPACK's `\` on a singular K
+      const T q = t_scale(t_mul(v, t_conj(d)), 1.0 / den);
+      x[j] = q;
+      s_xj = q;
+    }
+    __syncthreads();
+    const T xj = s_xj;
+    const T* col = R + (int64_t)j * ld;
+    for (int i = tid; i < j; i += 256) x[i] = t_sub(x[i], t_mul(col[i], xj));
+    __syncthreads();
+  }
+  for (int i = tid; i < N; i += 256) y[i] = x[i];
+}
+}  // namespace
+
+template <class T>
+void dense_solve(LocalOp<T>& op, const T* rhs, T* x) {
+  const int64_t n64 = op.size();
+  ttn_assert(n64 <= 8192, 7, "dense_solve: window too large");
+  const int N = (int)n64;
+  DevBuf Id(sizeof(T) * (size_t)N * N), K(sizeof(T) * (size_t)N * N), tau(sizeof(T) * (size_t)N);
+  set_identity<T>(Id.as<T>(), N, N, N);
+  op.apply_batch(Id.as<T>(), K.as<T>(), N);          // column j of K = K e_j
+  Id.release();
+  qr_factor<T>(K.as<T>(), N, N, N, tau.as<T>());
+  TTN_CUDA(cudaMemcpyAsync(x, rhs, sizeof(T) * (size_t)N, cudaMemcpyDeviceToDevice, ctx().stream));
+  qr_apply<T>(K.as<T>(), N, N, N, tau.as<T>(), x, 1, N, true);
+  static bool attr_done = false;
+  if (!attr_done) {
+    TTN_CUDA(cudaFuncSetAttribute(trsv_upper_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * (int)sizeof(T)));
+    attr_done = true;
+  }
+  trsv_upper_kernel<T><<<1, 256, sizeof(T) * (size_t)N, ctx().stream>>>(K.as<T>(), N, N, x);
+  TTN_CHECK_LAUNCH();
+  ctx().launches++;
+  TTN_CUDA(cudaStreamSynchronize(ctx().stream));     // K / tau are released when this scope ends
+}
+
+template <class T>
+void local_linsolve(LocalOp<T>& op, const T* rhs, T* x, int krylovdim, int maxiter, double tol, const ttn_solver_params& p) {
+  const int64_t dense_max = std::max<int64_t>(p.itslv_thresh, 2048);
+  if (!p.it_solver && op.size() <= dense_max) dense_solve<T>(op, rhs, x);
+  else gmres_solve<T>(op, rhs, x, krylovdim, maxiter, tol, nullptr);
+}
+
 template <class T>
 void gmres_solve(LocalOp<T>& op, const T* rhs, T* x, int krylovdim, int maxiter, double tol, KrylovInfo* info) {
   typedef typename HostScalar<T>::type S;
@@ -306,6 +366,8 @@ void lanczos_expm(LocalOp<T>& op, T* x, double tre, double tim, int krylovdim, i
 #define INST(T)                                                                                         \
   template double lanczos_lowest<T>(LocalOp<T>&, T*, int, int, double, KrylovInfo*);                    \
   template void gmres_solve<T>(LocalOp<T>&, const T*, T*, int, int, double, KrylovInfo*);               \
+  template void dense_solve<T>(LocalOp<T>&, const T*, T*);                                                \
+  template void local_linsolve<T>(LocalOp<T>&, const T*, T*, int, int, double, const ttn_solver_params&); \
   template void lanczos_expm<T>(LocalOp<T>&, T*, double, double, int, int, double, KrylovInfo*);
 INST(double)
 INST(zc)

@@ -68,41 +68,47 @@ void LocalOp<T>::setup(const T* Lenv, int chil, int wl, const T* Renv, int chir,
   if (!zero_site) T2.alloc(sizeof(T) * (size_t)chi_l * nn * w_r * chi_r);
 }
 
+// One pass of the three-GEMM chain on `nvec` window vectors stored back to back (V, Y: (chi_l, nn, chi_r, nvec)).
 template <class T>
-static void localop_pass(LocalOp<T>& op, const T* Lx, const T* Wx, const T* Rx, const T* V, T* Y, double alpha, double beta) {
+static void localop_pass(LocalOp<T>& op, const T* Lx, const T* Wx, const T* Rx, const T* V, T* Y, double alpha, double beta,
+                         int nvec, T* T1, T* T2) {
   const int cl = op.chi_l, cr = op.chi_r, wl = op.w_l, wr = op.w_r, nn = op.nn;
   {
-    GemmArgs g;  // T1[(a,y),(e,f)] = L[(a,y),d] V[d,(e,f)]
-    g.M = cl * wl; g.N = nn * cr; g.K = cl;
+    GemmArgs g;  // T1[(a,y),(e,f,j)] = L[(a,y),d] V[d,(e,f,j)]
+    g.M = cl * wl; g.N = nn * cr * nvec; g.K = cl;
     g.A = Lx; g.sAm = 1; g.sAk = (int64_t)cl * wl;
     g.B = V; g.sBk = 1; g.sBn = cl;
-    g.C = op.T1.p; g.sCm = 1; g.sCn = (int64_t)cl * wl;
+    g.C = T1; g.sCm = 1; g.sCn = (int64_t)cl * wl;
     gemm<T>(g);
   }
   if (op.zero_site) {
-    GemmArgs g;  // Y[a,c] = T1[a,(y,f)] R[(y,f),c]
+    GemmArgs g;  // Y[a,c,j] = T1[a,(y,f),j] R[(y,f),c]
     g.M = cl; g.N = cr; g.K = wr * cr;
-    g.A = op.T1.p; g.sAm = 1; g.sAk = cl;
+    g.A = T1; g.sAm = 1; g.sAk = cl; g.bA1 = (int64_t)cl * wl * cr;
     g.B = Rx; g.sBk = 1; g.sBn = (int64_t)wr * cr;
-    g.C = Y; g.sCm = 1; g.sCn = cl; g.alpha = alpha; g.beta = beta;
+    g.C = Y; g.sCm = 1; g.sCn = cl; g.bC1 = (int64_t)cl * cr; g.alpha = alpha; g.beta = beta;
+    g.batch1 = nvec;
     gemm<T>(g);
     return;
   }
   {
-    GemmArgs g;  // T2[a,(b,z),f] = T1[a,(y,e),f] W'[(y,e),(b,z)]   (batch over f)
+    GemmArgs g;  // T2[a,(b,z),(f,j)] = T1[a,(y,e),(f,j)] W'[(y,e),(b,z)]   (batch over (f,j))
     g.M = cl; g.N = nn * wr; g.K = wl * nn;
-    g.A = op.T1.p; g.sAm = 1; g.sAk = cl; g.bA1 = (int64_t)cl * wl * nn;
+    g.A = T1; g.sAm = 1; g.sAk = cl; g.bA1 = (int64_t)cl * wl * nn;
     g.B = Wx; g.sBk = 1; g.sBn = (int64_t)wl * nn; g.bB1 = 0;
-    g.C = op.T2.p; g.sCm = 1; g.sCn = cl; g.bC1 = (int64_t)cl * nn * wr;
-    g.batch1 = cr;
+    g.C = T2; g.sCm = 1; g.sCn = cl; g.bC1 = (int64_t)cl * nn * wr;
+    const int64_t nb = (int64_t)cr * nvec;
+    if (nb <= 65535) { g.batch1 = (int)nb; }
+    else { g.batch1 = cr; g.batch2 = nvec; g.bA2 = g.bA1 * cr; g.bC2 = g.bC1 * cr; }
     gemm<T>(g);
   }
   {
-    GemmArgs g;  // Y[(a,b),c] = T2[(a,b),(z,f)] R[(z,f),c]
+    GemmArgs g;  // Y[(a,b),c,j] = T2[(a,b),(z,f),j] R[(z,f),c]
     g.M = cl * nn; g.N = cr; g.K = wr * cr;
-    g.A = op.T2.p; g.sAm = 1; g.sAk = (int64_t)cl * nn;
+    g.A = T2; g.sAm = 1; g.sAk = (int64_t)cl * nn; g.bA1 = (int64_t)cl * nn * wr * cr;
     g.B = Rx; g.sBk = 1; g.sBn = (int64_t)wr * cr;
-    g.C = Y; g.sCm = 1; g.sCn = (int64_t)cl * nn; g.alpha = alpha; g.beta = beta;
+    g.C = Y; g.sCm = 1; g.sCn = (int64_t)cl * nn; g.bC1 = (int64_t)cl * nn * cr; g.alpha = alpha; g.beta = beta;
+    g.batch1 = nvec;
     gemm<T>(g);
   }
 }
@@ -110,11 +116,25 @@ static void localop_pass(LocalOp<T>& op, const T* Lx, const T* Wx, const T* Rx, 
 template <class T>
 void LocalOp<T>::apply(const T* V, T* Y) {
   if (ext_apply) { ext_apply(V, Y); return; }
+  apply_batch(V, Y, 1);
+}
+
+template <class T>
+void LocalOp<T>::apply_batch(const T* V, T* Y, int nvec) {
+  ttn_assert(!ext_apply, 7, "apply_batch: not available for an external operator");
+  DevBuf B1, B2;
+  T* t1 = T1.as<T>();
+  T* t2 = T2.as<T>();
+  if (nvec > 1) {   // the resident workspaces hold one vector
+    B1.alloc(sizeof(T) * (size_t)chi_l * w_l * nn * chi_r * nvec);
+    if (!zero_site) B2.alloc(sizeof(T) * (size_t)chi_l * nn * w_r * chi_r * nvec);
+    t1 = B1.as<T>(); t2 = B2.as<T>();
+  }
   if (symmetrize) {
-    localop_pass<T>(*this, L, Wp.as<T>(), Rm.as<T>(), V, Y, 0.5, 0.0);
-    localop_pass<T>(*this, Lt.as<T>(), Wpt.as<T>(), Rmt.as<T>(), V, Y, 0.5, 1.0);
+    localop_pass<T>(*this, L, Wp.as<T>(), Rm.as<T>(), V, Y, 0.5, 0.0, nvec, t1, t2);
+    localop_pass<T>(*this, Lt.as<T>(), Wpt.as<T>(), Rmt.as<T>(), V, Y, 0.5, 1.0, nvec, t1, t2);
   } else {
-    localop_pass<T>(*this, L, Wp.as<T>(), Rm.as<T>(), V, Y, 1.0, 0.0);
+    localop_pass<T>(*this, L, Wp.as<T>(), Rm.as<T>(), V, Y, 1.0, 0.0, nvec, t1, t2);
   }
 }
 

@@ -31,6 +31,7 @@ struct LocalOp {
   // Wfused: (w_l, nn, nn, w_r) in the reference Amid layout [y, b, e, z]; nullptr for zero_site
   void setup(const T* Lenv, int chil, int wl, const T* Renv, int chir, int wr, const T* Wfused, int nn_, bool sym);
   void apply(const T* V, T* Y);
+  void apply_batch(const T* V, T* Y, int nvec);   // nvec window vectors stored back to back
   double flops() const;
 };
 
@@ -54,6 +55,12 @@ struct KrylovInfo { int matvecs = 0; int restarts = 0; double resid = 0.0; bool 
 template <class T> double lanczos_lowest(LocalOp<T>& op, T* x, int krylovdim, int maxiter, double tol, KrylovInfo* info);
 // K x = rhs (GMRES(m); stands in for `\` als.jl:69 / mals.jl:167 and KrylovKit.linsolve dmrg.jl:170)
 template <class T> void gmres_solve(LocalOp<T>& op, const T* rhs, T* x, int krylovdim, int maxiter, double tol, KrylovInfo* info);
+// dense direct solve K x = rhs for small windows (`K_full` + `\\`: als.jl:58-70, mals.jl:148-169, dmrg.jl:49-54,173-174):
+// K assembled by applying the operator to the identity (one batched three-GEMM pass), Householder QR, back substitution
+template <class T> void dense_solve(LocalOp<T>& op, const T* rhs, T* x);
+// dense when the window has at most max(itslv_thresh, 2048) unknowns and it_solver is off, GMRES otherwise
+template <class T>
+void local_linsolve(LocalOp<T>& op, const T* rhs, T* x, int krylovdim, int maxiter, double tol, const ttn_solver_params& p);
 // x <- exp(t K) x  for Hermitian K (KrylovKit.exponentiate stand-in, tdvp.jl:75); t = (tre, tim)
 template <class T>
 void lanczos_expm(LocalOp<T>& op, T* x, double tre, double tim, int krylovdim, int maxiter, double tol, KrylovInfo* info);

@@ -382,7 +382,7 @@ void als_linsolve(const TTO<T>& A, const TT<T>& b, const TT<T>& x0, const ttn_so
     S.setup_op(op, W, k, 1, false);
     S.local_rhs(k, 1, Pb);
     S.window(k, 1, V);
-    gmres_solve<T>(op, Pb.as<T>(), V.as<T>(), kd, maxit, tol, nullptr);
+    local_linsolve<T>(op, Pb.as<T>(), V.as<T>(), kd, maxit, tol, p);
   };
   int nsweeps = 0;
   while (nsweeps < p.sweep_count) {
@@ -500,7 +500,7 @@ void mals_linsolve(const TTO<T>& A, const TT<T>& b, const TT<T>& x0, const ttn_s
     S.setup_op(op, W, k, 2, false);
     S.local_rhs(k, 2, Pb);
     S.window(k, 2, V);
-    gmres_solve<T>(op, Pb.as<T>(), V.as<T>(), kd, maxit, tol, nullptr);
+    local_linsolve<T>(op, Pb.as<T>(), V.as<T>(), kd, maxit, tol, p);
   };
   for (int k = 0; k < d - 1; ++k) {
     DevBuf V;
@@ -576,7 +576,7 @@ struct DmrgLocal {
     if (lin) {
       DevBuf Pb;
       S.local_rhs(k, N, Pb);
-      gmres_solve<T>(op, Pb.as<T>(), V.as<T>(), kd, maxit, p.linsolv_tol, nullptr);
+      local_linsolve<T>(op, Pb.as<T>(), V.as<T>(), kd, maxit, p.linsolv_tol, p);
       return 0.0;
     }
     return lanczos_lowest<T>(op, V.as<T>(), kd, maxit, p.linsolv_tol, nullptr);

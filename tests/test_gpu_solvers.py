@@ -184,3 +184,42 @@ def test_tdvp_real_time_vs_oracle(two_site):
         ref = o.tdvp(H, u0, steps, normalize=True)
     assert relerr(dv(got), dv(ref)) < 1e-9
     assert abs(np.linalg.norm(dv(got)) - 1.0) < 1e-10
+
+
+@pytest.mark.parametrize("bits", [3, 5, 6])
+def test_cfg3_laplace2d_interleaved_mals_linsolve(bits):
+    """cfg3 in miniature: interleaved 2-D Laplace QTT operator (tt_operators.jl:654-656 scaling),
+    right-hand side sin(pi x) sin(pi y), `mals_linsolve` (mals.jl:240-309: exactly one forward + one backward two-site
+    sweep from a random rank-4 start).  Parity is against the oracle running the same algorithm (dense local solves,
+    mals.jl:148-169): one sweep with the squared-weight rule `sv_trunc` (mals.jl:42-56) is itself only accurate to
+    ~1e-5 against the dense solution at 2 x 5 bits, so the dense check is loose and the oracle check is tight."""
+    import ttn_b200 as t
+    d = 2 * bits
+    A = o.laplace2d_interleaved(bits)
+    b = o.qtt_sin2d_interleaved(bits)
+    x0 = o.rand_tt((2,) * d, 4, rng=np.random.default_rng(2), normalise=True)
+    x, info = t.mals_linsolve(A, b, x0, tol=1e-12, rmax=32, return_info=True)
+    xo = o.mals_linsolve(A, b, x0, tol=1e-12, rmax=32)
+    assert x.ttv_rks == xo.ttv_rks
+    assert relerr(dv(x), dv(xo)) < 1e-8
+    Ad = o.tto_to_matrix(A)
+    ref = np.linalg.solve(Ad, dv(b))
+    assert relerr(dv(x), ref) < (1e-12 if bits == 3 else 1e-3)
+    res_dense = np.linalg.norm(Ad @ dv(x) - dv(b)) / np.linalg.norm(dv(b))
+    assert abs(info["residual"] - res_dense) < 1e-6 * max(1.0, res_dense)
+
+
+def test_local_linsolve_dense_vs_gmres_paths():
+    """als_linsolve with the dense direct local solve (default, K_full + `\\` of als.jl:58-70) and with it_solver=True
+    (matrix-free GMRES) must agree with each other and with the dense solution."""
+    import ttn_b200 as t
+    d = 6
+    rng = np.random.default_rng(21)
+    A = spd_op(d, 2.0)
+    b = o.rand_tt((2,) * d, 2, rng=rng)
+    x0 = o.rand_tt((2,) * d, 4, rng=rng)
+    ref = np.linalg.solve(o.tto_to_matrix(A), dv(b))
+    xd = t.als_linsolve(A, b, x0, sweep_count=6)
+    xg = t.als_linsolve(A, b, x0, sweep_count=6, it_solver=True)
+    assert relerr(dv(xd), ref) < 1e-10
+    assert relerr(dv(xg), ref) < 1e-9

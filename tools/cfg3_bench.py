@@ -1,0 +1,144 @@
+"""cfg3 (BASELINE.json configs[2]): 2-D Laplace in interleaved QTT format, 2 x `bits` bits, `mals_linsolve` with rank cap
+`rmax`.  One call = one forward and one backward two-site sweep (mals.jl:240-309), local systems
+solved matrix-free by GMRES on the DMMA three-GEMM matvec.  Prints one JSON line: wall seconds, relative residual
+||Ax-b||/||b|| (TT arithmetic on the device), ranks, launches.
+
+usage: python tools/cfg3_bench.py [--bits 20] [--rmax 128] [--tol 1e-12] [--maxiter 200] [--krylovdim 30]
+The operator / right-hand side builders below restate the reference generators (tt_operators.jl:4-19,282-284,654-656,
+qtt_tools.jl:138-154) for this tool; the oracle package is test infrastructure and is not imported here.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import ttn_b200 as t  # noqa: E402
+
+
+def toeplitz_cores(alpha, beta, gamma, d):
+    I2, J = np.eye(2), np.array([[0.0, 1.0], [0.0, 0.0]])
+    cores = []
+    for k in range(d):
+        rl, rr = (1 if k == 0 else 3), (1 if k == d - 1 else 3)
+        c = np.zeros((2, 2, rl, rr))
+        for i in range(2):
+            for j in range(2):
+                if d == 1:
+                    c[i, j, 0, 0] = alpha * I2[i, j] + beta * J[i, j] + gamma * J[j, i]
+                elif k == 0:
+                    c[i, j, 0, :] = [I2[i, j], J[j, i], J[i, j]]
+                elif k == d - 1:
+                    c[i, j, :, 0] = [alpha * I2[i, j] + beta * J[i, j] + gamma * J[j, i], gamma * J[i, j], beta * J[j, i]]
+                else:
+                    c[i, j] = np.array([[I2[i, j], J[j, i], J[i, j]], [0.0, J[i, j], 0.0], [0.0, 0.0, J[j, i]]])
+        cores.append(c)
+    return cores
+
+
+def interleave(cores, own_first):
+    out = []
+    for c in cores:
+        Rl, Rr = c.shape[2], c.shape[3]
+        R = Rr if own_first else Rl
+        p = np.zeros((2, 2, R, R))
+        for s in range(2):
+            p[s, s] = np.eye(R)
+        out += [c.copy(), p] if own_first else [p, c.copy()]
+    return out
+
+
+def add_ops(xc, yc):
+    d, out = len(xc), []
+    for k, (a, b) in enumerate(zip(xc, yc)):
+        if k == 0:
+            c = np.concatenate([a, b], axis=3)
+        elif k == d - 1:
+            c = np.concatenate([a, b], axis=2)
+        else:
+            c = np.zeros((2, 2, a.shape[2] + b.shape[2], a.shape[3] + b.shape[3]))
+            c[:, :, :a.shape[2], :a.shape[3]] = a
+            c[:, :, a.shape[2]:, a.shape[3]:] = b
+        out.append(c)
+    return out
+
+
+def laplace2d(bits):
+    lap = toeplitz_cores(2.0, -1.0, -1.0, bits)
+    cores = add_ops(interleave(lap, True), interleave(lap, False))
+    h = 1.0 / (2 ** bits - 1)
+    cores[0] = cores[0] / h ** 2
+    d = 2 * bits
+    return t.TToperator(d, [np.asfortranarray(c) for c in cores], (2,) * d, [1] + [c.shape[3] for c in cores])
+
+
+def qtt_sin_cores(d, lam=1.0, a=0.0, b=1.0):
+    """sin(lam*pi*x) on the 2^d points of [a,b] as a rank-2 QTT, site 1 = most significant bit (qtt_tools.jl:138-154)"""
+    h = (b - a) / (2 ** d - 1)
+    w = lam * np.pi
+    cores = [np.zeros((2, 1, 2))] + [np.zeros((2, 2, 2)) for _ in range(d - 2)] + [np.zeros((2, 2, 1))]
+    cores[0][0, 0, :] = [np.sin(w * a), np.cos(w * a)]
+    t1 = w * (a + h * 2 ** (d - 1))
+    cores[0][1, 0, :] = [np.sin(t1), np.cos(t1)]
+    for k in range(2, d):
+        tk = w * h * 2 ** (d - k)
+        cores[k - 1][0] = np.eye(2)
+        cores[k - 1][1] = [[np.cos(tk), -np.sin(tk)], [np.sin(tk), np.cos(tk)]]
+    cores[d - 1][0, 0, 0] = 1.0
+    cores[d - 1][1, :, 0] = [np.cos(w * h), np.sin(w * h)]
+    return cores
+
+
+def sin2d(bits):
+    sx = qtt_sin_cores(bits); sy = qtt_sin_cores(bits)
+    vec = []
+    for k in range(bits):
+        cx, cy = sx[k], sy[k]
+        ryl = cy.shape[1]
+        gx = np.einsum("sab,cd->sacbd", cx, np.eye(ryl)).reshape(2, cx.shape[1] * ryl, cx.shape[2] * ryl, order="F")
+        rxr = cx.shape[2]
+        gy = np.einsum("ab,scd->sacbd", np.eye(rxr), cy).reshape(2, rxr * cy.shape[1], rxr * cy.shape[2], order="F")
+        vec += [gx, gy]
+    d = 2 * bits
+    return t.TTvector(d, [np.asfortranarray(c) for c in vec], (2,) * d, [1] + [c.shape[2] for c in vec])
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--bits", type=int, default=20)
+    ap.add_argument("--rmax", type=int, default=128)
+    ap.add_argument("--tol", type=float, default=1e-12)
+    ap.add_argument("--maxiter", type=int, default=200)
+    ap.add_argument("--krylovdim", type=int, default=30)
+    ap.add_argument("--x0rank", type=int, default=8)
+    args = ap.parse_args()
+    d = 2 * args.bits
+    A, b = laplace2d(args.bits), sin2d(args.bits)
+    rks = [min(2 ** k, 2 ** (d - k), args.x0rank) for k in range(d + 1)]
+    rng = np.random.default_rng(2)
+    x0 = t.TTvector(d, [np.asfortranarray(rng.standard_normal((2, rks[k], rks[k + 1])) / np.sqrt(2 * rks[k + 1])) for k in range(d)],
+                    (2,) * d, rks)
+    Ad, bd, xd = t.DeviceTTO.upload(A), t.DeviceTT.upload(b), t.DeviceTT.upload(x0)
+    t.synchronize()
+    t.reset_launch_count()
+    t.profile(True)
+    t0 = time.perf_counter()
+    x, info = t.mals_linsolve(Ad, bd, xd, tol=args.tol, rmax=args.rmax, return_info=True, linsolv_maxiter=args.maxiter,
+                              krylovdim=args.krylovdim)
+    t.synchronize()
+    el = time.perf_counter() - t0
+    fam = t.profile_read(); t.profile(False)
+    r = t.sub(t.apply(Ad, x), bd)
+    res = t.norm(r) / t.norm(bd)
+    print(json.dumps({"metric": "cfg3 mals_linsolve s", "bits": args.bits, "d": d, "rmax": args.rmax, "tol": args.tol,
+                      "seconds": el, "relative_residual": float(res), "solver_residual": float(info["residual"]),
+                      "max_rank": int(max(x.ttv_rks)), "mpo_rank": int(max(A.tto_rks)), "gpu_launches": int(t.launch_count()),
+                      "family_ms": {k: round(v[0], 1) for k, v in fam.items()}}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
