@@ -340,6 +340,9 @@ def run_ours(args, rank, local_rank, world):
         if rank == 0:
             extras["matvec_cfg4"] = bench_matvec(t, torch, stream, peak64)
             extras["dmrg_sweep"] = bench_dmrg(t, args.dmrg_chi)
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import cfg3_bench
+            extras["mals_cfg3"] = cfg3_bench.run(bits=20, rmax=128)
 
     line = None
     if rank == 0:
@@ -451,7 +454,7 @@ def bench_dmrg(t, chi, L=64, kd=8):
     el = time.perf_counter() - t0
     return {"metric": "DMRG sweep s", "value": el, "unit": "s", "L": L, "chi": chi, "krylovdim": kd, "bond_steps": len(E),
             "max_rank": int(max(rh)), "E_last": float(E[-1]), "gpu_launches": int(t.launch_count()),
-            "note": "BASELINE.json cfg4 is chi=1024; run with --dmrg-chi 1024 for the full-size sweep"}
+            "note": "cfg4 (BASELINE.json configs[3]): Heisenberg XYZ L=64, MPO rank 5, one full two-site sweep from a random TT capped at chi"}
 
 
 def main():
@@ -462,7 +465,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="skip the cfg4 matvec / DMRG sweep / cfg5 batch extras")
-    ap.add_argument("--dmrg-chi", type=int, default=256, help="bond cap of the DMRG sweep extra (cfg4 is 1024)")
+    ap.add_argument("--dmrg-chi", type=int, default=1024, help="bond cap of the DMRG sweep extra (cfg4: 1024)")
     ap.add_argument("--batch-vectors", type=int, default=128, help="cfg5 vectors per rank in the batch extra")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
