@@ -309,8 +309,13 @@ def run_ours(args, rank, local_rank, world):
     alg = {"jacobi": model["jacobi"], "gemm": model["gemm_theta"] + model["gemm_proj"], "qr_panel": model["qr"],
            "qr_apply": model["qr"]}.get(dom, 0.0)
     achieved = alg / (fam_ms[dom] * 1e-3) / 1e12 if fam_ms[dom] > 0 else 0.0
+    # DRAM bytes per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full`
+    # capture, profiles/ncu_cfg2_kernels_r01.txt / ncu_gemm_r01.txt); the bond matrices live in L2, so it is tiny
+    traffic = {"jacobi": 161536, "qr_panel": 1132800, "gemm": None}.get(dom)
     roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak64["fp64_tflops"], "unit": "TFLOP/s",
-                "frac": achieved / peak64["fp64_tflops"], "traffic": None,
+                "frac": achieved / peak64["fp64_tflops"], "traffic": traffic,
+                "traffic_source": "profiles/ncu_cfg2_kernels_r01.txt (per launch; algorithmic bytes of a 128 x 128 Jacobi "
+                                  "launch are 262144: one read + one write of the matrix, both served by L2)",
                 "peak_source": "measured cuBLAS FP64 GEMM 8192^3 burst on this pool's B200 (profiles/fp64_peak_r01.json; "
                                "MEASURED_PEAKS.json carries no FP64 figure)",
                 "algorithmic_flops_per_step": alg, "launches_per_step": fam_cnt[dom], "ms_per_step_in_kernel": fam_ms[dom],
