@@ -189,6 +189,58 @@ def host_threads():
         return os.cpu_count() or 1
 
 
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU legs of the extras (rank 0, N = 1 only): the oracle timed beside the GPU numbers, bounded samples
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_extras(extras, chi=1024, w=5, nn=4):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ttn_oracle as o
+    cores = host_threads()
+    rng = np.random.default_rng(4)
+    out = {}
+    # cfg4 matvec at full size: K_matfree lowered to three BLAS GEMMs (what @tensoropt does in the reference)
+    G = rng.standard_normal((w, chi, chi)); H = rng.standard_normal((w, chi, chi))
+    Am = rng.standard_normal((w, nn, nn, w)); V = rng.standard_normal((chi, nn, chi))
+    o.dmrg_matvec2_blas(G, Am, V, H)
+    t0 = time.perf_counter(); o.dmrg_matvec2_blas(G, Am, V, H); t_mv = time.perf_counter() - t0
+    flops = 4.0 * w * nn * chi ** 3 + 2.0 * w * w * nn * nn * chi ** 2
+    out["matvec_cfg4"] = {"value": flops / t_mv / 1e12, "unit": "TFLOP/s", "seconds": t_mv, "cores": cores, "kind": "port",
+                          "sample": "one full-size application (chi=1024) through three BLAS GEMMs; NumPy restatement, not Julia"}
+    # cfg4 DMRG sweep: one bulk bond step at full size = 8 Lanczos matvecs (the reference applies K twice per matvec,
+    # dmrg.jl:241) + gesdd of the 2048 x 2048 two-site tensor + one environment update; sweep = 125 bond steps, of which
+    # ~105 are at the full bond dimension for L = 64
+    chi_svd = 2 * chi
+    Th = rng.standard_normal((chi_svd, chi_svd))
+    import scipy.linalg as sla
+    t0 = time.perf_counter(); sla.svd(Th, full_matrices=False, lapack_driver="gesdd"); t_svd = time.perf_counter() - t0
+    bond = 8 * 2 * t_mv + t_svd          # the environment update (43 GF, half a matvec) is left out: lower bound
+    out["dmrg_sweep"] = {"value": 105 * bond, "unit": "s", "cores": cores, "kind": "port",
+                         "bulk_bond_step_s": bond, "matvec_s": t_mv, "gesdd_s": t_svd, "gesdd_n": chi_svd,
+                         "sample": "one bulk bond step measured at full size (8 Lanczos matvecs x 2 applications + gesdd 2048^2; "
+                                   "environment update not counted), times the ~105 full-rank bond steps of the L=64 sweep; "
+                                   "NumPy restatement, not Julia"}
+    # cfg5: one vector through A*x + tt_compress!(y, 64) (algorithm-equivalent: the discarded orthogonalize is not run)
+    d, r, W = 30, 64, 4
+    rks = [min(2 ** k, 2 ** (d - k), r) for k in range(d + 1)]
+    Rk = [min(4 ** k, 4 ** (d - k), W) for k in range(d + 1)]
+    g = np.random.default_rng(7)
+    Aop = o.TToperator(d, [np.asfortranarray((g.standard_normal((2, 2, Rk[k], Rk[k + 1])) + 1j * g.standard_normal((2, 2, Rk[k], Rk[k + 1])))
+                                             / math.sqrt(2.0 * Rk[k + 1])) for k in range(d)], (2,) * d, Rk)
+    xv = o.TTvector(d, [np.asfortranarray((g.standard_normal((2, rks[k], rks[k + 1])) + 1j * g.standard_normal((2, rks[k], rks[k + 1])))
+                                          / math.sqrt(4.0 * rks[k + 1])) for k in range(d)], (2,) * d, rks, [0] * d)
+    t0 = time.perf_counter()
+    y = o.apply(Aop, xv)
+    for k in list(range(1, d)) + list(range(d - 1, 0, -1)):
+        o.tt_bond_truncate(y, k, max_bond=r, truncerr=0.0, faithful=False)
+    t_vec = time.perf_counter() - t0
+    out["batch_cfg5"] = {"value": 1.0 / t_vec, "unit": "vectors/s", "seconds_per_vector": t_vec, "cores": cores, "kind": "port",
+                         "sample": "one of the 4096 vectors (multithreaded BLAS/LAPACK inside the vector); NumPy restatement, not Julia"}
+    for k, v in out.items():
+        if k in extras:
+            extras[k]["cpu_baseline"] = v
+
+
 # ---------------------------------------------------------------------------------------------------------------
 def run_reference(args, rank):
     if rank != 0:
@@ -348,6 +400,8 @@ def run_ours(args, rank, local_rank, world):
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             import cfg3_bench
             extras["mals_cfg3"] = cfg3_bench.run(bits=20, rmax=128)
+            if world == 1 and not args.no_cpu:
+                cpu_extras(extras)
 
     line = None
     if rank == 0:

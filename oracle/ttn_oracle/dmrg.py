@@ -65,6 +65,16 @@ def dmrg_matvec2(G, Am, V, H, symmetrize=True):
     return Y
 
 
+def dmrg_matvec2_blas(G, Am, V, H):
+    """The single application G·Amid·V·H of dmrg.jl:239-244 lowered to three BLAS GEMMs (tensordot = permute + gemm), which
+    is what TensorOperations' `@tensoropt` does for the reference on the CPU.  Same result as dmrg_matvec2(symmetrize=False);
+    used as the timed CPU baseline of the matvec (bench.py), where the plain-einsum version would understate the CPU."""
+    t1 = np.tensordot(G, V, axes=([2], [0]))              # [y, a, e, f]
+    t2 = np.tensordot(Am, t1, axes=([0, 2], [0, 2]))      # [b, z, a, f]
+    Y = np.tensordot(t2, H, axes=([1, 3], [0, 2]))        # [b, a, c]
+    return np.transpose(Y, (1, 0, 2))
+
+
 def K_full(G, H, Am):
     """dmrg.jl:49-54 (without the Hermitian wrapper)."""
     dims = (G.shape[1], Am.shape[1], H.shape[1])

@@ -225,3 +225,11 @@ def test_tdvp_real_time_norm_and_exact_small():
     ref = sla.expm(-1j * 0.2 * o.tto_to_matrix(H)) @ dv(u0)
     assert np.linalg.norm(dv(psi2) - ref) / np.linalg.norm(ref) < 1e-3   # Trotter error O(dt²) of the 2-site splitting
     assert abs(np.linalg.norm(dv(psi2)) - np.linalg.norm(dv(u0))) < 1e-10
+
+
+def test_matvec_blas_restatement_equals_einsum():
+    # the GEMM-lowered K_matfree (CPU baseline of bench.py) against the index-by-index contraction of dmrg.jl:239-244
+    rng = np.random.default_rng(3)
+    G = rng.standard_normal((3, 6, 6)); H = rng.standard_normal((4, 5, 5))
+    Am = rng.standard_normal((3, 4, 4, 4)); V = rng.standard_normal((6, 4, 5))
+    assert np.allclose(o.dmrg_matvec2_blas(G, Am, V, H), o.dmrg_matvec2(G, Am, V, H, symmetrize=False), rtol=1e-13, atol=1e-13)
