@@ -223,3 +223,20 @@ def test_local_linsolve_dense_vs_gmres_paths():
     xg = t.als_linsolve(A, b, x0, sweep_count=6, it_solver=True)
     assert relerr(dv(xd), ref) < 1e-10
     assert relerr(dv(xg), ref) < 1e-9
+
+
+def test_als_linsolve_complex_dense_local_solve():
+    """ComplexF64 through the dense local solve (K assembled by the batched three-GEMM pass, complex Householder QR, complex
+    back substitution): Hermitian positive definite operator with a complex right-hand side against the dense solution."""
+    import ttn_b200 as t
+    d = 5
+    rng = np.random.default_rng(31)
+    Ar = spd_op(d, 2.5)
+    A = o.TToperator(Ar.N, [c.astype(np.complex128) for c in Ar.tto_vec], Ar.tto_dims, Ar.tto_rks)
+    b = o.rand_tt((2,) * d, 2, rng=rng)
+    b = o.TTvector(b.N, [c + 1j * rng.standard_normal(c.shape) for c in b.ttv_vec], b.ttv_dims, b.ttv_rks, b.ttv_ot)
+    x0 = o.rand_tt((2,) * d, 4, rng=rng)
+    x0 = o.TTvector(x0.N, [c.astype(np.complex128) for c in x0.ttv_vec], x0.ttv_dims, x0.ttv_rks, x0.ttv_ot)
+    x = t.als_linsolve(A, b, x0, sweep_count=6)
+    ref = np.linalg.solve(o.tto_to_matrix(A), dv(b))
+    assert relerr(dv(x), ref) < 1e-10
