@@ -1,0 +1,67 @@
+"""Oracle restatement of the time steppers (src/solvers/euler.jl) against dense linear algebra — ports of
+test/test_euler.jl:5-135 (one step of each scheme on the 1-D QTT Laplacian, tolerances as in the reference)."""
+import numpy as np
+
+import ttn_oracle as o
+
+
+def _setup(d=4, seed=0):
+    h = 1.0 / d ** 2
+    A = o.tto_scale(-h ** 2, o.toeplitz_to_qtto(-2.0, 1.0, 1.0, d))
+    u0 = o.rand_tt((2,) * d, [1] + [2] * (d - 1) + [1], rng=np.random.default_rng(seed))
+    Ad = o.tto_to_matrix(A)
+    return A, u0, Ad, o.ttv_to_tensor(u0).reshape(-1)
+
+
+def _vec(x):
+    return o.ttv_to_tensor(x).reshape(-1)
+
+
+def _rel(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+def test_euler_single_step_vs_dense():
+    # test_euler.jl:5-32
+    A, u0, Ad, ud = _setup()
+    sol = o.euler_method(A, u0, [0.05], normalize=False)
+    assert _rel(_vec(sol), ud + 0.05 * (Ad @ ud)) < 1e-6
+
+
+def test_implicit_euler_dmrg_vs_dense():
+    # test_euler.jl:34-59
+    A, u0, Ad, ud = _setup()
+    sol = o.implicit_euler_method(A, u0, u0, [0.05], normalize=False, tt_solver="dmrg")
+    ref = np.linalg.solve(np.eye(Ad.shape[0]) - 0.05 * Ad, ud)
+    assert _rel(_vec(sol), ref) < 1e-5
+
+
+def test_crank_nicholson_mals_vs_dense():
+    # test_euler.jl:88-111
+    A, u0, Ad, ud = _setup()
+    sol = o.crank_nicholson_method(A, u0, u0, [0.05], normalize=False, tt_solver="mals")
+    I = np.eye(Ad.shape[0])
+    ref = np.linalg.solve(I - 0.025 * Ad, (I + 0.025 * Ad) @ ud)
+    assert _rel(_vec(sol), ref) < 1e-5
+
+
+def test_rk4_step_vs_dense_and_error_flag():
+    A, u0, Ad, ud = _setup()
+    h = 0.05
+    sol, err = o.rk4_method(A, u0, [h], 16, normalize=False, return_error=True)
+    k1 = Ad @ ud; k2 = Ad @ (ud + h / 2 * k1); k3 = Ad @ (ud + h / 2 * k2); k4 = Ad @ (ud + h * k3)
+    ref = ud + h / 6 * (k1 + 2 * k2 + 2 * k3 + k4)
+    assert _rel(_vec(sol), ref) < 1e-10
+    assert err < 1e-10
+
+
+def test_euler_normalize_and_return_error():
+    A, u0, Ad, ud = _setup(seed=3)
+    sol, err = o.euler_method(A, u0, [0.01, 0.01], normalize=True, return_error=True)
+    v = ud
+    for h in (0.01, 0.01):
+        v = v + h * (Ad @ v)
+        v = v / np.linalg.norm(v)
+    assert _rel(_vec(sol), v) < 1e-10
+    assert abs(np.linalg.norm(_vec(sol)) - 1.0) < 1e-12
+    assert err < 1.0
