@@ -12,29 +12,81 @@
 namespace ttn {
 namespace {
 
+__device__ __forceinline__ double shfl_elem(double v, unsigned src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ zc shfl_elem(zc v, unsigned src) {
+  return make_cuDoubleComplex(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+}
+
+// QTT fast path (n_out = n_in = 2, power-of-two bonds): one thread per (a, nu, b) produces the two outputs i = 0, 1 (32
+// contiguous bytes for ComplexF64), consecutive threads continue at the next address.  Index split by shifts and masks,
+// everything unrolled, 32-bit offsets inside one (mu, batch) slab.  grid: x = chunks of (a, nu, b), y = mu chunks, z = batch.
 template <class T>
-__global__ void apply_kernel(const T* __restrict__ A, const T* __restrict__ x, T* __restrict__ y, int n_out, int n_in,
-                             int Rl, int Rr, int rl, int rr, int64_t bx, int64_t by) {
+__global__ void __launch_bounds__(256) apply_qtt_kernel(const T* __restrict__ A, const T* __restrict__ x, T* __restrict__ y,
+                                                        int Rl, int Rr, int rl, int rr, int sh_a, int sh_nu, int64_t bx,
+                                                        int64_t by) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* As = reinterpret_cast<T*>(smem_raw);          // [ (a,b) ][ j ][ i ]  re-packed so that one thread reads 4 consecutive values
+  const int nab = Rl * Rr;
+  for (int t = threadIdx.x; t < 4 * nab; t += blockDim.x) {
+    const int ab = t >> 2, j = (t >> 1) & 1, i = t & 1;
+    As[t] = A[i + 2 * j + 4 * ab];                   // A[i, j, a, b], i fastest
+  }
+  __syncthreads();
+  const unsigned inner = (unsigned)Rl * rl * Rr;
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned mu = blockIdx.y; mu < (unsigned)rr; mu += gridDim.y) {
+    const T* xb = x + blockIdx.z * bx + (int64_t)2 * rl * mu;
+    T* yb = y + blockIdx.z * by + (int64_t)2 * inner * mu;
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < inner; idx += stride) {
+      const unsigned a = idx & (Rl - 1), nu = (idx >> sh_a) & (rl - 1), b = idx >> (sh_a + sh_nu);
+      const T x0 = xb[2 * nu], x1 = xb[2 * nu + 1];
+      const T* ap = As + 4 * (a + Rl * b);
+      const T a00 = ap[0], a10 = ap[1], a01 = ap[2], a11 = ap[3];     // a_ij
+      T y0 = t_mul(a00, x0), y1 = t_mul(a10, x0);
+      t_fma(y0, a01, x1);
+      t_fma(y1, a11, x1);
+      // lane L of a full warp holds outputs 2L, 2L+1 of a 64-element run; re-distribute by shuffles so that each of the two
+      // store instructions writes one contiguous 32-element half of the run (full sectors) instead of every other 16 bytes
+      const unsigned lane = threadIdx.x & 31;
+      const unsigned wbase = idx - lane;                         // warp-uniform
+      if (wbase + 31 < inner) {
+        const unsigned src0 = lane >> 1, src1 = 16 + (lane >> 1);
+        const T lo0 = shfl_elem(y0, src0), hi0 = shfl_elem(y1, src0);
+        const T lo1 = shfl_elem(y0, src1), hi1 = shfl_elem(y1, src1);
+        yb[2 * wbase + lane] = (lane & 1) ? hi0 : lo0;
+        yb[2 * wbase + 32 + lane] = (lane & 1) ? hi1 : lo1;
+      } else {
+        yb[2 * idx] = y0;
+        yb[2 * idx + 1] = y1;
+      }
+    }
+  }
+}
+
+// generic path: one thread per (a, nu, b) produces the n_out outputs; divisions for the index split
+template <class T>
+__global__ void __launch_bounds__(256) apply_kernel(const T* __restrict__ A, const T* __restrict__ x, T* __restrict__ y,
+                                                    int n_out, int n_in, int Rl, int Rr, int rl, int rr, int64_t bx, int64_t by) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* As = reinterpret_cast<T*>(smem_raw);
   const int na = n_out * n_in * Rl * Rr;
   for (int i = threadIdx.x; i < na; i += blockDim.x) As[i] = A[i];
   __syncthreads();
-  const T* xb = x + blockIdx.y * bx;
-  T* yb = y + blockIdx.y * by;
-  const int64_t total = (int64_t)n_out * Rl * rl * Rr * rr;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    int64_t r = idx;
-    const int i = (int)(r % n_out); r /= n_out;
-    const int a = (int)(r % Rl); r /= Rl;
-    const int nu = (int)(r % rl); r /= rl;
-    const int b = (int)(r % Rr); r /= Rr;
-    const int mu = (int)r;
-    const T* xp = xb + (int64_t)n_in * (nu + (int64_t)rl * mu);
-    const T* ap = As + i + (int64_t)n_out * n_in * (a + Rl * b);
-    T acc = t_zero<T>();
-    for (int j = 0; j < n_in; ++j) t_fma(acc, ap[(int64_t)n_out * j], xp[j]);
-    yb[idx] = acc;
+  const unsigned inner = (unsigned)Rl * rl * Rr;
+  for (unsigned mu = blockIdx.y; mu < (unsigned)rr; mu += gridDim.y) {
+    const T* xb = x + blockIdx.z * bx + (int64_t)n_in * rl * mu;
+    T* yb = y + blockIdx.z * by + (int64_t)inner * n_out * mu;
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < inner; idx += gridDim.x * blockDim.x) {
+      const unsigned t1 = idx / Rl, a = idx - t1 * Rl, b = t1 / rl, nu = t1 - b * rl;
+      const T* xp = xb + (size_t)n_in * nu;
+      const T* ap = As + (size_t)n_out * n_in * (a + Rl * b);
+      T* yp = yb + (size_t)idx * n_out;
+      for (int i = 0; i < n_out; ++i) {
+        T acc = t_zero<T>();
+        for (int j = 0; j < n_in; ++j) t_fma(acc, ap[i + n_out * j], xp[j]);
+        yp[i] = acc;
+      }
+    }
   }
 }
 
@@ -43,19 +95,30 @@ __global__ void apply_kernel(const T* __restrict__ A, const T* __restrict__ x, T
 template <class T>
 void apply_core(const T* A, const T* x, T* y, int n_out, int n_in, int Rl, int Rr, int rl, int rr, int batch, int64_t bx,
                 int64_t by) {
-  const int64_t total = (int64_t)n_out * Rl * rl * Rr * rr;
-  if (total <= 0 || batch <= 0) return;
+  const int64_t inner = (int64_t)Rl * rl * Rr;
+  if (inner <= 0 || n_out <= 0 || rr <= 0 || batch <= 0) return;
+  ttn_assert(inner * n_out < (1LL << 31), 2, "apply: core too large for 32-bit sub-index arithmetic");
   ProfScope prof_scope_(KF_APPLY);
   const size_t smem = sizeof(T) * (size_t)n_out * n_in * Rl * Rr;
   ttn_assert(smem <= 48 * 1024, 2, "apply: MPO core does not fit in shared memory");
-  int64_t blocks = (total + 255) / 256;
-  const int64_t cap = std::max<int64_t>(1, (int64_t)ctx().sm_count * 8 / std::max(1, std::min(batch, 8)));
-  if (blocks > cap) blocks = cap;
+  const bool qtt = n_out == 2 && n_in == 2 && (Rl & (Rl - 1)) == 0 && (rl & (rl - 1)) == 0;
+  int sh_a = 0, sh_nu = 0;
+  while ((1 << sh_a) < Rl) ++sh_a;
+  while ((1 << sh_nu) < rl) ++sh_nu;
+  const unsigned bxg = (unsigned)std::min<int64_t>((inner + 255) / 256, 64);
+  ttn_assert(rr <= 65535, 2, "apply: right bond too large for grid.y");
   for (int b0 = 0; b0 < batch; b0 += 65535) {
     const int nb = std::min(65535, batch - b0);
-    dim3 grid((unsigned)blocks, (unsigned)nb);
-    apply_kernel<T><<<grid, 256, smem, ctx().stream>>>(A, x + (int64_t)b0 * bx, y + (int64_t)b0 * by, n_out, n_in, Rl, Rr, rl,
-                                                       rr, bx, by);
+    // enough CTAs for ~16 per SM, each looping over several mu so that the MPO-core staging is amortised
+    const int64_t want = (int64_t)ctx().sm_count * 16;
+    const unsigned gy = (unsigned)std::max<int64_t>(1, std::min<int64_t>(rr, want / std::max<int64_t>(1, (int64_t)bxg * nb)));
+    dim3 grid(bxg, gy, (unsigned)nb);
+    if (qtt)
+      apply_qtt_kernel<T><<<grid, 256, smem, ctx().stream>>>(A, x + (int64_t)b0 * bx, y + (int64_t)b0 * by, Rl, Rr, rl, rr, sh_a,
+                                                             sh_nu, bx, by);
+    else
+      apply_kernel<T><<<grid, 256, smem, ctx().stream>>>(A, x + (int64_t)b0 * bx, y + (int64_t)b0 * by, n_out, n_in, Rl, Rr, rl,
+                                                         rr, bx, by);
     TTN_CHECK_LAUNCH();
     ctx().launches++;
   }
