@@ -38,7 +38,7 @@ int ttn_init(int device) {
   TTN_CUDA(cudaSetDevice(device));
   Context& c = ctx();
   if (!c.inited || c.device != device) {
-    if (c.inited && c.stream) cudaStreamDestroy(c.stream);
+    if (c.inited && c.stream) { devbuf_cache_trim(); cudaStreamSynchronize(c.stream); cudaStreamDestroy(c.stream); }
     c.device = device;
     TTN_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     cudaDeviceProp prop;
@@ -60,6 +60,7 @@ int ttn_shutdown(void) {
   API_BEGIN
   Context& c = ctx();
   if (c.inited) {
+    devbuf_cache_trim();
     cudaStreamSynchronize(c.stream);
     cudaStreamDestroy(c.stream);
     c.stream = nullptr;

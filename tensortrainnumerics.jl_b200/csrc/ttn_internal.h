@@ -79,7 +79,8 @@ struct ProfScope {
   }
 };
 
-// stream-ordered device buffer (cudaMallocAsync pool on the context stream)
+void devbuf_cache_trim();   // returns the exact-size block cache of DevBuf to the stream-ordered pool
+// stream-ordered device buffer (cudaMallocAsync pool on the context stream, exact-size cache for blocks >= 256 KB)
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;

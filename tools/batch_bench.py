@@ -66,16 +66,20 @@ def main():
 
     host = make_chunk(rank)
     xd, xs = upload(host)
-    # warm-up
-    y = t.tt_compress_(t.apply(Ad, xd), r)
-    t.synchronize()
+    # warm-up (twice, results dropped: the timed loop must not grow the stream-ordered memory pool)
+    for _ in range(2):
+        y = t.tt_compress_(t.apply(Ad, xd), r)
+        t.synchronize()
+        del y
     if dist is not None:
         dist.barrier()
     t.reset_launch_count()
     if args.profile:
         t.profile(True)
     t0 = time.perf_counter()
+    y = None
     for c in range(nchunks):
+        del y
         y = t.tt_compress_(t.apply(Ad, xd), r)
     t.synchronize()
     el = time.perf_counter() - t0
