@@ -234,3 +234,45 @@ def test_cfg2_shape_property_checks():
         assert len(a) == len(b) and np.abs(a - b).max() / b[0] < 1e-8
     err_ref = o.rel_distance(ref, x)
     assert abs(err - err_ref) < 1e-10
+
+
+@pytest.mark.gpu
+def test_cuda_matches_golden():
+    """The CUDA path against the committed vectors of tests/golden/hotpath_golden.npz (provenance in
+    tests/golden/make_golden.py): cfg1 solution, tt_compress! result + per-bond singular values, orthogonalize, A*x,
+    K_matfree, the Heisenberg ground-state energy (examples/heisenberg_xyz_dmrg.jl:9-19) and a prescribed-spectrum SVD."""
+    import os
+    import ttn_b200 as t
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hotpath_golden.npz"))
+
+    def tt_from(prefix, d):
+        rks = [int(v) for v in g[prefix + "_rks"]]
+        return o.TTvector(d, [np.asfortranarray(g[f"{prefix}_core{k}"]) for k in range(d)], (2,) * d, rks, [0] * d)
+
+    def dense(x):
+        return o.ttv_to_tensor(x).reshape(-1)
+
+    def rel(a, b):
+        return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+    x = t.als_linsolve(o.id_tto(6), o.qtt_sin(6, lam=np.pi), tt_from("cfg1_x0", 6), sweep_count=4)
+    assert rel(dense(x), g["cfg1_x"]) < 1e-10 and rel(dense(x), g["cfg1_b"]) < 1e-12
+    y = tt_from("cmp_in", 8)
+    z, sig = t.tt_compress_(o.copy_tt(y), 5, return_sigma=True)
+    assert list(z.ttv_rks) == [int(v) for v in g["cmp_out_rks"]]
+    assert rel(dense(z), g["cmp_out"]) < 1e-10
+    gs = g["cmp_sigma"]
+    for k in range(gs.shape[0]):
+        n = min(len(sig[k]), gs.shape[1])
+        assert np.abs(np.asarray(sig[k])[:n] - gs[k][:n]).max() < 1e-10 * gs[k][0]
+    assert rel(dense(t.orthogonalize(y, 4)), g["orth_dense"]) < 1e-12
+    assert rel(dense(t.apply(o.laplace_dd(8), y)), g["apply_dense"]) < 1e-12
+    assert rel(t.matvec2(g["mv_G"], g["mv_Am"], g["mv_H"], g["mv_V"]), g["mv_Y"]) < 1e-13
+    d = int(g["heis_d"])
+    H = o.heisenberg_xyz_tto(d, jx=1.1, jy=0.8, jz=1.2, lam=0.0)
+    x0 = o.rand_tt((2,) * d, 8, rng=np.random.default_rng(3), normalise=True)
+    E, _, _ = t.dmrg_eigsolve(H, x0, N=2, tol=1e-12, sweep_schedule=[2, 4, 6], rmax_schedule=[8, 16, 32], linsolv_tol=1e-12,
+                              linsolv_maxiter=20, krylovdim=20)
+    assert abs(E[-1] - float(g["heis_e0"])) < 1e-9 * abs(float(g["heis_e0"]))
+    U, s, Vt = t.svdtrunc(np.asfortranarray(g["svd_A"]))
+    assert np.abs(s[:10] - g["svd_s"]).max() < 1e-12 and np.abs(s[10:]).max() < 1e-12

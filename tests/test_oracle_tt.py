@@ -275,3 +275,34 @@ def test_laplace2d_interleaved_dense():
         for iy in range(n):
             f[inter(ix, iy)] = np.sin(np.pi * xs[ix]) * np.sin(np.pi * xs[iy])
     assert np.allclose(o.qtt_to_vector(b), f)
+
+
+def _golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hotpath_golden.npz"))
+
+
+def _tt_from(g, prefix, d):
+    rks = [int(v) for v in g[prefix + "_rks"]]
+    return o.TTvector(d, [g[f"{prefix}_core{k}"] for k in range(d)], (2,) * d, rks, [0] * d)
+
+
+def test_oracle_reproduces_golden():
+    """tests/golden/hotpath_golden.npz (generated by tests/golden/make_golden.py from the oracle and tied to dense ground
+    truth there): the oracle must keep reproducing it bit-for-bit-ish (1e-13), so that the GPU parity tests and the
+    committed vectors stay anchored to the same mathematics."""
+    g = _golden()
+    x0 = _tt_from(g, "cfg1_x0", 6)
+    x = o.als_linsolve(o.id_tto(6), o.qtt_sin(6, lam=np.pi), x0, sweep_count=4)
+    assert np.linalg.norm(o.ttv_to_tensor(x).reshape(-1) - g["cfg1_x"]) < 1e-13 * np.linalg.norm(g["cfg1_x"])
+    y = _tt_from(g, "cmp_in", 8)
+    sig = []
+    z = o.tt_compress(o.copy_tt(y), 5, sigma_out=sig)
+    assert list(z.ttv_rks) == [int(v) for v in g["cmp_out_rks"]]
+    assert np.linalg.norm(o.ttv_to_tensor(z).reshape(-1) - g["cmp_out"]) < 1e-12 * np.linalg.norm(g["cmp_out"])
+    for k, s in enumerate(sig):
+        assert np.allclose(s, g["cmp_sigma"][k][:len(s)], rtol=1e-12, atol=1e-14)
+    assert np.allclose(o.dmrg_matvec2(g["mv_G"], g["mv_Am"], g["mv_V"], g["mv_H"], symmetrize=False), g["mv_Y"], rtol=1e-13, atol=1e-13)
+    U, S, Vt = o.svdtrunc(g["svd_A"])
+    sv = np.diag(np.asarray(S)) if np.ndim(S) == 2 else np.asarray(S)
+    assert np.abs(sv[:10] - g["svd_s"]).max() < 1e-14 and np.abs(sv[10:]).max() < 1e-14
