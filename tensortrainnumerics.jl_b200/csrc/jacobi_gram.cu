@@ -5,7 +5,7 @@
 // The n columns are cut into blocks of 32; a sweep is a round-robin tournament of the blocks (circle method), and one
 // step treats n/64 disjoint block pairs concurrently with three kernels:
 //   1. gram_pairs_kernel  : G_k = P_k^H P_k for every 64-column panel P_k = [X_i X_j]   — DMMA, split over the rows;
-//   2. gram_eig_kernel    : one cyclic two-sided Jacobi sweep on the 64 x 64 Hermitian G_k in shared memory, rotations
+//   2. gram_eig_kernel    : one two-sided Jacobi pass over the cross pairs of the 64 x 64 Hermitian G_k in shared memory, rotations
 //                           accumulated in V_k (the plane rotations are the ones the scalar method would apply to the
 //                           columns, but each costs 64-vectors instead of m-vectors);
 //   3. update_pairs_kernel: P_k <- P_k V_k in place                                      — DMMA.
@@ -25,10 +25,12 @@ constexpr int PW = 2 * GB;    // panel width (columns of a block pair)
 constexpr int GT = 256;       // threads per CTA
 constexpr int GK = 32;        // rows per staged slab in the Gram kernel
 constexpr int UM = 128;       // rows per CTA tile in the update kernel
+constexpr int GE = 1024;      // threads of the inner eigen-sweep kernel (one 2 x 2 block of G per thread)
 
 // column j of panel (blkA, blkB): pointer to its first row, or nullptr beyond the matrix
 template <class T>
 __device__ __forceinline__ T* panel_col(T* X, int64_t ldx, int n, int blkA, int blkB, int j) {
+  if (j >= GB && blkB < 0) return nullptr;           // single-block panel (intra-block step)
   const int c = (j < GB ? blkA * GB + j : blkB * GB + (j - GB));
   return c < n ? X + (int64_t)c * ldx : nullptr;
 }
@@ -107,8 +109,11 @@ __global__ void __launch_bounds__(GT) gram_pairs_kernel(const T* __restrict__ X,
 // ---------------------------------------------------------------------------------------------------------------------
 // 2. Two-sided Jacobi on the 64 x 64 Gram matrix of every panel; V accumulates the rotations.  grid (npairs).
 // ---------------------------------------------------------------------------------------------------------------------
-template <class T>
-__global__ void __launch_bounds__(GT) gram_eig_kernel(const T* __restrict__ Gp, int nsplit, int inner_sweeps, double tol,
+// cross_only: the panel is [A | B] and only the 32 x 32 pairs (p in A, q in B) are rotated, 32 steps of 32 disjoint pairs
+// (p, 32 + (p + s) mod 32) — every column pair of the matrix is then rotated exactly once per sweep; otherwise a full
+// round-robin over the 64 panel columns (used for the intra-block step, where B is empty).
+template <class T, int ET>
+__global__ void __launch_bounds__(ET) gram_eig_kernel(const T* __restrict__ Gp, int nsplit, int cross_only, double tol,
                                                       const double* __restrict__ d_frob2, double floor_k, T* __restrict__ Vg, int* __restrict__ skip,
                                                       unsigned int* __restrict__ d_rotated) {
   constexpr int P = PW + 1;
@@ -123,9 +128,15 @@ __global__ void __launch_bounds__(GT) gram_eig_kernel(const T* __restrict__ Gp, 
   const double tol2 = tol * tol;
   const double floor2 = floor_k * d_frob2[0];   // optional noise floor (jacobi.cu JAC_FLOOR2), 0 = off
   const T* gp = Gp + (size_t)blockIdx.x * nsplit * PW * PW;
-  for (int idx = tid; idx < PW * PW; idx += GT) {
+  for (int idx = tid; idx < PW * PW; idx += ET) {
     T a = t_zero<T>();
-    for (int z = 0; z < nsplit; ++z) a = t_add(a, gp[(size_t)z * PW * PW + idx]);
+    T v[4];
+    for (int z0 = 0; z0 < nsplit; z0 += 4) {           // four partial loads in flight
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = (z0 + u < nsplit) ? gp[(size_t)(z0 + u) * PW * PW + idx] : t_zero<T>();
+#pragma unroll
+      for (int u = 0; u < 4; ++u) a = t_add(a, v[u]);
+    }
     const int i = idx % PW, j = idx / PW;
     G[i * P + j] = a;
     V[i * P + j] = i == j ? t_one<T>() : t_zero<T>();
@@ -134,11 +145,13 @@ __global__ void __launch_bounds__(GT) gram_eig_kernel(const T* __restrict__ Gp, 
   __syncthreads();
 
   int gs = 0;   // global step counter: its parity selects the rotation flag slot
-  for (int sw = 0; sw < inner_sweeps; ++sw) {
-    for (int r = 0; r < PW - 1; ++r, ++gs) {
+  {
+    const int nsteps = cross_only ? GB : PW - 1;
+    for (int r = 0; r < nsteps; ++r, ++gs) {
       if (tid < GB) {
         int p, q;
-        if (tid == 0) { p = PW - 1; q = r; }
+        if (cross_only) { p = tid; q = GB + ((tid + r) & (GB - 1)); }
+        else if (tid == 0) { p = PW - 1; q = r; }
         else { p = r + tid; if (p >= PW - 1) p -= PW - 1; q = r - tid; if (q < 0) q += PW - 1; }
         if (p > q) { const int t_ = p; p = q; q = t_; }
         const double a = t_real(G[p * P + p]), b = t_real(G[q * P + q]);
@@ -166,8 +179,8 @@ __global__ void __launch_bounds__(GT) gram_eig_kernel(const T* __restrict__ Gp, 
       if (stepped) {
         // G <- J^H G J on the 32 x 32 grid of 2 x 2 blocks (rows of pair k, columns of pair l); J = [[cs, s], [-conj(s), cs]]
 #pragma unroll
-        for (int it = 0; it < (GB * GB) / GT; ++it) {
-          const int bidx = tid + it * GT;
+        for (int it = 0; it < (GB * GB) / ET; ++it) {
+          const int bidx = tid + it * ET;
           const int k = bidx / GB, l = bidx % GB;
           const int pk = s_p[k], qk = s_q[k], pl = s_p[l], ql = s_q[l];
           const double ck = s_cs[k], cl = s_cs[l];
@@ -184,8 +197,8 @@ __global__ void __launch_bounds__(GT) gram_eig_kernel(const T* __restrict__ Gp, 
         }
         // V <- V J
 #pragma unroll
-        for (int it = 0; it < (PW * GB) / GT; ++it) {
-          const int vidx = tid + it * GT;
+        for (int it = 0; it < (PW * GB) / ET; ++it) {
+          const int vidx = tid + it * ET;
           const int i = vidx % PW, l = vidx / PW;
           const int pl = s_p[l], ql = s_q[l];
           const double cl = s_cs[l];
@@ -201,7 +214,7 @@ __global__ void __launch_bounds__(GT) gram_eig_kernel(const T* __restrict__ Gp, 
   const int any = s_any;
   T* vout = Vg + (size_t)blockIdx.x * PW * PW;
   if (any)
-    for (int idx = tid; idx < PW * PW; idx += GT) vout[idx] = V[(idx % PW) * P + idx / PW];   // column-major V[k + 64 n]
+    for (int idx = tid; idx < PW * PW; idx += ET) vout[idx] = V[(idx % PW) * P + idx / PW];   // column-major V[k + 64 n]
   if (tid == 0) {
     skip[blockIdx.x] = any ? 0 : 1;
     if (any) atomicOr(d_rotated, 1u);
@@ -293,7 +306,10 @@ int jacobi_gram(T* X, int m, int n, int64_t ldx, double tol, const double* frob2
     }
     off[r + 1] = (int)hA.size();
   }
-  const int maxpairs = ne / 2;
+  // intra-block step: every block alone (B = -1), full round-robin inside the kernel
+  const int off_diag = (int)hA.size();
+  for (int i = 0; i < nblk; ++i) { hA.push_back(i); hB.push_back(-1); }
+  const int maxpairs = std::max(ne / 2, nblk);
   int nsplit = std::max(1, std::min((2 * ctx().sm_count + maxpairs - 1) / maxpairs, m / (2 * GK)));
   nsplit = std::min(nsplit, 16);
   int mc = (m + nsplit - 1) / nsplit;
@@ -310,38 +326,38 @@ int jacobi_gram(T* X, int m, int n, int64_t ldx, double tol, const double* frob2
   const size_t smem_e = sizeof(T) * 2 * PW * (PW + 1);
   static bool attr_done = false;
   if (!attr_done) {
-    TTN_CUDA(cudaFuncSetAttribute(gram_eig_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
+    TTN_CUDA(cudaFuncSetAttribute(gram_eig_kernel<T, GE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
     TTN_CUDA(cudaFuncSetAttribute(gram_pairs_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
     TTN_CUDA(cudaFuncSetAttribute(update_pairs_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_u));
     attr_done = true;
   }
-  const int inner = 1;
   int sweeps = 0;
+  auto step = [&](const int* pa, const int* pb, int cnt, int cross) {
+    {
+      ProfScope prof_scope_(KF_GEMM);
+      gram_pairs_kernel<T><<<dim3(cnt, nsplit), GT, smem_g, ctx().stream>>>(X, m, n, ldx, pa, pb, mc, Gp.as<T>());
+      TTN_CHECK_LAUNCH();
+    }
+    {
+      ProfScope prof_scope_(KF_JACOBI);
+      gram_eig_kernel<T, GE><<<cnt, GE, smem_e, ctx().stream>>>(Gp.as<T>(), nsplit, cross, tol, frob2, fk, Vg.as<T>(),
+                                                               skip.as<int>(), rot.as<unsigned int>());
+      TTN_CHECK_LAUNCH();
+    }
+    {
+      ProfScope prof_scope_(KF_GEMM);
+      update_pairs_kernel<T><<<dim3(cnt, (m + UM - 1) / UM), GT, smem_u, ctx().stream>>>(X, m, n, ldx, pa, pb, Vg.as<T>(),
+                                                                                        skip.as<int>());
+      TTN_CHECK_LAUNCH();
+    }
+    ctx().launches += 3;
+  };
   for (int sw = 0; sw < max_sweeps; ++sw) {
     TTN_CUDA(cudaMemsetAsync(rot.p, 0, sizeof(unsigned int), ctx().stream));
-    for (int st = 0; st < ne - 1; ++st) {
+    step(gA.as<int>() + off_diag, gB.as<int>() + off_diag, nblk, 0);          // pairs inside each block
+    for (int st = 0; st < ne - 1; ++st) {                                      // cross pairs of the block tournament
       const int cnt = off[st + 1] - off[st];
-      if (cnt <= 0) continue;
-      const int* pa = gA.as<int>() + off[st];
-      const int* pb = gB.as<int>() + off[st];
-      {
-        ProfScope prof_scope_(KF_GEMM);
-        gram_pairs_kernel<T><<<dim3(cnt, nsplit), GT, smem_g, ctx().stream>>>(X, m, n, ldx, pa, pb, mc, Gp.as<T>());
-        TTN_CHECK_LAUNCH();
-      }
-      {
-        ProfScope prof_scope_(KF_JACOBI);
-        gram_eig_kernel<T><<<cnt, GT, smem_e, ctx().stream>>>(Gp.as<T>(), nsplit, inner, tol, frob2, fk, Vg.as<T>(), skip.as<int>(),
-                                                        rot.as<unsigned int>());
-        TTN_CHECK_LAUNCH();
-      }
-      {
-        ProfScope prof_scope_(KF_GEMM);
-        update_pairs_kernel<T><<<dim3(cnt, (m + UM - 1) / UM), GT, smem_u, ctx().stream>>>(X, m, n, ldx, pa, pb, Vg.as<T>(),
-                                                                                          skip.as<int>());
-        TTN_CHECK_LAUNCH();
-      }
-      ctx().launches += 3;
+      if (cnt > 0) step(gA.as<int>() + off[st], gB.as<int>() + off[st], cnt, 1);
     }
     unsigned int rotated = 0;
     TTN_CUDA(cudaMemcpyAsync(&rotated, rot.p, sizeof(rotated), cudaMemcpyDeviceToHost, ctx().stream));
