@@ -7,8 +7,9 @@
 // B200); here the O(m k^2) work is three DMMA GEMMs and the sequential part is a k x k Cholesky in one SM:
 //     G1 = A^H A,  R1 = chol(G1),  Q1 = A R1^-1,  G2 = Q1^H Q1,  R2 = chol(G2),  Q = Q1 R2^-1,  R = R2 R1.
 // The second pass restores orthogonality to O(eps) as long as eps*cond(A)^2 << 1.  The first Cholesky reports
-// min/max of diag(R1) (a lower bound of cond(A)); the caller falls back to Householder when the ratio is below 1e-4
-// or a pivot is not positive, so ill-conditioned and rank-deficient inputs never take this path.
+// min/max of diag(R1) (a lower bound of 1/cond(A)): below 1e-4 (or with a non-positive pivot) the caller falls back to
+// Householder, so ill-conditioned and rank-deficient inputs never take this path; above 0.3 (cond(A) of a few units) the
+// first pass alone is accurate to a few tens of eps and the second one is skipped.
 #include "ttn_internal.h"
 
 namespace ttn {
@@ -255,15 +256,51 @@ bool cholqr2(const T* A, int m, int k, int64_t lda, int64_t bA, T* R, T* Q, int6
     attr_done = true;
   }
   const size_t kk = (size_t)k * k;
-  DevBuf Gp(sizeof(T) * kk * nsplit * batch), R1(sizeof(T) * kk * batch), R2(sizeof(T) * kk * batch), X(sizeof(T) * kk * batch);
-  DevBuf Q1(sizeof(T) * (size_t)m * k * batch), st(sizeof(double) * batch);
+  DevBuf Gp(sizeof(T) * kk * nsplit * batch), R1(sizeof(T) * kk * batch), X(sizeof(T) * kk * batch), st(sizeof(double) * batch);
   gram_partials<T>(A, m, k, lda, bA, nsplit, Gp.as<T>(), batch);
+  // first Cholesky.  The inverse is only computed when an explicit Q is wanted; an R-only call (SVD preconditioner) can stop
+  // after this kernel if the matrix turns out to be well conditioned (below).
   {
     ProfScope prof_scope_(KF_QR_PANEL);
-    chol_inv_kernel<T><<<batch, CQ_T, smem, ctx().stream>>>(Gp.as<T>(), nsplit, k, nullptr, R1.as<T>(), X.as<T>(), st.as<double>());
+    chol_inv_kernel<T><<<batch, CQ_T, smem, ctx().stream>>>(Gp.as<T>(), nsplit, k, nullptr, R1.as<T>(), Q ? X.as<T>() : nullptr,
+                                                           st.as<double>());
     TTN_CHECK_LAUNCH();
     ctx().launches++;
   }
+  std::vector<double> h(batch);
+  TTN_CUDA(cudaMemcpyAsync(h.data(), st.p, sizeof(double) * batch, cudaMemcpyDeviceToHost, ctx().stream));
+  TTN_CUDA(cudaStreamSynchronize(ctx().stream));
+  double worst = 1.0;
+  for (double v : h) {
+    if (!(v >= 1e-4)) return false;                 // ill conditioned / not positive definite: Householder path
+    worst = std::min(worst, v);
+  }
+  // One pass is enough when cond(A) is small: the loss of CholeskyQR is eps*cond^2 (relative, in R and in Q^H Q - I);
+  // min/max diag(R1) >= 0.3 means cond(A) of a few units (cfg2's bonds: 0.39 ... 0.78), i.e. a few tens of eps — the level of
+  // the rounding of the K = 512 GEMMs around it.
+  const bool single = worst >= 0.3;
+  if (getenv("TTN_DEBUG_SVD")) fprintf(stderr, "[ttn] cholqr2 %d x %d batch %d: min/max diag(R1) = %.3g -> %s\n", m, k, batch, worst, single ? "one pass" : "two passes");
+  if (single) {
+    TTN_CUDA(cudaMemcpyAsync(R, R1.p, sizeof(T) * kk * batch, cudaMemcpyDeviceToDevice, ctx().stream));
+    if (Q != nullptr) {
+      GemmArgs g;   // Q = A X1
+      g.M = m; g.N = k; g.K = k;
+      g.A = A; g.sAm = 1; g.sAk = lda; g.bA1 = bA;
+      g.B = X.p; g.sBk = 1; g.sBn = k; g.bB1 = (int64_t)kk;
+      g.C = Q; g.sCm = 1; g.sCn = ldq; g.bC1 = bQ;
+      g.batch1 = batch;
+      gemm<T>(g);
+    }
+    return true;                                     // (workspaces are stream-ordered: no sync needed to release them)
+  }
+  if (Q == nullptr) {
+    // second pass needs X1 = R1^-1 after all: redo the (cheap, k x k) factorisation with the inverse
+    ProfScope prof_scope_(KF_QR_PANEL);
+    chol_inv_kernel<T><<<batch, CQ_T, smem, ctx().stream>>>(Gp.as<T>(), nsplit, k, nullptr, R1.as<T>(), X.as<T>(), nullptr);
+    TTN_CHECK_LAUNCH();
+    ctx().launches++;
+  }
+  DevBuf R2(sizeof(T) * kk * batch), Q1(sizeof(T) * (size_t)m * k * batch);
   {
     GemmArgs g;   // Q1 = A X1
     g.M = m; g.N = k; g.K = k;
@@ -298,11 +335,6 @@ bool cholqr2(const T* A, int m, int k, int64_t lda, int64_t bA, T* R, T* Q, int6
     g.batch1 = batch;
     gemm<T>(g);
   }
-  std::vector<double> h(batch);
-  TTN_CUDA(cudaMemcpyAsync(h.data(), st.p, sizeof(double) * batch, cudaMemcpyDeviceToHost, ctx().stream));
-  TTN_CUDA(cudaStreamSynchronize(ctx().stream));
-  for (double v : h)
-    if (!(v >= 1e-4)) return false;
   return true;
 }
 
