@@ -180,6 +180,15 @@ def cpu_reference_sweep(budget_s, faithful=True):
     return full, done, len(order)
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 for N > 1; the CPU legs are meant to use every host core the BLAS can use."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        pass
+
+
 def host_threads():
     try:
         from threadpoolctl import threadpool_info
@@ -196,6 +205,7 @@ def host_threads():
 def cpu_extras(extras, chi=1024, w=5, nn=4):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import ttn_oracle as o
+    use_all_host_threads()
     cores = host_threads()
     rng = np.random.default_rng(4)
     out = {}
@@ -245,6 +255,7 @@ def cpu_extras(extras, chi=1024, w=5, nn=4):
 def run_reference(args, rank):
     if rank != 0:
         return
+    use_all_host_threads()
     budget = max(2.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
     times = []
     for i in range(args.warmup + args.steps):
@@ -407,6 +418,7 @@ def run_ours(args, rank, local_rank, world):
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu:
+            use_all_host_threads()
             full, done, total = cpu_reference_sweep(25.0, faithful=False)
             ffull, fdone, ftotal = cpu_reference_sweep(12.0, faithful=True)
             cpu = {"value": 1.0 / full, "unit": "sweeps/s", "cores": host_threads(), "kind": "port",
