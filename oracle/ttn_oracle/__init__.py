@@ -29,4 +29,5 @@ from .als import als_linsolve, als_eigsolve
 from .mals import mals_linsolve, mals_eigsolve, sv_trunc
 from .dmrg import dmrg_linsolve, dmrg_eigsolve, cut_off_index, dmrg_matvec2, dmrg_matvec2_blas, dmrg_update_G, dmrg_update_H, amid
 from .tdvp import tdvp, tdvp2, apply_H1_lsr, apply_H0, apply_H2_lsr, update_left_env, update_right_env
+from .krylov_tt import krylov_linsolve
 from .steppers import euler_method, implicit_euler_method, crank_nicholson_method, rk4_method

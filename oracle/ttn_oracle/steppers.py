@@ -20,7 +20,8 @@ def _shifted(A, alpha):
 
 
 def _lin(tt_solver, M, rhs, guess, kw):
-    fn = {"mals": mals_linsolve, "als": als_linsolve, "dmrg": dmrg_linsolve}.get(tt_solver)
+    from .krylov_tt import krylov_linsolve
+    fn = {"mals": mals_linsolve, "als": als_linsolve, "dmrg": dmrg_linsolve, "krylov": krylov_linsolve}.get(tt_solver)
     if fn is None:
         raise ValueError(f"Unknown TT solver: {tt_solver}")
     return fn(M, rhs, guess, **kw)
@@ -45,7 +46,7 @@ def _implicit(A, u0, guess, steps, normalize, return_error, tt_solver, max_bond,
     for h in steps:
         M = _shifted(A, -theta * h)
         rhs = sol if theta == 1.0 else apply(_shifted(A, (1.0 - theta) * h), sol)
-        nxt = _lin(tt_solver, M, rhs, guess, kw)
+        nxt = _lin(tt_solver, M, rhs, guess, dict(kw, max_bond=max_bond) if tt_solver == "krylov" else kw)
         if normalize:
             nxt = scale(1.0 / norm(nxt), nxt)
         prev = sol

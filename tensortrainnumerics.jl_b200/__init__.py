@@ -5,5 +5,6 @@ The directory name contains a dot, so import it through the top-level shim:  ``i
 """
 from .api import *  # noqa: F401,F403
 from .api import __all__  # noqa: F401
+from .krylov_tt import krylov_linsolve  # noqa: F401,E402
 from .steppers import (euler_method, implicit_euler_method, crank_nicholson_method, rk4_method,  # noqa: F401,E402
                        id_tto, tto_add, tto_scale)

@@ -69,7 +69,10 @@ def _lin(tt_solver, M, rhs, guess, kw):
         return _a.als_linsolve(M, rhs, guess, **kw)
     if tt_solver == "dmrg":
         return _a.dmrg_linsolve(M, rhs, guess, **kw)
-    raise ValueError(f"Unknown TT solver: {tt_solver}")    # "krylov" (krylov_linsolve, euler.jl:34-74) is not on the device path yet
+    if tt_solver == "krylov":
+        from .krylov_tt import krylov_linsolve
+        return krylov_linsolve(M, rhs, guess, **kw)
+    raise ValueError(f"Unknown TT solver: {tt_solver}")
 
 
 def _host_op(A):
@@ -105,7 +108,7 @@ def _implicit(A, u0, guess, steps, normalize, return_error, tt_solver, max_bond,
     for h in steps:
         M = _a.DeviceTTO.upload(_shifted(A, -theta * h))
         rhs = sol if theta == 1.0 else _a.apply(_a.DeviceTTO.upload(_shifted(A, (1.0 - theta) * h)), sol)
-        nxt = _lin(tt_solver, M, rhs, guess, kw)
+        nxt = _lin(tt_solver, M, rhs, guess, dict(kw, max_bond=max_bond) if tt_solver == "krylov" else kw)
         if normalize:
             nxt = _a.scale(1.0 / _a.norm(nxt), nxt)
         prev = sol

@@ -85,3 +85,44 @@ def test_rk4_vs_dense_and_oracle():
         v = v / np.linalg.norm(v)
     assert _rel(_vec(sol), v) < 1e-10
     assert err < 1e-8
+
+
+def _grad(d):
+    return o.tto_scale(0.1, o.toeplitz_to_qtto(1.0, 0.0, -1.0, d))     # 0.1 * nabla(d), tt_operators.jl:276-278
+
+
+def test_krylov_linsolve_solvers_vs_dense():
+    """`krylov_linsolve` (euler.jl:34-74) on the device: GMRES (unbounded rank), bounded BiCGStab, CG on an SPD operator."""
+    import ttn_b200 as t
+    d = 5
+    rng = np.random.default_rng(8)
+    A = o.tto_add(o.laplace_dd(d), o.tto_scale(2.0, o.id_tto(d)))
+    b = o.rand_tt((2,) * d, 2, rng=rng)
+    ref = np.linalg.solve(o.tto_to_matrix(A), _vec(b))
+    x = t.krylov_linsolve(A, b, b, krylov_solver=":gmres", krylovdim=12, maxiter=10, rtol=1e-12)
+    assert _rel(_vec(x), ref) < 1e-9
+    x = t.krylov_linsolve(A, b, b, isposdef=True, issymmetric=True, krylovdim=10, maxiter=10, rtol=1e-12)
+    assert _rel(_vec(x), ref) < 1e-9
+    x = t.krylov_linsolve(A, b, b, max_bond=16, maxiter=40, rtol=1e-11)          # :auto -> BiCGStab when max_bond > 0
+    assert _rel(_vec(x), ref) < 1e-8 and max(x.ttv_rks) <= 16
+    with pytest.raises(ValueError):
+        t.krylov_linsolve(A, b, b, krylov_solver=":minres")
+
+
+def test_crank_nicholson_krylov_nonsymmetric_vs_dense_and_oracle():
+    # test/test_euler.jl:139-200
+    import ttn_b200 as t
+    d = 5
+    A = _grad(d)
+    u0 = o.rand_tt((2,) * d, [1] + [2] * (d - 1) + [1], rng=np.random.default_rng(2))
+    Ad = o.tto_to_matrix(A); ud = _vec(u0)
+    I = np.eye(Ad.shape[0])
+    ref = np.linalg.solve(I - 0.025 * Ad, (I + 0.025 * Ad) @ ud)
+    sol = t.crank_nicholson_method(A, u0, u0, [0.05], normalize=False, tt_solver="krylov", tol=1e-12)
+    assert _rel(_vec(sol), ref) < 1e-8
+    sol = t.crank_nicholson_method(A, u0, u0, [0.05], normalize=False, tt_solver="krylov", max_bond=8,
+                                   krylov_solver=":bicgstab", maxiter=30, rtol=1e-10, atol=1e-12)
+    assert _rel(_vec(sol), ref) < 1e-7 and max(sol.ttv_rks) <= 8
+    solo = o.crank_nicholson_method(A, u0, u0, [0.05], normalize=False, tt_solver="krylov", max_bond=8,
+                                    krylov_solver=":bicgstab", maxiter=30, rtol=1e-10, atol=1e-12)
+    assert _rel(_vec(sol), _vec(solo)) < 1e-7

@@ -65,3 +65,51 @@ def test_euler_normalize_and_return_error():
     assert _rel(_vec(sol), v) < 1e-10
     assert abs(np.linalg.norm(_vec(sol)) - 1.0) < 1e-12
     assert err < 1.0
+
+
+def _grad(d):
+    return o.tto_scale(0.1, o.toeplitz_to_qtto(1.0, 0.0, -1.0, d))     # 0.1 * nabla(d), tt_operators.jl:276-278
+
+
+def test_implicit_euler_krylov_vs_dense():
+    # test_euler.jl:61-86 (GMRES through the TT vector interface, tol 1e-12, rel. error < 1e-8)
+    A, u0, Ad, ud = _setup()
+    sol = o.implicit_euler_method(A, u0, u0, [0.05], normalize=False, tt_solver="krylov", tol=1e-12)
+    ref = np.linalg.solve(np.eye(Ad.shape[0]) - 0.05 * Ad, ud)
+    assert _rel(_vec(sol), ref) < 1e-8
+
+
+def test_crank_nicholson_krylov_nonsymmetric_vs_dense():
+    # test_euler.jl:139-166
+    d = 4
+    A = _grad(d)
+    u0 = o.rand_tt((2,) * d, [1] + [2] * (d - 1) + [1], rng=np.random.default_rng(1))
+    Ad = o.tto_to_matrix(A); ud = _vec(u0)
+    assert not np.allclose(Ad, Ad.T)
+    sol = o.crank_nicholson_method(A, u0, u0, [0.05], normalize=False, tt_solver="krylov", tol=1e-12)
+    I = np.eye(Ad.shape[0])
+    ref = np.linalg.solve(I - 0.025 * Ad, (I + 0.025 * Ad) @ ud)
+    assert _rel(_vec(sol), ref) < 1e-8
+
+
+def test_crank_nicholson_bounded_bicgstab_vs_dense():
+    # test_euler.jl:168-200
+    d, max_bond = 5, 8
+    A = _grad(d)
+    u0 = o.rand_tt((2,) * d, [1] + [2] * (d - 1) + [1], rng=np.random.default_rng(2))
+    Ad = o.tto_to_matrix(A); ud = _vec(u0)
+    sol = o.crank_nicholson_method(A, u0, u0, [0.05], normalize=False, tt_solver="krylov", max_bond=max_bond,
+                                   krylov_solver=":bicgstab", maxiter=30, rtol=1e-10, atol=1e-12)
+    I = np.eye(Ad.shape[0])
+    ref = np.linalg.solve(I - 0.025 * Ad, (I + 0.025 * Ad) @ ud)
+    assert _rel(_vec(sol), ref) < 1e-7
+    assert max(sol.ttv_rks) <= max_bond
+
+
+def test_krylov_linsolve_cg_spd():
+    d = 5
+    A = o.tto_add(o.laplace_dd(d), o.tto_scale(2.0, o.id_tto(d)))
+    b = o.rand_tt((2,) * d, 2, rng=np.random.default_rng(4))
+    x = o.krylov_linsolve(A, b, b, isposdef=True, issymmetric=True, krylovdim=10, maxiter=10, rtol=1e-12)
+    ref = np.linalg.solve(o.tto_to_matrix(A), _vec(b))
+    assert _rel(_vec(x), ref) < 1e-9
