@@ -126,3 +126,27 @@ def test_crank_nicholson_krylov_nonsymmetric_vs_dense_and_oracle():
     solo = o.crank_nicholson_method(A, u0, u0, [0.05], normalize=False, tt_solver="krylov", max_bond=8,
                                     krylov_solver=":bicgstab", maxiter=30, rtol=1e-10, atol=1e-12)
     assert _rel(_vec(sol), _vec(solo)) < 1e-7
+
+
+def test_krylov_cg_selection_unknown_solver_and_options():
+    # test/test_euler.jl:203-267 on the device path
+    import ttn_b200 as t
+    d = 3
+    A = o.tto_scale(0.1, o.id_tto(d))
+    u0 = o.rand_tt((2,) * d, [1] + [2] * (d - 1) + [1], rng=np.random.default_rng(5))
+    sol = t.implicit_euler_method(A, u0, u0, [0.05], normalize=False, tt_solver="krylov", isposdef=True, issymmetric=True, tol=1e-12)
+    Ad = o.tto_to_matrix(A)
+    ref = np.linalg.solve(np.eye(Ad.shape[0]) - 0.05 * Ad, _vec(u0))
+    assert _rel(_vec(sol), ref) < 1e-8
+    with pytest.raises(ValueError):
+        t.implicit_euler_method(A, u0, u0, [0.05], normalize=False, tt_solver="krylov", krylov_solver=":unknown")
+    h = 1.0 / d ** 2
+    A = o.tto_scale(-h ** 2, o.toeplitz_to_qtto(-2.0, 1.0, 1.0, d))
+    steps = [0.02]
+    s1, e1 = t.euler_method(A, u0, steps, normalize=True, return_error=True)
+    s2, e2 = t.implicit_euler_method(A, u0, u0, steps, normalize=True, return_error=True, tt_solver="krylov", tol=1e-10)
+    s3, e3 = t.crank_nicholson_method(A, u0, u0, steps, normalize=True, return_error=True, tt_solver="krylov", tol=1e-10)
+    s4 = t.rk4_method(A, u0, steps, 6, normalize=True)
+    for s in (s1, s2, s3, s4):
+        assert abs(o.norm(s) - 1.0) < 1e-10
+    assert all(np.isfinite(e) for e in (e1, e2, e3))

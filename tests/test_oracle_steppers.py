@@ -113,3 +113,33 @@ def test_krylov_linsolve_cg_spd():
     x = o.krylov_linsolve(A, b, b, isposdef=True, issymmetric=True, krylovdim=10, maxiter=10, rtol=1e-12)
     ref = np.linalg.solve(o.tto_to_matrix(A), _vec(b))
     assert _rel(_vec(x), ref) < 1e-9
+
+
+def test_krylov_cg_selection_and_unknown_solver():
+    # test_euler.jl:203-236
+    import pytest
+    d = 3
+    A = o.tto_scale(0.1, o.id_tto(d))
+    u0 = o.rand_tt((2,) * d, [1] + [2] * (d - 1) + [1], rng=np.random.default_rng(5))
+    sol = o.implicit_euler_method(A, u0, u0, [0.05], normalize=False, tt_solver="krylov", isposdef=True, issymmetric=True, tol=1e-12)
+    Ad = o.tto_to_matrix(A)
+    ref = np.linalg.solve(np.eye(Ad.shape[0]) - 0.05 * Ad, _vec(u0))
+    assert _rel(_vec(sol), ref) < 1e-8
+    with pytest.raises(ValueError):
+        o.implicit_euler_method(A, u0, u0, [0.05], normalize=False, tt_solver="krylov", krylov_solver=":unknown")
+
+
+def test_euler_family_normalize_and_return_error_options():
+    # test_euler.jl:238-267
+    d = 3
+    h = 1.0 / d ** 2
+    A = o.tto_scale(-h ** 2, o.toeplitz_to_qtto(-2.0, 1.0, 1.0, d))
+    u0 = o.rand_tt((2,) * d, [1] + [2] * (d - 1) + [1], rng=np.random.default_rng(6))
+    steps = [0.02]
+    s1, e1 = o.euler_method(A, u0, steps, normalize=True, return_error=True)
+    s2, e2 = o.implicit_euler_method(A, u0, u0, steps, normalize=True, return_error=True, tt_solver="krylov", tol=1e-10)
+    s3, e3 = o.crank_nicholson_method(A, u0, u0, steps, normalize=True, return_error=True, tt_solver="krylov", tol=1e-10)
+    s4 = o.rk4_method(A, u0, steps, 6, normalize=True)
+    for s in (s1, s2, s3, s4):
+        assert abs(o.norm(s) - 1.0) < 1e-10
+    assert all(np.isfinite(e) for e in (e1, e2, e3))
