@@ -10,7 +10,7 @@
 //                           columns, but each costs 64-vectors instead of m-vectors);
 //   3. update_pairs_kernel: P_k <- P_k V_k in place                                      — DMMA.
 // The O(m n^2) work per sweep runs as GEMM tiles (8 m n^2 flop per sweep at ~70 % of the DMMA peak) instead of scalar
-// rotations bound by shared-memory bandwidth and shuffle latency (jacobi_cross_kernel: ~15 % of the FP64 peak).
+// rotations bound by shared-memory bandwidth and shuffle latency (jacobi_cross_kernel: FP64 pipe 22 % busy, profiles/ncu_dmrg_svd_r01.txt).
 // Entries of G are inner products of the actual columns, i.e. accurate relative to ||x_p|| ||x_q||, and two-sided Jacobi
 // on a positive definite matrix is relatively accurate (Demmel-Veselic), so the rotation threshold stays the relative
 // one, |x_p^H x_q| <= tol ||x_p|| ||x_q||, evaluated on a freshly computed Gram matrix at every step.
