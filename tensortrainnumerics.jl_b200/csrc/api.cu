@@ -50,7 +50,7 @@ int ttn_init(int device) {
     TTN_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
     c.use_cluster_jacobi = getenv("TTN_NO_CLUSTER_JACOBI") == nullptr;
     c.use_cholqr = getenv("TTN_NO_CHOLQR") == nullptr;
-    c.use_gram_jacobi = getenv("TTN_GRAM_JACOBI") != nullptr;   // experimental: at parity with the scalar block path from 1024^2 up, slower below
+    if (const char* e = getenv("TTN_GRAM_JACOBI")) c.gram_jacobi_min = (atoi(e) != 0) ? 128 : (1 << 30);
     c.inited = true;
   }
   API_END

@@ -461,7 +461,7 @@ int jacobi_orth(T* X, int m, int n, int64_t ldx, double* norms, int batch, int64
     TTN_CUDA(cudaMemcpyAsync(&hsw, dsw.p, sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
     TTN_CUDA(cudaStreamSynchronize(ctx().stream));
     sweeps_used = hsw;
-  } else if (ctx().use_gram_jacobi && n >= 128 && m >= 64) {
+  } else if (n >= 128 && m >= 64 && std::min(m, n) >= ctx().gram_jacobi_min) {
     // large matrices: Gram-block Jacobi, O(m n^2) work on the FP64 tensor pipe (jacobi_gram.cu)
     for (int b = 0; b < batch; ++b) {
       const int sw = jacobi_gram<T>(X + (int64_t)b * bX, m, n, ldx, tol, fr + b, fk, JAC_MAX_SWEEPS);

@@ -310,14 +310,29 @@ int jacobi_gram(T* X, int m, int n, int64_t ldx, double tol, const double* frob2
   const int off_diag = (int)hA.size();
   for (int i = 0; i < nblk; ++i) { hA.push_back(i); hB.push_back(-1); }
   const int maxpairs = std::max(ne / 2, nblk);
-  int nsplit = std::max(1, std::min((2 * ctx().sm_count + maxpairs - 1) / maxpairs, m / (2 * GK)));
-  nsplit = std::min(nsplit, 16);
-  int mc = (m + nsplit - 1) / nsplit;
-  mc = (mc + GK - 1) / GK * GK;
-  nsplit = (m + mc - 1) / mc;
+  // Two pair groups per step on two streams: while the (few, latency-bound) inner eigen-sweep CTAs of one group run, the
+  // DMMA Gram / update tiles of the other group fill the remaining SMs.  Each group has its own Gram / V / skip buffers
+  // and its own split of the rows sized for ~2 CTAs per SM.
+  static cudaStream_t s2 = nullptr;
+  static cudaEvent_t ev_main = nullptr, ev_s2 = nullptr;
+  if (s2 == nullptr) {
+    TTN_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+    TTN_CUDA(cudaEventCreateWithFlags(&ev_main, cudaEventDisableTiming));
+    TTN_CUDA(cudaEventCreateWithFlags(&ev_s2, cudaEventDisableTiming));
+  }
+  const int halfmax = (maxpairs + 1) / 2;
+  auto split_for = [&](int cnt, int& ns, int& mcs) {
+    ns = std::max(1, std::min((2 * ctx().sm_count + cnt - 1) / std::max(cnt, 1), m / (2 * GK)));
+    ns = std::min(ns, 16);
+    mcs = (m + ns - 1) / ns;
+    mcs = (mcs + GK - 1) / GK * GK;
+    ns = (m + mcs - 1) / mcs;
+  };
+  const size_t gp_elems = (size_t)halfmax * 16 * PW * PW;          // <= 16 row splits
   DevBuf gA(sizeof(int) * hA.size()), gB(sizeof(int) * hB.size());
-  DevBuf Gp(sizeof(T) * (size_t)maxpairs * nsplit * PW * PW), Vg(sizeof(T) * (size_t)maxpairs * PW * PW);
-  DevBuf skip(sizeof(int) * maxpairs), rot(sizeof(unsigned int));
+  DevBuf Gp0(sizeof(T) * gp_elems), Gp1(sizeof(T) * gp_elems);
+  DevBuf Vg0(sizeof(T) * (size_t)halfmax * PW * PW), Vg1(sizeof(T) * (size_t)halfmax * PW * PW);
+  DevBuf skip0(sizeof(int) * halfmax), skip1(sizeof(int) * halfmax), rot(sizeof(unsigned int));
   TTN_CUDA(cudaMemcpyAsync(gA.p, hA.data(), sizeof(int) * hA.size(), cudaMemcpyHostToDevice, ctx().stream));
   TTN_CUDA(cudaMemcpyAsync(gB.p, hB.data(), sizeof(int) * hB.size(), cudaMemcpyHostToDevice, ctx().stream));
   TTN_CUDA(cudaStreamSynchronize(ctx().stream));   // host staging vectors must outlive the copies
@@ -332,33 +347,40 @@ int jacobi_gram(T* X, int m, int n, int64_t ldx, double tol, const double* frob2
     attr_done = true;
   }
   int sweeps = 0;
-  auto step = [&](const int* pa, const int* pb, int cnt, int cross) {
-    {
-      ProfScope prof_scope_(KF_GEMM);
-      gram_pairs_kernel<T><<<dim3(cnt, nsplit), GT, smem_g, ctx().stream>>>(X, m, n, ldx, pa, pb, mc, Gp.as<T>());
-      TTN_CHECK_LAUNCH();
-    }
-    {
-      ProfScope prof_scope_(KF_JACOBI);
-      gram_eig_kernel<T, GE><<<cnt, GE, smem_e, ctx().stream>>>(Gp.as<T>(), nsplit, cross, tol, frob2, fk, Vg.as<T>(),
-                                                               skip.as<int>(), rot.as<unsigned int>());
-      TTN_CHECK_LAUNCH();
-    }
-    {
-      ProfScope prof_scope_(KF_GEMM);
-      update_pairs_kernel<T><<<dim3(cnt, (m + UM - 1) / UM), GT, smem_u, ctx().stream>>>(X, m, n, ldx, pa, pb, Vg.as<T>(),
-                                                                                        skip.as<int>());
-      TTN_CHECK_LAUNCH();
-    }
+  auto group = [&](cudaStream_t st, const int* pa, const int* pb, int cnt, int cross, T* Gp, T* Vg, int* skip) {
+    if (cnt <= 0) return;
+    int ns, mcs;
+    split_for(cnt, ns, mcs);
+    gram_pairs_kernel<T><<<dim3(cnt, ns), GT, smem_g, st>>>(X, m, n, ldx, pa, pb, mcs, Gp);
+    TTN_CHECK_LAUNCH();
+    gram_eig_kernel<T, GE><<<cnt, GE, smem_e, st>>>(Gp, ns, cross, tol, frob2, fk, Vg, skip, rot.as<unsigned int>());
+    TTN_CHECK_LAUNCH();
+    update_pairs_kernel<T><<<dim3(cnt, (m + UM - 1) / UM), GT, smem_u, st>>>(X, m, n, ldx, pa, pb, Vg, skip);
+    TTN_CHECK_LAUNCH();
     ctx().launches += 3;
   };
+  // one tournament step: group 0 on the library stream, group 1 on s2; each waits for the other group's previous step
+  auto step = [&](const int* pa, const int* pb, int cnt, int cross) {
+    const int c0 = (cnt + 1) / 2, c1 = cnt - c0;
+    TTN_CUDA(cudaStreamWaitEvent(ctx().stream, ev_s2, 0));
+    TTN_CUDA(cudaStreamWaitEvent(s2, ev_main, 0));
+    group(ctx().stream, pa, pb, c0, cross, Gp0.as<T>(), Vg0.as<T>(), skip0.as<int>());
+    group(s2, pa + c0, pb + c0, c1, cross, Gp1.as<T>(), Vg1.as<T>(), skip1.as<int>());
+    TTN_CUDA(cudaEventRecord(ev_main, ctx().stream));
+    TTN_CUDA(cudaEventRecord(ev_s2, s2));
+  };
+  ProfScope prof_scope_(KF_JACOBI);                  // (per-kernel families are not separable across two streams)
+  TTN_CUDA(cudaEventRecord(ev_main, ctx().stream));  // s2 starts after everything queued so far (X is ready)
+  TTN_CUDA(cudaEventRecord(ev_s2, s2));
   for (int sw = 0; sw < max_sweeps; ++sw) {
     TTN_CUDA(cudaMemsetAsync(rot.p, 0, sizeof(unsigned int), ctx().stream));
+    TTN_CUDA(cudaEventRecord(ev_main, ctx().stream));
     step(gA.as<int>() + off_diag, gB.as<int>() + off_diag, nblk, 0);          // pairs inside each block
     for (int st = 0; st < ne - 1; ++st) {                                      // cross pairs of the block tournament
       const int cnt = off[st + 1] - off[st];
       if (cnt > 0) step(gA.as<int>() + off[st], gB.as<int>() + off[st], cnt, 1);
     }
+    TTN_CUDA(cudaStreamWaitEvent(ctx().stream, ev_s2, 0));
     unsigned int rotated = 0;
     TTN_CUDA(cudaMemcpyAsync(&rotated, rot.p, sizeof(rotated), cudaMemcpyDeviceToHost, ctx().stream));
     TTN_CUDA(cudaStreamSynchronize(ctx().stream));

@@ -219,3 +219,22 @@ def test_svdtrunc_across_condition_numbers(shape, cond):
     assert np.abs(sg - s).max() < 1e-12
     assert relerr((Ug * sg) @ Vtg, A) < 1e-12
     assert np.abs(Ug.T @ Ug - np.eye(k)).max() < 1e-11
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(1024, 1024), (1100, 1030)])
+def test_svdtrunc_large_gram_block_path(shape):
+    """Bond matrices of DMRG size take the Gram-block Jacobi on the DMMA pipe (jacobi_gram.cu, two pair groups on two
+    streams) after the Householder preconditioning: singular values and reconstruction against LAPACK."""
+    import ttn_b200 as t
+    rng = np.random.default_rng(shape[1])
+    m, n = shape
+    k = min(m, n)
+    U, _ = np.linalg.qr(rng.standard_normal((m, k)))
+    V, _ = np.linalg.qr(rng.standard_normal((n, k)))
+    s = np.logspace(0, -8, k)
+    A = np.asfortranarray((U * s) @ V.T)
+    Ug, sg, Vtg = t.svdtrunc(A)
+    assert np.abs(sg - s).max() < 1e-11
+    assert relerr((Ug * sg) @ Vtg, A) < 1e-11
+    assert np.abs(Ug.T @ Ug - np.eye(k)).max() < 1e-10
