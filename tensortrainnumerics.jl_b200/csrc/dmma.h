@@ -31,4 +31,16 @@ template <> struct Acc<zc> {
 };
 
 
+// 8 / 16-byte asynchronous global -> shared copy (LDGSTS); src_bytes = 0 zero-fills the destination (out-of-range elements)
+template <class T>
+__device__ __forceinline__ void cp_async_elem(T* smem_dst, const T* gsrc, bool valid) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? (int)sizeof(T) : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;\n" ::"r"(dst), "l"(gsrc), "n"(sizeof(T)), "r"(n));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+
 }  // namespace ttn

@@ -224,67 +224,80 @@ __global__ void __launch_bounds__(ET) gram_eig_kernel(const T* __restrict__ Gp, 
 // ---------------------------------------------------------------------------------------------------------------------
 // 3. P_k <- P_k V_k in place.  grid (npairs, ceil(m / UM)).
 // ---------------------------------------------------------------------------------------------------------------------
+// The UM = 128 rows of a CTA tile are processed as two halves of 64: both halves (and V) are requested with cp.async up
+// front, the DMMA work on the first half and its write-back overlap the arrival of the second.
 template <class T>
 __global__ void __launch_bounds__(GT) update_pairs_kernel(T* __restrict__ X, int m, int n, int64_t ldx,
                                                           const int* __restrict__ pairA, const int* __restrict__ pairB,
                                                           const T* __restrict__ Vg, const int* __restrict__ skip) {
   if (skip[blockIdx.x]) return;
-  constexpr int PA = UM + 4, PB = PW + 4;
+  constexpr int UH = UM / 2;                 // rows per half tile
+  constexpr int PA = UH + 4, PB = PW + 4;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* As = reinterpret_cast<T*>(smem_raw);   // [PW][PA]  As[k][row]
-  T* Bs = As + PW * PA;                     // [PW][PB]  Bs[k][ncol]
+  T* As = reinterpret_cast<T*>(smem_raw);   // [2][PW][PA]  As[h][k][row]
+  T* Bs = As + 2 * PW * PA;                 // [PW][PB]     Bs[k][ncol]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g8 = lane >> 2, t4 = lane & 3;
   const int blkA = pairA[blockIdx.x], blkB = pairB[blockIdx.x];
   const int row0 = blockIdx.y * UM;
   {
-    const int row = tid & (UM - 1), c0 = tid / UM;          // 2 column phases
-    const bool rok = row0 + row < m;
-#pragma unroll 8
-    for (int i = 0; i < PW / 2; ++i) {
-      const int c = c0 + 2 * i;
-      const T* cp = panel_col<T>(X, ldx, n, blkA, blkB, c);
-      As[c * PA + row] = (cp != nullptr && rok) ? cp[row0 + row] : t_zero<T>();
-    }
     const T* vg = Vg + (size_t)blockIdx.x * PW * PW;
     const int k = tid & (PW - 1), n0 = tid / PW;             // 4 column phases
 #pragma unroll 4
     for (int i = 0; i < PW / 4; ++i) {
       const int nc = n0 + 4 * i;
-      Bs[k * PB + nc] = vg[(size_t)nc * PW + k];
+      cp_async_elem<T>(Bs + k * PB + nc, vg + (size_t)nc * PW + k, true);
+    }
+    const int row = tid & (UH - 1), c0 = tid / UH;           // 4 column phases of 64 rows
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const bool rok = row0 + h * UH + row < m;
+#pragma unroll 4
+      for (int i = 0; i < PW / 4; ++i) {
+        const int c = c0 + 4 * i;
+        const T* cp = panel_col<T>(X, ldx, n, blkA, blkB, c);
+        const bool ok = cp != nullptr && rok;
+        cp_async_elem<T>(As + (size_t)h * PW * PA + c * PA + row, ok ? cp + row0 + h * UH + row : X, ok);
+      }
+      cp_async_commit();                                      // group 0: V + half 0, group 1: half 1
     }
   }
-  __syncthreads();
-  const int wm0 = (warp & 3) * 32, wn0 = (warp >> 2) * 32;
-  Acc<T> acc[4][4];
+  const int wm0 = (warp & 1) * 32, wn0 = (warp >> 1) * 16;    // 2 x 4 warps over the 64 x 64 half tile
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j].zero();
-#pragma unroll 4
-  for (int kk = 0; kk < PW; kk += 4) {
-    T af[4], bf[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) af[i] = As[(kk + t4) * PA + wm0 + 8 * i + g8];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) bf[j] = Bs[(kk + t4) * PB + wn0 + 8 * j + g8];
+  for (int h = 0; h < 2; ++h) {
+    if (h == 0) cp_async_wait<1>(); else cp_async_wait<0>();
+    __syncthreads();
+    const T* as = As + (size_t)h * PW * PA;
+    Acc<T> acc[4][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j].mma(af[i], bf[j]);
-  }
+      for (int j = 0; j < 2; ++j) acc[i][j].zero();
+#pragma unroll 4
+    for (int kk = 0; kk < PW; kk += 4) {
+      T af[4], bf[2];
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
+      for (int i = 0; i < 4; ++i) af[i] = as[(kk + t4) * PA + wm0 + 8 * i + g8];
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int col = wn0 + 8 * j + 2 * t4 + e;
-      T* cp = panel_col<T>(X, ldx, n, blkA, blkB, col);
-      if (cp == nullptr) continue;
+      for (int j = 0; j < 2; ++j) bf[j] = Bs[(kk + t4) * PB + wn0 + 8 * j + g8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int row = row0 + wm0 + 8 * i + g8;
-        if (row < m) cp[row] = acc[i][j].get(e);
-      }
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) acc[i][j].mma(af[i], bf[j]);
     }
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int col = wn0 + 8 * j + 2 * t4 + e;
+        T* cp = panel_col<T>(X, ldx, n, blkA, blkB, col);
+        if (cp == nullptr) continue;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = row0 + h * UH + wm0 + 8 * i + g8;
+          if (row < m) cp[row] = acc[i][j].get(e);
+        }
+      }
+  }
 }
 
 }  // namespace
@@ -310,17 +323,21 @@ int jacobi_gram(T* X, int m, int n, int64_t ldx, double tol, const double* frob2
   const int off_diag = (int)hA.size();
   for (int i = 0; i < nblk; ++i) { hA.push_back(i); hB.push_back(-1); }
   const int maxpairs = std::max(ne / 2, nblk);
-  // Two pair groups per step on two streams: while the (few, latency-bound) inner eigen-sweep CTAs of one group run, the
-  // DMMA Gram / update tiles of the other group fill the remaining SMs.  Each group has its own Gram / V / skip buffers
+  // Several pair groups per step on separate streams: while the (few, latency-bound) inner eigen-sweep CTAs of one group
+  // run, the DMMA Gram / update tiles of the others fill the remaining SMs.  Each group has its own Gram / V / skip buffers
   // and its own split of the rows sized for ~2 CTAs per SM.
-  static cudaStream_t s2 = nullptr;
-  static cudaEvent_t ev_main = nullptr, ev_s2 = nullptr;
-  if (s2 == nullptr) {
-    TTN_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
-    TTN_CUDA(cudaEventCreateWithFlags(&ev_main, cudaEventDisableTiming));
-    TTN_CUDA(cudaEventCreateWithFlags(&ev_s2, cudaEventDisableTiming));
+  constexpr int NGMAX = 4;
+  static cudaStream_t strm[NGMAX] = {nullptr, nullptr, nullptr, nullptr};   // strm[0] is the library stream
+  static cudaEvent_t ev_grp[NGMAX], ev_join = nullptr;
+  if (ev_join == nullptr) {
+    for (int g = 1; g < NGMAX; ++g) TTN_CUDA(cudaStreamCreateWithFlags(&strm[g], cudaStreamNonBlocking));
+    for (int g = 0; g < NGMAX; ++g) TTN_CUDA(cudaEventCreateWithFlags(&ev_grp[g], cudaEventDisableTiming));
+    TTN_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
   }
-  const int halfmax = (maxpairs + 1) / 2;
+  strm[0] = ctx().stream;
+  static const int ng_env = getenv("TTN_GRAM_GROUPS") ? atoi(getenv("TTN_GRAM_GROUPS")) : 0;
+  const int NG = std::max(1, std::min(NGMAX, ng_env > 0 ? ng_env : 2));
+  const int grpmax = (maxpairs + NG - 1) / NG;
   auto split_for = [&](int cnt, int& ns, int& mcs) {
     ns = std::max(1, std::min((2 * ctx().sm_count + cnt - 1) / std::max(cnt, 1), m / (2 * GK)));
     ns = std::min(ns, 16);
@@ -328,16 +345,19 @@ int jacobi_gram(T* X, int m, int n, int64_t ldx, double tol, const double* frob2
     mcs = (mcs + GK - 1) / GK * GK;
     ns = (m + mcs - 1) / mcs;
   };
-  const size_t gp_elems = (size_t)halfmax * 16 * PW * PW;          // <= 16 row splits
+  const size_t gp_elems = (size_t)grpmax * 16 * PW * PW;          // <= 16 row splits
   DevBuf gA(sizeof(int) * hA.size()), gB(sizeof(int) * hB.size());
-  DevBuf Gp0(sizeof(T) * gp_elems), Gp1(sizeof(T) * gp_elems);
-  DevBuf Vg0(sizeof(T) * (size_t)halfmax * PW * PW), Vg1(sizeof(T) * (size_t)halfmax * PW * PW);
-  DevBuf skip0(sizeof(int) * halfmax), skip1(sizeof(int) * halfmax), rot(sizeof(unsigned int));
+  DevBuf Gp[NGMAX], Vg[NGMAX], skip[NGMAX], rot(sizeof(unsigned int));
+  for (int g = 0; g < NG; ++g) {
+    Gp[g].alloc(sizeof(T) * gp_elems);
+    Vg[g].alloc(sizeof(T) * (size_t)grpmax * PW * PW);
+    skip[g].alloc(sizeof(int) * grpmax);
+  }
   TTN_CUDA(cudaMemcpyAsync(gA.p, hA.data(), sizeof(int) * hA.size(), cudaMemcpyHostToDevice, ctx().stream));
   TTN_CUDA(cudaMemcpyAsync(gB.p, hB.data(), sizeof(int) * hB.size(), cudaMemcpyHostToDevice, ctx().stream));
   TTN_CUDA(cudaStreamSynchronize(ctx().stream));   // host staging vectors must outlive the copies
   const size_t smem_g = sizeof(T) * 2 * PW * (GK + 4);
-  const size_t smem_u = sizeof(T) * ((size_t)PW * (UM + 4) + (size_t)PW * (PW + 4));
+  const size_t smem_u = sizeof(T) * ((size_t)2 * PW * (UM / 2 + 4) + (size_t)PW * (PW + 4));
   const size_t smem_e = sizeof(T) * 2 * PW * (PW + 1);
   static bool attr_done = false;
   if (!attr_done) {
@@ -347,40 +367,47 @@ int jacobi_gram(T* X, int m, int n, int64_t ldx, double tol, const double* frob2
     attr_done = true;
   }
   int sweeps = 0;
-  auto group = [&](cudaStream_t st, const int* pa, const int* pb, int cnt, int cross, T* Gp, T* Vg, int* skip) {
+  auto group = [&](int g, const int* pa, const int* pb, int cnt, int cross) {
     if (cnt <= 0) return;
+    cudaStream_t st = strm[g];
     int ns, mcs;
     split_for(cnt, ns, mcs);
-    gram_pairs_kernel<T><<<dim3(cnt, ns), GT, smem_g, st>>>(X, m, n, ldx, pa, pb, mcs, Gp);
+    gram_pairs_kernel<T><<<dim3(cnt, ns), GT, smem_g, st>>>(X, m, n, ldx, pa, pb, mcs, Gp[g].as<T>());
     TTN_CHECK_LAUNCH();
-    gram_eig_kernel<T, GE><<<cnt, GE, smem_e, st>>>(Gp, ns, cross, tol, frob2, fk, Vg, skip, rot.as<unsigned int>());
+    gram_eig_kernel<T, GE><<<cnt, GE, smem_e, st>>>(Gp[g].as<T>(), ns, cross, tol, frob2, fk, Vg[g].as<T>(), skip[g].as<int>(),
+                                                   rot.as<unsigned int>());
     TTN_CHECK_LAUNCH();
-    update_pairs_kernel<T><<<dim3(cnt, (m + UM - 1) / UM), GT, smem_u, st>>>(X, m, n, ldx, pa, pb, Vg, skip);
+    update_pairs_kernel<T><<<dim3(cnt, (m + UM - 1) / UM), GT, smem_u, st>>>(X, m, n, ldx, pa, pb, Vg[g].as<T>(), skip[g].as<int>());
     TTN_CHECK_LAUNCH();
     ctx().launches += 3;
   };
-  // one tournament step: group 0 on the library stream, group 1 on s2; each waits for the other group's previous step
-  auto step = [&](const int* pa, const int* pb, int cnt, int cross) {
-    const int c0 = (cnt + 1) / 2, c1 = cnt - c0;
-    TTN_CUDA(cudaStreamWaitEvent(ctx().stream, ev_s2, 0));
-    TTN_CUDA(cudaStreamWaitEvent(s2, ev_main, 0));
-    group(ctx().stream, pa, pb, c0, cross, Gp0.as<T>(), Vg0.as<T>(), skip0.as<int>());
-    group(s2, pa + c0, pb + c0, c1, cross, Gp1.as<T>(), Vg1.as<T>(), skip1.as<int>());
-    TTN_CUDA(cudaEventRecord(ev_main, ctx().stream));
-    TTN_CUDA(cudaEventRecord(ev_s2, s2));
+  // join: the library stream waits for every group, then every group stream waits for the library stream
+  auto join = [&]() {
+    for (int g = 1; g < NG; ++g) {
+      TTN_CUDA(cudaEventRecord(ev_grp[g], strm[g]));
+      TTN_CUDA(cudaStreamWaitEvent(strm[0], ev_grp[g], 0));
+    }
+    TTN_CUDA(cudaEventRecord(ev_join, strm[0]));
+    for (int g = 1; g < NG; ++g) TTN_CUDA(cudaStreamWaitEvent(strm[g], ev_join, 0));
   };
-  ProfScope prof_scope_(KF_JACOBI);                  // (per-kernel families are not separable across two streams)
-  TTN_CUDA(cudaEventRecord(ev_main, ctx().stream));  // s2 starts after everything queued so far (X is ready)
-  TTN_CUDA(cudaEventRecord(ev_s2, s2));
+  // one tournament step: the pairs are dealt to the groups in contiguous chunks, all groups run concurrently
+  auto step = [&](const int* pa, const int* pb, int cnt, int cross) {
+    const int per = (cnt + NG - 1) / NG;
+    for (int g = 0; g < NG; ++g) {
+      const int lo = g * per, c = std::min(per, cnt - lo);
+      group(g, pa + lo, pb + lo, c, cross);
+    }
+    join();
+  };
+  ProfScope prof_scope_(KF_JACOBI);                  // (per-kernel families are not separable across the streams)
   for (int sw = 0; sw < max_sweeps; ++sw) {
     TTN_CUDA(cudaMemsetAsync(rot.p, 0, sizeof(unsigned int), ctx().stream));
-    TTN_CUDA(cudaEventRecord(ev_main, ctx().stream));
+    join();                                           // group streams start after everything queued so far
     step(gA.as<int>() + off_diag, gB.as<int>() + off_diag, nblk, 0);          // pairs inside each block
     for (int st = 0; st < ne - 1; ++st) {                                      // cross pairs of the block tournament
       const int cnt = off[st + 1] - off[st];
       if (cnt > 0) step(gA.as<int>() + off[st], gB.as<int>() + off[st], cnt, 1);
     }
-    TTN_CUDA(cudaStreamWaitEvent(ctx().stream, ev_s2, 0));
     unsigned int rotated = 0;
     TTN_CUDA(cudaMemcpyAsync(&rotated, rot.p, sizeof(rotated), cudaMemcpyDeviceToHost, ctx().stream));
     TTN_CUDA(cudaStreamSynchronize(ctx().stream));
