@@ -176,7 +176,30 @@ __global__ void __launch_bounds__(ET) gram_eig_kernel(const T* __restrict__ Gp, 
       __syncthreads();
       const int stepped = s_step[gs & 1];
       if (tid == 0) { s_step[(gs + 1) & 1] = 0; if (stepped) s_any = 1; }   // the other slot is idle during this phase
-      if (stepped) {
+      if (stepped && cross_only && ET == GB * GB) {
+        // cross ordering: pair i is (i, 32 + (i + r) mod 32), so the column indices need no shared-memory reads; one
+        // 2 x 2 block of G and two rows of V per thread (the kernel is bound by shared-memory instruction issue)
+        const int k = tid >> 5, l = tid & (GB - 1);
+        const int pk = k, qk = GB + ((k + r) & (GB - 1)), pl = l, ql = GB + ((l + r) & (GB - 1));
+        const double ck = s_cs[k], cl = s_cs[l];
+        const T sk = s_sn[k], sl = s_sn[l];
+        const T b00 = G[pk * P + pl], b01 = G[pk * P + ql], b10 = G[qk * P + pl], b11 = G[qk * P + ql];
+        const T slc = t_conj(sl), skc = t_conj(sk);
+        const T t00 = t_sub(t_scale(b00, cl), t_mul(b01, slc)), t01 = t_add(t_mul(b00, sl), t_scale(b01, cl));
+        const T t10 = t_sub(t_scale(b10, cl), t_mul(b11, slc)), t11 = t_add(t_mul(b10, sl), t_scale(b11, cl));
+        G[pk * P + pl] = t_sub(t_scale(t00, ck), t_mul(sk, t10));
+        G[pk * P + ql] = t_sub(t_scale(t01, ck), t_mul(sk, t11));
+        G[qk * P + pl] = t_add(t_mul(skc, t00), t_scale(t10, ck));
+        G[qk * P + ql] = t_add(t_mul(skc, t01), t_scale(t11, ck));
+        // V <- V J: rows i = k and i = k + 32 of column pair l (same l: its rotation is already in registers)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int i = k + h * GB;
+          const T vp = V[i * P + pl], vq = V[i * P + ql];
+          V[i * P + pl] = t_sub(t_scale(vp, cl), t_mul(vq, slc));
+          V[i * P + ql] = t_add(t_mul(vp, sl), t_scale(vq, cl));
+        }
+      } else if (stepped) {
         // G <- J^H G J on the 32 x 32 grid of 2 x 2 blocks (rows of pair k, columns of pair l); J = [[cs, s], [-conj(s), cs]]
 #pragma unroll
         for (int it = 0; it < (GB * GB) / ET; ++it) {
