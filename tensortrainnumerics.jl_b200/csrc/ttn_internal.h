@@ -58,7 +58,7 @@ struct Context {
   bool use_cholqr = true;           // CholeskyQR2 fast path for tall-skinny QR (TTN_NO_CHOLQR=1 disables)
   bool jacobi_noise_floor = false;  // see JAC_FLOOR2 in jacobi.cu
   bool use_cluster_jacobi = true;   // single-matrix SVDs on an 8-SM cluster (TTN_NO_CLUSTER_JACOBI=1 disables; A/B timing)
-  int gram_jacobi_min = 1024;       // Gram-block Jacobi (DMMA, two streams) for matrices with min(m, n) >= this;
+  int gram_jacobi_min = 640;        // Gram-block Jacobi (DMMA, two streams) for matrices with min(m, n) >= this (measured crossover);
                                     // TTN_GRAM_JACOBI=1: from 128 columns up, TTN_GRAM_JACOBI=0: never
 };
 Context& ctx();
