@@ -222,7 +222,7 @@ def test_svdtrunc_across_condition_numbers(shape, cond):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape", [(1024, 1024), (1100, 1030)])
+@pytest.mark.parametrize("shape", [(1024, 1024), (1100, 1030), (700, 660)])
 def test_svdtrunc_large_gram_block_path(shape):
     """Bond matrices of DMRG size take the Gram-block Jacobi on the DMMA pipe (jacobi_gram.cu, two pair groups on two
     streams) after the Householder preconditioning: singular values and reconstruction against LAPACK."""
