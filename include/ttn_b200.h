@@ -104,6 +104,21 @@ int ttn_compress(ttn_ttv x, int64_t max_bond, double truncerr, int sweeps, doubl
  * orthogonalize(x; i = k) as the reference does.                src/tt_tools.jl:743-770 */
 int ttn_bond_truncate(ttn_ttv x, int k, int64_t max_bond, double truncerr, ttn_ttv* y);
 
+/* ---- site surgery: the other users of the two-site truncated split (single trains, in place) ----------
+ * `mode` selects the rank rule of the caller: 0 = keep sigma_j > tol * sigma_1 (all if tol <= 0), the rule of
+ * `_swap_adjacent_sites` / `to_qtt` (src/qtt_tools.jl:680-685, 286-289); 1 = the `_svdtrunc` tail-norm rule with
+ * the `max_bond` cap (src/tt_cross_interpolation.jl:149-166) used by `_ttm_swap!`.  Split: U | S*Vt. */
+/* _swap_adjacent_sites(cores[k], cores[k+1]; threshold)   src/qtt_tools.jl:660-694  (driver `reorder`, :731-774)
+ * _ttm_swap!(cores, rks, k; tol, rmax)                     src/tt_operations.jl:366-383
+ * Contracts sites k, k+1 (1-based), exchanges their physical indices and re-factorises. */
+int ttn_swap_sites(ttn_ttv x, int k, int mode, int64_t max_bond, double tol);
+/* _ttm_contract!(cores, rks, k): core_k[s] <- core_k[s] * core_{k+1}[s], site k+1 removed (equal physical dims).
+ *                                                          src/tt_operations.jl:385-397 */
+int ttn_merge_sites_diag(ttn_ttv x, int k);
+/* one split of `to_qtt`: site k with n_k = coarse * fine becomes sites (coarse, fine), s = fine_idx + coarse_idx * fine.
+ *                                                          src/qtt_tools.jl:270-298 */
+int ttn_split_site(ttn_ttv x, int k, int64_t coarse, int mode, int64_t max_bond, double tol);
+
 /* ---- alternating solvers ----------------------------------------------------------------------------- */
 typedef struct {
   int N;                       /* window size for dmrg_* (1 or 2); ignored by als/mals */

@@ -24,10 +24,12 @@ from .generators import (toeplitz_to_qtto, laplace_dd, id_tto, heisenberg_xyz_tt
                          qtt_to_vector, tto_add, tto_scale, laplace2d_interleaved, qtt_sin2d_interleaved,
                          shift_op)
 from .ops import (apply, add, scale, sub, dot, norm, orthogonalize, svdtrunc, svdtrunc_abs,
-                  tt_bond_truncate, tt_compress, euclidean_distance, rel_distance, norm_stable)
+                  tt_bond_truncate, tt_compress, euclidean_distance, rel_distance, norm_stable, hadamard)
 from .als import als_linsolve, als_eigsolve
 from .mals import mals_linsolve, mals_eigsolve, sv_trunc
 from .dmrg import dmrg_linsolve, dmrg_eigsolve, cut_off_index, dmrg_matvec2, dmrg_matvec2_blas, dmrg_update_G, dmrg_update_H, amid
 from .tdvp import tdvp, tdvp2, apply_H1_lsr, apply_H0, apply_H2_lsr, update_left_env, update_right_env
 from .krylov_tt import krylov_linsolve
 from .steppers import euler_method, implicit_euler_method, crank_nicholson_method, rk4_method
+from .sites import (swap_adjacent_sites, bubble_sort_swaps, reorder_perm, reorder, ttm_swap, ttm_contract, hadamard_ttm,
+                    to_qtt)

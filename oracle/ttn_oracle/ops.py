@@ -209,3 +209,16 @@ def tt_compress(psi: TTvector, max_bond: int, truncerr: float = 0.0, sweeps: int
         for k in range(psi.N - 1, 0, -1):
             tt_bond_truncate(psi, k, max_bond=max_bond, truncerr=truncerr, faithful=faithful, sigma_out=sigma_out)
     return psi
+
+
+def hadamard(x: TTvector, y: TTvector) -> TTvector:
+    """src/tt_operations.jl:343-360: core_k[s] = kron(x_k[s], y_k[s])."""
+    assert x.ttv_dims == y.ttv_dims, "Incompatible TT dimensions"
+    vec, rks = [], [x.ttv_rks[k] * y.ttv_rks[k] for k in range(x.N + 1)]
+    for k in range(x.N):
+        cx, cy = x.ttv_vec[k], y.ttv_vec[k]
+        core = np.zeros((cx.shape[0], cx.shape[1] * cy.shape[1], cx.shape[2] * cy.shape[2]), dtype=np.result_type(cx.dtype, cy.dtype))
+        for s_ in range(cx.shape[0]):
+            core[s_] = np.kron(cx[s_], cy[s_])
+        vec.append(core)
+    return TTvector(x.N, vec, x.ttv_dims, rks, [0] * x.N)

@@ -73,6 +73,9 @@ def load():
         "ttn_scale": [vp, C.c_double, C.c_double, vpp], "ttn_orthogonalize": [vp, C.c_int, vpp],
         "ttn_compress": [vp, C.c_int64, C.c_double, C.c_int, dp, C.c_int64],
         "ttn_bond_truncate": [vp, C.c_int, C.c_int64, C.c_double, vpp],
+        "ttn_swap_sites": [vp, C.c_int, C.c_int, C.c_int64, C.c_double],
+        "ttn_merge_sites_diag": [vp, C.c_int],
+        "ttn_split_site": [vp, C.c_int, C.c_int64, C.c_int, C.c_int64, C.c_double],
         "ttn_solver_params_default": [C.POINTER(SolverParams)], "ttn_tdvp_params_default": [C.POINTER(TdvpParams)],
         "ttn_als_linsolve": [vp, vp, vp, C.POINTER(SolverParams), vpp, dp],
         "ttn_als_eigsolve": [vp, vp, C.POINTER(SolverParams), vpp, dp, C.c_int, ip],

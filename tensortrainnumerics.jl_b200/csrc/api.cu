@@ -370,6 +370,32 @@ int ttn_bond_truncate(ttn_ttv x, int k, int64_t max_bond, double truncerr, ttn_t
   API_END
 }
 
+int ttn_swap_sites(ttn_ttv x, int k, int mode, int64_t max_bond, double tol) {
+  API_BEGIN
+  need_init();
+  ttn_assert(x != nullptr, TTN_EARG, "null handle");
+  ttn_assert(mode == 0 || mode == 1, TTN_EARG, "mode must be 0 (relative threshold) or 1 (tail norm)");
+  if (x->dtype == TTN_F64) tt_swap_sites(x->r, k, mode, max_bond, tol);
+  else tt_swap_sites(x->c, k, mode, max_bond, tol);
+  API_END
+}
+int ttn_merge_sites_diag(ttn_ttv x, int k) {
+  API_BEGIN
+  need_init();
+  ttn_assert(x != nullptr, TTN_EARG, "null handle");
+  if (x->dtype == TTN_F64) tt_merge_diag(x->r, k); else tt_merge_diag(x->c, k);
+  API_END
+}
+int ttn_split_site(ttn_ttv x, int k, int64_t coarse, int mode, int64_t max_bond, double tol) {
+  API_BEGIN
+  need_init();
+  ttn_assert(x != nullptr, TTN_EARG, "null handle");
+  ttn_assert(mode == 0 || mode == 1, TTN_EARG, "mode must be 0 (relative threshold) or 1 (tail norm)");
+  if (x->dtype == TTN_F64) tt_split_site(x->r, k, coarse, mode, max_bond, tol);
+  else tt_split_site(x->c, k, coarse, mode, max_bond, tol);
+  API_END
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // solvers
 // ---------------------------------------------------------------------------------------------------------

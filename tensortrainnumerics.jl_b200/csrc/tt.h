@@ -40,6 +40,12 @@ void tt_bond_truncate(TT<T>& x, int k /*1-based*/, int64_t max_bond, double trun
 template <class T>
 void tt_compress(TT<T>& x, int64_t max_bond, double truncerr, int sweeps, double* sigma_out, int64_t sigma_stride);
 
+// site surgery (sites.cu): adjacent-site swap, diagonal merge, site split.  mode 0: relative threshold `tol` on sigma_j/sigma_1
+// (qtt_tools.jl:680-685);  mode 1: `_svdtrunc` tail-norm rule with `max_bond` cap (tt_cross_interpolation.jl:149-166)
+template <class T> void tt_swap_sites(TT<T>& x, int k /*1-based*/, int mode, int64_t max_bond, double tol);
+template <class T> void tt_merge_diag(TT<T>& x, int k /*1-based*/);
+template <class T> void tt_split_site(TT<T>& x, int k /*1-based*/, int64_t coarse, int mode, int64_t max_bond, double tol);
+
 // Truncated split of a strided p x q matrix Theta (batch 1):  Theta ~ U * (S Vt),  U (p x r) orthonormal columns
 // (column-major, ld p) and SVt = U^H Theta (r x q, column-major, ld r).  `rule(sigma, k)` returns the rank.
 template <class T, class Rule>

@@ -131,6 +131,51 @@ function tt_compress!(ψ::TTvector, max_bond::Int; truncerr::Real = 0.0, sweeps:
     return ψ
 end
 
+# ---- site surgery (the other two-site-SVD users) -----------------------------------------------------------------------
+const NO_CAP = Int64(1) << 62
+
+# hadamard_ttm(x, y; tol, rmax)                                   src/tt_operations.jl:399-422
+function hadamard_ttm(x::TTvector{T, N}, y::TTvector{T, N}; tol::Float64 = 1.0e-14, rmax::Int = typemax(Int)) where {T, N}
+    @assert x.ttv_dims == y.ttv_dims "Incompatible TT dimensions"
+    d = x.N
+    cores = vcat([copy(c) for c in x.ttv_vec], [permutedims(y.ttv_vec[d + 1 - k], (1, 3, 2)) for k in 1:d])
+    rks = vcat(collect(x.ttv_rks), reverse(collect(y.ttv_rks))[2:end])
+    dims = (x.ttv_dims..., reverse(y.ttv_dims)...)
+    z = upload(TTvector{T, 2d}(2d, cores, dims, rks, zeros(Int64, 2d)))
+    cap = rmax >= NO_CAP ? NO_CAP : Int64(rmax)
+    for iter in 1:d
+        for j in d:-1:(d - iter + 2)                              # _ttm_swap!, :366-383
+            check(ccall((:ttn_swap_sites, LIB[]), Cint, (Ptr{Cvoid}, Cint, Cint, Int64, Float64), z.h, j, 1, cap, tol))
+        end
+        check(ccall((:ttn_merge_sites_diag, LIB[]), Cint, (Ptr{Cvoid}, Cint), z.h, d - iter + 1))   # _ttm_contract!, :385-397
+    end
+    return download(z)
+end
+
+# the swap loop of reorder(q::QTTvector, new_ordering; threshold)  src/qtt_tools.jl:758-765
+function apply_swaps(x::TTvector, swaps::Vector{Int}; threshold::Real = 0.0)
+    xd = upload(x)
+    for k in swaps
+        check(ccall((:ttn_swap_sites, LIB[]), Cint, (Ptr{Cvoid}, Cint, Cint, Int64, Float64), xd.h, k, 0, NO_CAP, threshold))
+    end
+    return download(xd)
+end
+
+# to_qtt(tt, split_dims; threshold)                               src/qtt_tools.jl:254-310
+function to_qtt(tt::TTvector, split_dims::Vector{Vector{Int}}; threshold::Float64 = 0.0)
+    @assert length(split_dims) == tt.N "split_dims must have one entry per TT core"
+    xd = upload(tt)
+    site = 1
+    for sd in split_dims
+        for s in sd[1:(end - 1)]
+            check(ccall((:ttn_split_site, LIB[]), Cint, (Ptr{Cvoid}, Cint, Int64, Cint, Int64, Float64), xd.h, site, s, 0, NO_CAP, threshold))
+            site += 1
+        end
+        site += 1
+    end
+    return download(xd)
+end
+
 # ---- solvers ---------------------------------------------------------------------------------------------------
 # mirrors `ttn_solver_params` (include/ttn_b200.h)
 struct SolverParams

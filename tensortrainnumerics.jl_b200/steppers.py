@@ -159,3 +159,4 @@ def rk4_method(A, u0, steps, max_bond, normalize=True, return_error=False):
         res = rnd(_a.sub(_a.sub(u, _a.sub(u, incr)), incr))
         return _a._ret(u, host), _a.norm(res) / max(_a.norm(u), np.finfo(float).eps)
     return _a._ret(u, host)
+

@@ -1,0 +1,137 @@
+"""Parity of the site-surgery entry points (`ttn_swap_sites`, `ttn_merge_sites_diag`, `ttn_split_site`; SURVEY.md section
+8(f)-4) against the oracle: represented tensors to 1e-10 (the tolerance of the path), ranks and singular-value rules equal."""
+import numpy as np
+import pytest
+
+import ttn_oracle as o
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def _rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_swap_adjacent_sites_vs_oracle(cplx):
+    import ttn_b200 as t
+    rng = np.random.default_rng(31)
+    x = o.rand_tt((2, 3, 2, 4, 2), 5, rng=rng, dtype=np.complex128 if cplx else np.float64)
+    full = o.ttv_to_tensor(x)
+    y = o.copy_tt(x)
+    t.swap_adjacent_sites_(y, 2)
+    assert tuple(y.ttv_dims) == (2, 2, 3, 4, 2)
+    A, B = o.swap_adjacent_sites(x.ttv_vec[1], x.ttv_vec[2])
+    assert y.ttv_rks[2] == A.shape[2]
+    assert _rel(o.ttv_to_tensor(y), np.transpose(full, (0, 2, 1, 3, 4))) < TOL
+    # U | S Vt split: the left core is an isometry (qtt_tools.jl:687-692)
+    L = y.ttv_vec[1].reshape(-1, y.ttv_rks[2], order="F")
+    assert np.allclose(L.conj().T @ L, np.eye(L.shape[1]), atol=1e-12)
+
+
+def test_swap_threshold_rule_matches_oracle():
+    import ttn_b200 as t
+    rng = np.random.default_rng(32)
+    # a train whose swapped bond has a decaying spectrum: sum of a dominant and a small component
+    a = o.rand_tt((2,) * 6, 2, rng=rng); b = o.scale(1e-6, o.rand_tt((2,) * 6, 3, rng=rng))
+    x = o.add(a, b)
+    for thr in (0.0, 1e-3, 1e-9):
+        y = o.copy_tt(x)
+        t.swap_adjacent_sites_(y, 3, threshold=thr)
+        A, B = o.swap_adjacent_sites(x.ttv_vec[2], x.ttv_vec[3], threshold=thr)
+        if thr > 0:
+            assert y.ttv_rks[3] == A.shape[2]
+        ref = o.TTvector(6, x.ttv_vec[:2] + [A, B] + x.ttv_vec[4:], x.ttv_dims, x.ttv_rks[:3] + [A.shape[2]] + x.ttv_rks[4:], [0] * 6)
+        assert _rel(o.ttv_to_tensor(y), o.ttv_to_tensor(ref)) < (TOL if thr == 0 else 1e-8)
+
+
+@pytest.mark.parametrize("n_dims,bits", [(2, 4), (3, 3)])
+def test_reorder_vs_oracle(n_dims, bits):
+    import ttn_b200 as t
+    rng = np.random.default_rng(33)
+    x = o.rand_tt((2,) * (n_dims * bits), 6, rng=rng)
+    y = t.reorder(x, n_dims, bits, "serial", "interleaved")
+    yo = o.reorder(x, n_dims, bits, "serial", "interleaved")
+    assert list(y.ttv_rks) == list(yo.ttv_rks)
+    assert _rel(o.ttv_to_tensor(y), o.ttv_to_tensor(yo)) < TOL
+    z = t.reorder(y, n_dims, bits, "interleaved", "serial")
+    assert _rel(o.ttv_to_tensor(z), o.ttv_to_tensor(x)) < TOL
+    same = t.reorder(x, n_dims, bits, "serial", "serial")
+    assert all(np.array_equal(a, b) for a, b in zip(same.ttv_vec, x.ttv_vec))
+
+
+def test_reorder_2d_function_known_answer():
+    """f(x, y) = sin(2 pi x) cos(2 pi y) on a 2^5 x 2^5 grid: serial QTT (x bits then y bits) -> interleaved, checked against
+    the interleaved generator (test/test_qtt_tools.jl reorder round trip)."""
+    import ttn_b200 as t
+    bits = 5
+    sx, cy = o.qtt_sin(bits, lam=1.0), o.qtt_cos(bits, lam=1.0)
+    cores = [c.copy() for c in sx.ttv_vec] + [c.copy() for c in cy.ttv_vec]
+    x = o.TTvector(2 * bits, cores, (2,) * (2 * bits), list(sx.ttv_rks) + list(cy.ttv_rks)[1:], [0] * (2 * bits))
+    y = t.reorder(x, 2, bits, "serial", "interleaved", threshold=1e-12)
+    full = o.ttv_to_tensor(x)
+    axes = [0] * (2 * bits)
+    for src, tgt in enumerate(o.reorder_perm(2, bits, "serial")):
+        axes[tgt] = src
+    assert _rel(o.ttv_to_tensor(y), np.transpose(full, axes)) < TOL
+    assert max(y.ttv_rks) <= 4                                           # rank-2 x rank-2 separable function
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_hadamard_ttm_vs_oracle(cplx):
+    import ttn_b200 as t
+    rng = np.random.default_rng(34)
+    dt = np.complex128 if cplx else np.float64
+    x = o.rand_tt((2, 3, 2, 2, 2, 2), 4, rng=rng, dtype=dt); y = o.rand_tt((2, 3, 2, 2, 2, 2), 3, rng=rng, dtype=dt)
+    ref = o.ttv_to_tensor(x) * o.ttv_to_tensor(y)
+    z = t.hadamard_ttm(x, y, tol=1e-12)
+    zo = o.hadamard_ttm(x, y, tol=1e-12)
+    assert tuple(z.ttv_dims) == tuple(x.ttv_dims) and list(z.ttv_rks) == list(zo.ttv_rks)
+    assert _rel(o.ttv_to_tensor(z), ref) < TOL
+    assert _rel(o.ttv_to_tensor(z), o.ttv_to_tensor(zo)) < TOL
+    zt = t.hadamard_ttm(x, y, tol=1e-3, rmax=5)
+    zto = o.hadamard_ttm(x, y, tol=1e-3, rmax=5)
+    assert list(zt.ttv_rks) == list(zto.ttv_rks)
+    assert _rel(o.ttv_to_tensor(zt), o.ttv_to_tensor(zto)) < 1e-8
+    with pytest.raises(AssertionError):
+        t.hadamard_ttm(x, o.rand_tt((2, 2, 2, 2, 2, 2), 2, rng=rng))
+
+
+def test_hadamard_ttm_qtt_functions():
+    """sin^2 + cos^2 = 1 on a 2^10 grid through the truncated element-wise product."""
+    import ttn_b200 as t
+    s, c = o.qtt_sin(10, lam=3.0), o.qtt_cos(10, lam=3.0)
+    one = t.add(t.hadamard_ttm(s, s, tol=1e-13), t.hadamard_ttm(c, c, tol=1e-13))
+    v = o.qtt_to_vector(one)
+    assert np.max(np.abs(v - 1.0)) < 1e-10
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_to_qtt_vs_oracle(cplx):
+    import ttn_b200 as t
+    rng = np.random.default_rng(35)
+    x = o.rand_tt((8, 4, 6, 16), 5, rng=rng, dtype=np.complex128 if cplx else np.float64)
+    split = [[2, 2, 2], [4], [3, 2], [2, 2, 2, 2]]
+    q = t.to_qtt(x, split)
+    qo = o.to_qtt(x, split)
+    assert tuple(q.ttv_dims) == tuple(qo.ttv_dims) and list(q.ttv_rks) == list(qo.ttv_rks)
+    assert _rel(o.ttv_to_tensor(q), o.ttv_to_tensor(x).reshape(q.ttv_dims)) < TOL
+    qt = t.to_qtt(x, split, threshold=1e-2)
+    qto = o.to_qtt(x, split, threshold=1e-2)
+    assert list(qt.ttv_rks) == list(qto.ttv_rks)
+    assert _rel(o.ttv_to_tensor(qt), o.ttv_to_tensor(qto)) < 1e-8
+    with pytest.raises(AssertionError):
+        t.to_qtt(x, [[2, 2, 2], [4], [3, 3], [16]])
+
+
+def test_site_calls_reject_bad_arguments():
+    import ttn_b200 as t
+    rng = np.random.default_rng(36)
+    xd = t.DeviceTT.upload(o.rand_tt((2, 3, 2), 2, rng=rng))
+    with pytest.raises(Exception):
+        t.swap_adjacent_sites_(xd, 3)                     # k must be in 1:(N-1)
+    with pytest.raises(Exception):
+        t._lib.check(t._lib.lib().ttn_merge_sites_diag(xd._h, 1))   # 2 != 3 physical dims
+    with pytest.raises(Exception):
+        t._lib.check(t._lib.lib().ttn_split_site(xd._h, 2, 2, 0, 1 << 62, 0.0))   # 2 does not divide 3

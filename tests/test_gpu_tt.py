@@ -277,3 +277,24 @@ def test_cuda_matches_golden():
     assert abs(E[-1] - float(g["heis_e0"])) < 1e-9 * abs(float(g["heis_e0"]))
     U, s, Vt = t.svdtrunc(np.asfortranarray(g["svd_A"]))
     assert np.abs(s[:10] - g["svd_s"]).max() < 1e-12 and np.abs(s[10:]).max() < 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cplx", [False, True])
+def test_hadamard_device_vs_oracle(cplx):
+    """`hadamard` (tt_operations.jl:343-360) through the apply kernel: same tensor as the oracle's kron form and as the
+    element-wise product of the dense tensors; followed by `tt_compress!` it stays within the truncation tolerance."""
+    import ttn_b200 as t
+    rng = np.random.default_rng(19)
+    x = o.rand_tt((2,) * 7, 3, rng=rng); y = o.rand_tt((2,) * 7, 4, rng=rng)
+    if cplx:
+        x = o.complex_tt(x); y = o.complex_tt(y)
+        y.ttv_vec[2] = y.ttv_vec[2] * (0.3 + 0.8j)
+    z = t.hadamard(x, y)
+    ref = o.ttv_to_tensor(x) * o.ttv_to_tensor(y)
+    got = o.ttv_to_tensor(z)
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-13
+    assert np.linalg.norm(got - o.ttv_to_tensor(o.hadamard(x, y))) / np.linalg.norm(ref) < 1e-13
+    assert list(z.ttv_rks) == [a * b for a, b in zip(x.ttv_rks, y.ttv_rks)]
+    zc = t.tt_compress_(z, 12)
+    assert np.linalg.norm(o.ttv_to_tensor(zc) - ref) / np.linalg.norm(ref) < 1e-10

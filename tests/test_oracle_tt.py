@@ -306,3 +306,12 @@ def test_oracle_reproduces_golden():
     U, S, Vt = o.svdtrunc(g["svd_A"])
     sv = np.diag(np.asarray(S)) if np.ndim(S) == 2 else np.asarray(S)
     assert np.abs(sv[:10] - g["svd_s"]).max() < 1e-14 and np.abs(sv[10:]).max() < 1e-14
+
+
+def test_hadamard_vs_dense():
+    # tt_operations.jl:343-360 (test_tt_operations.jl hadamard checks): element-wise product of the dense tensors
+    rng = np.random.default_rng(9)
+    x = o.rand_tt((2, 3, 2, 2), 3, rng=rng); y = o.rand_tt((2, 3, 2, 2), 2, rng=rng)
+    z = o.hadamard(x, y)
+    assert np.allclose(o.ttv_to_tensor(z), o.ttv_to_tensor(x) * o.ttv_to_tensor(y), rtol=1e-13, atol=1e-14)
+    assert z.ttv_rks == [a * b for a, b in zip(x.ttv_rks, y.ttv_rks)]
