@@ -226,3 +226,55 @@ def qtt_sin2d_interleaved(bits, lam=1.0) -> TTvector:
         vec.append(gy)
         rks.append(gy.shape[2])
     return TTvector(2 * d, vec, (2,) * (2 * d), rks, [0] * (2 * d))
+
+
+# ---- quantum-Fourier-transform MPO (src/tt_transformations.jl:1-77) and uniform-grid QTT sampling ---------------------
+def _cheb_lobatto(K):
+    """tt_transformations.jl:6-11: nodes on [0, 1] and barycentric weights."""
+    j = np.arange(K + 1)
+    c = 0.5 * (1.0 - np.cos(np.pi * j / K))
+    w = np.where((j == 0) | (j == K), 0.5, 1.0) * (-1.0) ** j
+    return c, w
+
+
+def _lagrange_eval(c, w, alpha, x):
+    """tt_transformations.jl:13-24."""
+    if abs(x - c[alpha]) <= 1.0e-14:
+        return 1.0
+    with np.errstate(divide="ignore"):           # x on another node: the denominator is Inf and the value 0, as in Julia
+        return (w[alpha] / (x - c[alpha])) / np.sum(w / (x - c))
+
+
+def fourier_qtto(d, sign=-1.0, K=25, normalize=True) -> TToperator:
+    """tt_transformations.jl:38-77: rank K+1 interpolative QFT operator (arXiv:2404.03182); output bits come out reversed."""
+    assert d >= 1
+    c, w = _cheb_lobatto(K)
+    r = K + 1
+    A = np.empty((2, 2, r, r), dtype=np.complex128)
+    for al in range(r):
+        for be in range(r):
+            for s in range(2):
+                lag = _lagrange_eval(c, w, al, 0.5 * (s + c[be]))
+                for t in range(2):
+                    A[s, t, al, be] = lag * np.exp(1j * np.pi * sign * (s + c[be]) * t)          # :27-34
+    AL = A.sum(axis=2, keepdims=True)                                                             # :48-55
+    AR = A[:, :, :, :1].copy()                                                                    # :57-60
+    cores = [AL.copy()] + [A.copy() for _ in range(d - 2)] + [AR]
+    if normalize:
+        cores[0] = cores[0] / np.sqrt(2.0 ** d)
+    return TToperator(d, cores, (2,) * d, [1] + [r] * (d - 1) + [1])
+
+
+def function_to_qtt_uniform(f, d) -> TTvector:
+    """src/qtt_tools.jl:73-82: samples f(n / 2^d); site 1 carries the LEAST significant bit (`digits` is little-endian)."""
+    from .core import ttv_decomp
+    N = 2 ** d
+    y = np.array([f(n / N) for n in range(N)])
+    return ttv_decomp(np.reshape(y, (2,) * d, order="F"))
+
+
+def matricize(q: TTvector, core: int) -> np.ndarray:
+    """src/tt_tools.jl:694-705: entries of the full tensor listed with site 1 as the MOST significant bit."""
+    from .core import ttv_to_tensor
+    assert core == q.N
+    return np.reshape(ttv_to_tensor(q), -1, order="C")

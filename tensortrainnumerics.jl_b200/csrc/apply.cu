@@ -23,15 +23,15 @@ __device__ __forceinline__ zc shfl_elem(zc v, unsigned src) {
 template <class T>
 __global__ void __launch_bounds__(256) apply_qtt_kernel(const T* __restrict__ A, const T* __restrict__ x, T* __restrict__ y,
                                                         int Rl, int Rr, int rl, int rr, int sh_a, int sh_nu, int64_t bx,
-                                                        int64_t by) {
+                                                        int64_t by, int staged) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* As = reinterpret_cast<T*>(smem_raw);          // [ (a,b) ][ j ][ i ]  re-packed so that one thread reads 4 consecutive values
-  const int nab = Rl * Rr;
-  for (int t = threadIdx.x; t < 4 * nab; t += blockDim.x) {
-    const int ab = t >> 2, j = (t >> 1) & 1, i = t & 1;
-    As[t] = A[i + 2 * j + 4 * ab];                   // A[i, j, a, b], i fastest
+  const T* As = A;                                 // [ (a,b) ][ j ][ i ]: one thread reads 4 consecutive values A[i, j, a, b]
+  if (staged) {
+    T* S = reinterpret_cast<T*>(smem_raw);
+    for (int t = threadIdx.x; t < 4 * Rl * Rr; t += blockDim.x) S[t] = A[t];
+    __syncthreads();
+    As = S;
   }
-  __syncthreads();
   const unsigned inner = (unsigned)Rl * rl * Rr;
   const unsigned stride = gridDim.x * blockDim.x;
   for (unsigned mu = blockIdx.y; mu < (unsigned)rr; mu += gridDim.y) {
@@ -66,12 +66,17 @@ __global__ void __launch_bounds__(256) apply_qtt_kernel(const T* __restrict__ A,
 // generic path: one thread per (a, nu, b) produces the n_out outputs; divisions for the index split
 template <class T>
 __global__ void __launch_bounds__(256) apply_kernel(const T* __restrict__ A, const T* __restrict__ x, T* __restrict__ y,
-                                                    int n_out, int n_in, int Rl, int Rr, int rl, int rr, int64_t bx, int64_t by) {
+                                                    int n_out, int n_in, int Rl, int Rr, int rl, int rr, int64_t bx, int64_t by,
+                                                    int staged) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* As = reinterpret_cast<T*>(smem_raw);
-  const int na = n_out * n_in * Rl * Rr;
-  for (int i = threadIdx.x; i < na; i += blockDim.x) As[i] = A[i];
-  __syncthreads();
+  const T* As = A;
+  if (staged) {
+    T* S = reinterpret_cast<T*>(smem_raw);
+    const int na = n_out * n_in * Rl * Rr;
+    for (int i = threadIdx.x; i < na; i += blockDim.x) S[i] = A[i];
+    __syncthreads();
+    As = S;
+  }
   const unsigned inner = (unsigned)Rl * rl * Rr;
   for (unsigned mu = blockIdx.y; mu < (unsigned)rr; mu += gridDim.y) {
     const T* xb = x + blockIdx.z * bx + (int64_t)n_in * rl * mu;
@@ -99,8 +104,11 @@ void apply_core(const T* A, const T* x, T* y, int n_out, int n_in, int Rl, int R
   if (inner <= 0 || n_out <= 0 || rr <= 0 || batch <= 0) return;
   ttn_assert(inner * n_out < (1LL << 31), 2, "apply: core too large for 32-bit sub-index arithmetic");
   ProfScope prof_scope_(KF_APPLY);
-  const size_t smem = sizeof(T) * (size_t)n_out * n_in * Rl * Rr;
-  ttn_assert(smem <= 48 * 1024, 2, "apply: MPO core does not fit in shared memory");
+  // the MPO core is staged in shared memory when it fits (up to 200 KB: e.g. the rank-51 ComplexF64 QFT operator of
+  // examples/dft.jl needs 166 KB); larger cores are read through L1 / L2 from global memory
+  size_t smem = sizeof(T) * (size_t)n_out * n_in * Rl * Rr;
+  const int staged = smem <= 200 * 1024;
+  if (!staged) smem = 0;
   const bool qtt = n_out == 2 && n_in == 2 && (Rl & (Rl - 1)) == 0 && (rl & (rl - 1)) == 0;
   int sh_a = 0, sh_nu = 0;
   while ((1 << sh_a) < Rl) ++sh_a;
@@ -113,12 +121,17 @@ void apply_core(const T* A, const T* x, T* y, int n_out, int n_in, int Rl, int R
     const int64_t want = (int64_t)ctx().sm_count * 16;
     const unsigned gy = (unsigned)std::max<int64_t>(1, std::min<int64_t>(rr, want / std::max<int64_t>(1, (int64_t)bxg * nb)));
     dim3 grid(bxg, gy, (unsigned)nb);
-    if (qtt)
+    if (qtt) {
+      if (smem > 48 * 1024)
+        TTN_CUDA(cudaFuncSetAttribute(apply_qtt_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       apply_qtt_kernel<T><<<grid, 256, smem, ctx().stream>>>(A, x + (int64_t)b0 * bx, y + (int64_t)b0 * by, Rl, Rr, rl, rr, sh_a,
-                                                             sh_nu, bx, by);
-    else
+                                                             sh_nu, bx, by, staged);
+    } else {
+      if (smem > 48 * 1024)
+        TTN_CUDA(cudaFuncSetAttribute(apply_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       apply_kernel<T><<<grid, 256, smem, ctx().stream>>>(A, x + (int64_t)b0 * bx, y + (int64_t)b0 * by, n_out, n_in, Rl, Rr, rl,
-                                                         rr, bx, by);
+                                                         rr, bx, by, staged);
+    }
     TTN_CHECK_LAUNCH();
     ctx().launches++;
   }

@@ -298,3 +298,70 @@ def test_hadamard_device_vs_oracle(cplx):
     assert list(z.ttv_rks) == [a * b for a, b in zip(x.ttv_rks, y.ttv_rks)]
     zc = t.tt_compress_(z, 12)
     assert np.linalg.norm(o.ttv_to_tensor(zc) - ref) / np.linalg.norm(ref) < 1e-10
+
+
+@pytest.mark.gpu
+def test_dft_example_on_device():
+    """examples/dft.jl:5-25 on the device: ComplexF64 `A*x` (MPO rank 51) + `tt_compress!(·, 100)`; the spectrum of a
+    12-mode signal comes back to 1e-8 and the rest of the spectrum is below 1e-10, as the example asserts; the train also
+    matches the oracle's to the tolerance of the path."""
+    import ttn_b200 as t
+    d, K, r = 10, 50, 12
+    rng = np.random.default_rng(1234)
+    coeffs = rng.standard_normal(r) + 1j * rng.standard_normal(r)
+    f = lambda x: np.sum(coeffs * np.exp(2j * np.pi * np.arange(r) * x))
+    F, x = o.fourier_qtto(d, K=K, sign=-1.0, normalize=True), o.function_to_qtt_uniform(f, d)
+    y = t.tt_compress_(t.apply(F, x), 100)
+    spec = o.matricize(y, d)
+    scale = np.sqrt(2.0 ** d)
+    assert np.linalg.norm(spec[:r] - scale * coeffs) / (scale * np.linalg.norm(coeffs)) < 1e-8
+    assert np.linalg.norm(spec[r:]) / np.linalg.norm(spec) < 1e-10
+    yo = o.tt_compress(o.apply(F, x), 100)
+    assert np.linalg.norm(spec - o.matricize(yo, d)) / np.linalg.norm(spec) < 1e-10
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ordering", ["serial", "interleaved"])
+def test_laplacian_2d_action_both_orderings(ordering):
+    """test/test_qtt_multidim.jl:658-692: (Δ⊗I + I⊗Δ)/h² applied to sin(πx)sin(πy) on an 8 x 8 grid in serial and interleaved
+    bit order against the dense Kronecker-sum matrix; the two orderings are tied together by `reorder`."""
+    import ttn_b200 as t
+    bits = 3
+    n = 2 ** bits
+    h = 1.0 / (n - 1)
+    M1 = o.tto_to_matrix(o.laplace_dd(bits)) / h ** 2
+    M2 = np.kron(M1, np.eye(n)) + np.kron(np.eye(n), M1)
+    sx = o.qtt_sin(bits, lam=1.0)
+    xs = o.qtt_to_vector(sx)
+    ref = (M2 @ np.kron(xs, xs)).reshape(n, n)                              # [x, y]
+    L, I = o.tto_scale(1.0 / h ** 2, o.laplace_dd(bits)), o.id_tto(bits)
+    cat = lambda a, b: o.TToperator(2 * bits, a.tto_vec + b.tto_vec, (2,) * (2 * bits), list(a.tto_rks) + list(b.tto_rks)[1:])
+    A_serial = o.tto_add(cat(L, I), cat(I, L))
+    v_serial = o.TTvector(2 * bits, [c.copy() for c in sx.ttv_vec] * 2, (2,) * (2 * bits), list(sx.ttv_rks) + list(sx.ttv_rks)[1:],
+                          [0] * (2 * bits))
+    if ordering == "serial":
+        Av = t.apply(A_serial, v_serial)
+        got = o.ttv_to_tensor(Av).reshape(n, n)                             # C-order: x bits then y bits, MSB first
+    else:
+        A_il = o.laplace2d_interleaved(bits)
+        v_il = t.reorder(v_serial, 2, bits, "serial", "interleaved")
+        assert np.allclose(o.ttv_to_tensor(v_il), o.ttv_to_tensor(o.qtt_sin2d_interleaved(bits)), atol=1e-12)
+        Av = t.reorder(t.apply(A_il, v_il), 2, bits, "interleaved", "serial", threshold=1e-14)
+        got = o.ttv_to_tensor(Av).reshape(n, n)
+    assert np.max(np.abs(got - ref)) < 1e-8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("R", [51, 64, 96])
+def test_apply_large_mpo_cores(R):
+    """`A*x` with MPO cores beyond the default 48 KB of shared memory: staged with the opt-in limit (R = 51: 166 KB, the QFT
+    operator of examples/dft.jl) or read from global memory (R = 64: 262 KB real would fit, ComplexF64 does not; R = 96)."""
+    import ttn_b200 as t
+    rng = np.random.default_rng(R)
+    cplx = lambda shp: (rng.standard_normal(shp) + 1j * rng.standard_normal(shp)) / np.sqrt(R)
+    A = o.TToperator(3, [cplx((2, 2, 1, R)), cplx((2, 2, R, R)), cplx((2, 2, R, 1))], (2, 2, 2), [1, R, R, 1])
+    x = o.rand_tt((2, 2, 2), 2, rng=rng, dtype=np.complex128)
+    y = t.apply(A, x)
+    ref = o.ttv_to_tensor(o.apply(A, x))
+    assert list(y.ttv_rks) == [1, 2 * R, 2 * R, 1]
+    assert np.linalg.norm(o.ttv_to_tensor(y) - ref) / np.linalg.norm(ref) < 1e-13

@@ -315,3 +315,30 @@ def test_hadamard_vs_dense():
     z = o.hadamard(x, y)
     assert np.allclose(o.ttv_to_tensor(z), o.ttv_to_tensor(x) * o.ttv_to_tensor(y), rtol=1e-13, atol=1e-14)
     assert z.ttv_rks == [a * b for a, b in zip(x.ttv_rks, y.ttv_rks)]
+
+
+def _dft_example():
+    """examples/dft.jl:5-17 with NumPy's RNG in place of Julia's."""
+    d, K, r = 10, 50, 12
+    rng = np.random.default_rng(1234)
+    coeffs = rng.standard_normal(r) + 1j * rng.standard_normal(r)
+    f = lambda x: np.sum(coeffs * np.exp(2j * np.pi * np.arange(r) * x))
+    return d, r, coeffs, o.fourier_qtto(d, K=K, sign=-1.0, normalize=True), o.function_to_qtt_uniform(f, d)
+
+
+def test_dft_example_known_answer():
+    # examples/dft.jl:17-25: QFT of a 12-mode signal through `A*x` + `tt_compress!`, spectrum read in bit-reversed order
+    d, r, coeffs, F, x = _dft_example()
+    y = o.tt_compress(o.apply(F, x), 100)
+    spec = o.matricize(y, d)
+    scale = np.sqrt(2.0 ** d)
+    assert np.linalg.norm(spec[:r] - scale * coeffs) / (scale * np.linalg.norm(coeffs)) < 1e-8
+    assert np.linalg.norm(spec[r:]) / np.linalg.norm(spec) < 1e-10
+    # the operator is the DFT matrix with reversed output bits
+    Fm = o.tto_to_matrix(o.fourier_qtto(4, K=25))
+    n = 16
+    rev = [int(format(i, "04b")[::-1], 2) for i in range(n)]
+    W = np.exp(-2j * np.pi * np.outer(np.arange(n), np.arange(n)) / n) / np.sqrt(n)
+    # tto_to_matrix is big-endian (site 1 = most significant bit): the input of the QFT operator is little-endian
+    # (function_to_qtt_uniform), its output big-endian (matricize), so the columns are the bit-reversed ones
+    assert np.allclose(Fm[:, rev], W, atol=1e-10)
