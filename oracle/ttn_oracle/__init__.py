@@ -22,7 +22,8 @@ from .core import (TTvector, TToperator, zeros_tt, zeros_tto, rand_tt, rand_tto,
                    increase_ranks)
 from .generators import (toeplitz_to_qtto, laplace_dd, id_tto, heisenberg_xyz_tto, qtt_sin, qtt_cos,
                          qtt_to_vector, tto_add, tto_scale, laplace2d_interleaved, qtt_sin2d_interleaved,
-                         shift_op, fourier_qtto, function_to_qtt_uniform, matricize)
+                         shift_op, fourier_qtto, function_to_qtt_uniform, matricize,
+                         qtt_exp)
 from .ops import (apply, add, scale, sub, dot, norm, orthogonalize, svdtrunc, svdtrunc_abs,
                   tt_bond_truncate, tt_compress, euclidean_distance, rel_distance, norm_stable, hadamard)
 from .als import als_linsolve, als_eigsolve

@@ -278,3 +278,19 @@ def matricize(q: TTvector, core: int) -> np.ndarray:
     from .core import ttv_to_tensor
     assert core == q.N
     return np.reshape(ttv_to_tensor(q), -1, order="C")
+
+
+def qtt_exp(d, a=0.0, b=1.0, alpha=1.0, beta=0.0) -> TTvector:
+    """src/qtt_tools.jl:160-176: exp(αx + β) on 2^d points of [a, b] (rank 1, coarsest bit first)."""
+    h = (b - a) / (2 ** d - 1)
+    vec = []
+    for k in range(1, d + 1):
+        c = np.zeros((2, 1, 1))
+        if k == 1:
+            c[0, 0, 0] = np.exp(alpha * a + beta)
+            c[1, 0, 0] = np.exp(alpha * (a + h * 2 ** (d - 1)) + beta)
+        else:
+            c[0, 0, 0] = 1.0
+            c[1, 0, 0] = np.exp(alpha * h * 2 ** (d - k))
+        vec.append(c)
+    return TTvector(d, vec, (2,) * d, [1] * (d + 1), [0] * d)

@@ -7,9 +7,11 @@
 // B200); here the O(m k^2) work is three DMMA GEMMs and the sequential part is a k x k Cholesky in one SM:
 //     G1 = A^H A,  R1 = chol(G1),  Q1 = A R1^-1,  G2 = Q1^H Q1,  R2 = chol(G2),  Q = Q1 R2^-1,  R = R2 R1.
 // The second pass restores orthogonality to O(eps) as long as eps*cond(A)^2 << 1.  The first Cholesky reports
-// min/max of diag(R1) (a lower bound of 1/cond(A)): below 1e-4 (or with a non-positive pivot) the caller falls back to
-// Householder, so ill-conditioned and rank-deficient inputs never take this path; above 0.3 (cond(A) of a few units) the
-// first pass alone is accurate to a few tens of eps and the second one is skipped.
+// min/max of diag(R1) (an upper bound of 1/cond(A)): below 1e-4 (or with a non-positive pivot) the caller falls back to
+// Householder; above 0.3 (cond(A) of a few units) the first pass alone is accurate to a few tens of eps and the second one
+// is skipped.  Because the diagonal only bounds the conditioning from one side, the second pass verifies itself: diag(R2)
+// must be 1 within 10 % (Q1 orthonormal to O(eps cond^2)), otherwise the factorisation is rejected as well, so
+// ill-conditioned and rank-deficient inputs never leave this path with a result.
 #include "ttn_internal.h"
 
 namespace ttn {
@@ -156,7 +158,10 @@ __global__ void __launch_bounds__(CQ_T) chol_inv_kernel(const T* __restrict__ Gp
       }
     }
   }
-  if (tid == 0 && status != nullptr) status[blockIdx.x] = s_bad ? -1.0 : s_dmin / s_dmax;
+  if (tid == 0 && status != nullptr) {
+    status[2 * blockIdx.x] = s_bad ? -1.0 : s_dmin / s_dmax;
+    status[2 * blockIdx.x + 1] = s_dmax;
+  }
 
   if (Xout == nullptr) return;
   // X = R^-1 by blocks of CQ_B.  Diagonal blocks first (one thread per column, back-substitution inside the block) ...
@@ -242,8 +247,91 @@ bool cholqr2_fits(int m, int k) {
 // A (m x k, lda, batch stride bA) = Q R.  R: k x k upper triangular (dense, ld k, zeros below), batch stride k*k.
 // Q (optional): m x k, ldq, batch stride bQ.  Returns false if any matrix of the batch is rejected (ill conditioned /
 // not positive definite): outputs are then undefined and the caller must use the Householder path.
+namespace {
+template <class T>
+bool cholqr2_impl(const T* A, int m, int k, int64_t lda, int64_t bA, T* R, T* Q, int64_t ldq, int64_t bQ, int batch, double* h_diag);
+}
+
+// Two column panels when the k x k Cholesky does not fit one SM's shared memory (ComplexF64 beyond k = 117, Float64 beyond
+// k = 165) but k/2 does: block classical Gram-Schmidt with re-orthogonalisation around CholeskyQR2 of each panel,
+//     [Q1, R11] = cholqr2(A1);  twice: { S = Q1^H P;  P -= Q1 S;  R12 += S }  (P starts as A2);  [Q2, R22] = cholqr2(P),
+// all GEMMs.  The panels are accepted or rejected by their own conditioning test; a rejection sends the caller to Householder.
+template <class T>
+bool cholqr2_two_panel(const T* A, int m, int k, int64_t lda, int64_t bA, T* R, T* Q, int64_t ldq, int64_t bQ, int batch) {
+  const int k1 = (k / 2 + CQ_B - 1) / CQ_B * CQ_B, k2 = k - k1;
+  if (k2 < 8 || m < 2 * k || !cholqr2_fits<T>(m, k1) || !cholqr2_fits<T>(m, k2)) return false;
+  DevBuf Qw;
+  if (Q == nullptr) {                                  // R-only call: the panels of Q are still needed as projectors
+    Qw.alloc(sizeof(T) * (size_t)m * k * batch);
+    Q = Qw.as<T>(); ldq = m; bQ = (int64_t)m * k;
+  }
+  const bool want_q = Qw.p == nullptr;
+  DevBuf R11(sizeof(T) * (size_t)k1 * k1 * batch), R22(sizeof(T) * (size_t)k2 * k2 * batch);
+  DevBuf R12(sizeof(T) * (size_t)k1 * k2 * batch), S2(sizeof(T) * (size_t)k1 * k2 * batch);
+  std::vector<double> d1(2 * (size_t)batch), d2(2 * (size_t)batch);     // (min, max) of diag(R1) of each panel's first pass
+  if (!cholqr2_impl<T>(A, m, k1, lda, bA, R11.as<T>(), Q, ldq, bQ, batch, d1.data())) return false;
+  T* P = Q + (int64_t)k1 * ldq;
+  {
+    Copy4 c; c.n0 = m; c.n1 = k2; c.n2 = batch; c.s0 = 1; c.s1 = lda; c.s2 = bA; c.d0 = 1; c.d1 = ldq; c.d2 = bQ;
+    copy4<T>(A + (int64_t)k1 * lda, P, c);
+  }
+  for (int pass = 0; pass < 2; ++pass) {
+    T* S = pass == 0 ? R12.as<T>() : S2.as<T>();
+    GemmArgs g;   // S = Q1^H P
+    g.M = k1; g.N = k2; g.K = m;
+    g.A = Q; g.sAm = ldq; g.sAk = 1; g.conjA = true; g.bA1 = bQ;
+    g.B = P; g.sBk = 1; g.sBn = ldq; g.bB1 = bQ;
+    g.C = S; g.sCm = 1; g.sCn = k1; g.bC1 = (int64_t)k1 * k2;
+    g.batch1 = batch;
+    gemm<T>(g);
+    GemmArgs u;   // P -= Q1 S
+    u.M = m; u.N = k2; u.K = k1;
+    u.A = Q; u.sAm = 1; u.sAk = ldq; u.bA1 = bQ;
+    u.B = S; u.sBk = 1; u.sBn = k1; u.bB1 = (int64_t)k1 * k2;
+    u.C = P; u.sCm = 1; u.sCn = ldq; u.bC1 = bQ;
+    u.alpha = -1.0; u.beta = 1.0;
+    u.batch1 = batch;
+    gemm<T>(u);
+  }
+  axpy<T>((int64_t)k1 * k2 * batch, t_one<T>(), S2.as<T>(), R12.as<T>());
+  DevBuf Q2;
+  if (want_q) Q2.alloc(sizeof(T) * (size_t)m * k2 * batch);
+  if (!cholqr2_impl<T>(P, m, k2, ldq, bQ, R22.as<T>(), want_q ? Q2.as<T>() : nullptr, m, (int64_t)m * k2, batch, d2.data()))
+    return false;
+  // the conditioning estimate of the whole matrix is the diagonal spread of the assembled R (each panel only saw its own)
+  for (int b = 0; b < batch; ++b) {
+    const double ratio = std::min(d1[2 * b], d2[2 * b]) / std::max(d1[2 * b + 1], d2[2 * b + 1]);
+    if (!(ratio >= 1e-4)) {
+      if (getenv("TTN_DEBUG_SVD")) fprintf(stderr, "[ttn] cholqr2 %d x %d (two panels): min/max diag(R) = %.3g -> rejected\n", m, k, ratio);
+      return false;
+    }
+  }
+  if (want_q) {
+    Copy4 c; c.n0 = m; c.n1 = k2; c.n2 = batch; c.s0 = 1; c.s1 = m; c.s2 = (int64_t)m * k2; c.d0 = 1; c.d1 = ldq; c.d2 = bQ;
+    copy4<T>(Q2.as<T>(), P, c);
+  }
+  // R = [R11 R12; 0 R22]
+  const int64_t kk = (int64_t)k * k;
+  fill<T>(R, kk * batch, t_zero<T>());
+  Copy4 a; a.n0 = k1; a.n1 = k1; a.n2 = batch; a.s0 = 1; a.s1 = k1; a.s2 = (int64_t)k1 * k1; a.d0 = 1; a.d1 = k; a.d2 = kk;
+  copy4<T>(R11.as<T>(), R, a);
+  Copy4 b; b.n0 = k1; b.n1 = k2; b.n2 = batch; b.s0 = 1; b.s1 = k1; b.s2 = (int64_t)k1 * k2; b.d0 = 1; b.d1 = k; b.d2 = kk;
+  copy4<T>(R12.as<T>(), R + (int64_t)k1 * k, b);
+  Copy4 c; c.n0 = k2; c.n1 = k2; c.n2 = batch; c.s0 = 1; c.s1 = k2; c.s2 = (int64_t)k2 * k2; c.d0 = 1; c.d1 = k; c.d2 = kk;
+  copy4<T>(R22.as<T>(), R + (int64_t)k1 * k + k1, c);
+  return true;
+}
+
 template <class T>
 bool cholqr2(const T* A, int m, int k, int64_t lda, int64_t bA, T* R, T* Q, int64_t ldq, int64_t bQ, int batch) {
+  if (batch <= 0) return false;
+  if (!cholqr2_fits<T>(m, k)) return cholqr2_two_panel<T>(A, m, k, lda, bA, R, Q, ldq, bQ, batch);
+  return cholqr2_impl<T>(A, m, k, lda, bA, R, Q, ldq, bQ, batch, nullptr);
+}
+
+namespace {
+template <class T>
+bool cholqr2_impl(const T* A, int m, int k, int64_t lda, int64_t bA, T* R, T* Q, int64_t ldq, int64_t bQ, int batch, double* h_diag) {
   if (!cholqr2_fits<T>(m, k) || batch <= 0) return false;
   int nsplit = 1;
   if (batch * ((k + 63) / 64) * ((k + 63) / 64) < ctx().sm_count)
@@ -256,7 +344,7 @@ bool cholqr2(const T* A, int m, int k, int64_t lda, int64_t bA, T* R, T* Q, int6
     attr_done = true;
   }
   const size_t kk = (size_t)k * k;
-  DevBuf Gp(sizeof(T) * kk * nsplit * batch), R1(sizeof(T) * kk * batch), X(sizeof(T) * kk * batch), st(sizeof(double) * batch);
+  DevBuf Gp(sizeof(T) * kk * nsplit * batch), R1(sizeof(T) * kk * batch), X(sizeof(T) * kk * batch), st(sizeof(double) * 2 * batch);
   gram_partials<T>(A, m, k, lda, bA, nsplit, Gp.as<T>(), batch);
   // first Cholesky.  The inverse is only computed when an explicit Q is wanted; an R-only call (SVD preconditioner) can stop
   // after this kernel if the matrix turns out to be well conditioned (below).
@@ -267,13 +355,15 @@ bool cholqr2(const T* A, int m, int k, int64_t lda, int64_t bA, T* R, T* Q, int6
     TTN_CHECK_LAUNCH();
     ctx().launches++;
   }
-  std::vector<double> h(batch);
-  TTN_CUDA(cudaMemcpyAsync(h.data(), st.p, sizeof(double) * batch, cudaMemcpyDeviceToHost, ctx().stream));
+  std::vector<double> h(2 * (size_t)batch);
+  TTN_CUDA(cudaMemcpyAsync(h.data(), st.p, sizeof(double) * 2 * batch, cudaMemcpyDeviceToHost, ctx().stream));
   TTN_CUDA(cudaStreamSynchronize(ctx().stream));
   double worst = 1.0;
-  for (double v : h) {
+  for (int b = 0; b < batch; ++b) {
+    const double v = h[2 * b];
     if (!(v >= 1e-4)) return false;                 // ill conditioned / not positive definite: Householder path
     worst = std::min(worst, v);
+    if (h_diag) { h_diag[2 * b] = v * h[2 * b + 1]; h_diag[2 * b + 1] = h[2 * b + 1]; }
   }
   // One pass is enough when cond(A) is small: the loss of CholeskyQR is eps*cond^2 (relative, in R and in Q^H Q - I);
   // min/max diag(R1) >= 0.3 means cond(A) of a few units (cfg2's bonds: 0.39 ... 0.78), i.e. a few tens of eps — the level of
@@ -313,9 +403,21 @@ bool cholqr2(const T* A, int m, int k, int64_t lda, int64_t bA, T* R, T* Q, int6
   gram_partials<T>(Q1.as<T>(), m, k, m, (int64_t)m * k, nsplit, Gp.as<T>(), batch);
   {
     ProfScope prof_scope_(KF_QR_PANEL);
-    chol_inv_kernel<T><<<batch, CQ_T, smem, ctx().stream>>>(Gp.as<T>(), nsplit, k, nullptr, R2.as<T>(), Q ? X.as<T>() : nullptr, nullptr);
+    chol_inv_kernel<T><<<batch, CQ_T, smem, ctx().stream>>>(Gp.as<T>(), nsplit, k, nullptr, R2.as<T>(), Q ? X.as<T>() : nullptr,
+                                                           st.as<double>());
     TTN_CHECK_LAUNCH();
     ctx().launches++;
+  }
+  // min/max diag(R1) only bounds cond(A) from below.  The second Gram matrix is the direct evidence: Q1^H Q1 = I + O(eps cond^2),
+  // so diag(R2) must sit at 1; a spread means the first pass lost orthogonality (cond(A) >~ 1e7) and the result is rejected.
+  TTN_CUDA(cudaMemcpyAsync(h.data(), st.p, sizeof(double) * 2 * batch, cudaMemcpyDeviceToHost, ctx().stream));
+  TTN_CUDA(cudaStreamSynchronize(ctx().stream));
+  for (int b = 0; b < batch; ++b) {
+    const double v = h[2 * b];
+    if (!(v >= 0.9)) {
+      if (getenv("TTN_DEBUG_SVD")) fprintf(stderr, "[ttn] cholqr2 %d x %d: second pass min/max diag(R2) = %.3g -> rejected\n", m, k, v);
+      return false;
+    }
   }
   {
     GemmArgs g;   // R = R2 R1
@@ -337,6 +439,7 @@ bool cholqr2(const T* A, int m, int k, int64_t lda, int64_t bA, T* R, T* Q, int6
   }
   return true;
 }
+}  // namespace
 
 template bool cholqr2_fits<double>(int, int);
 template bool cholqr2_fits<zc>(int, int);

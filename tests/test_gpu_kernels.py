@@ -238,3 +238,24 @@ def test_svdtrunc_large_gram_block_path(shape):
     assert np.abs(sg - s).max() < 1e-11
     assert relerr((Ug * sg) @ Vtg, A) < 1e-11
     assert np.abs(Ug.T @ Ug - np.eye(k)).max() < 1e-10
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cond", [3.0, 1e3, 1e9])
+@pytest.mark.parametrize("shape,cplx", [((1024, 128), True), ((128, 1024), True), ((1024, 256), False), ((256, 1024), False)])
+def test_svdtrunc_two_panel_cholqr(shape, cplx, cond):
+    """Column counts whose k x k Cholesky does not fit one SM (ComplexF64 k = 128, the cfg5 bond; Float64 k = 256) take the
+    two-panel CholeskyQR2 (cholqr.cu) for well-conditioned inputs and Householder QR otherwise: same accuracy either way."""
+    import ttn_b200 as t
+    rng = np.random.default_rng(shape[0] + int(cond))
+    m, n = shape
+    k = min(m, n)
+    g = lambda a, b: rng.standard_normal((a, b)) + (1j * rng.standard_normal((a, b)) if cplx else 0.0)
+    U, _ = np.linalg.qr(g(m, k))
+    V, _ = np.linalg.qr(g(n, k))
+    s = np.logspace(0, -np.log10(cond), k)
+    A = np.asfortranarray((U * s) @ V.conj().T)
+    Ug, sg, Vtg = t.svdtrunc(A)
+    assert np.abs(sg - s).max() < 1e-12
+    assert relerr((Ug * sg) @ Vtg, A) < 1e-12
+    assert np.abs(Ug.conj().T @ Ug - np.eye(k)).max() < 1e-11

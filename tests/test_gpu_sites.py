@@ -135,3 +135,20 @@ def test_site_calls_reject_bad_arguments():
         t._lib.check(t._lib.lib().ttn_merge_sites_diag(xd._h, 1))   # 2 != 3 physical dims
     with pytest.raises(Exception):
         t._lib.check(t._lib.lib().ttn_split_site(xd._h, 2, 2, 0, 1 << 62, 0.0))   # 2 does not divide 3
+
+
+def test_hadamard_function_reconstruction_on_device():
+    """test/test_tt_operations.jl:41-104 (exp / sin / cos cases) through the device `hadamard` and `hadamard_ttm`."""
+    import ttn_b200 as t
+    d = 8
+    xs = np.linspace(0.0, 1.0, 2 ** d)
+    A1, A2, A3 = o.qtt_exp(d), o.qtt_sin(d, lam=np.pi), o.qtt_cos(d, lam=np.pi)
+    cases = [(A2, A3, np.cos(np.pi ** 2 * xs) * np.sin(np.pi ** 2 * xs)), (A1, A2, np.exp(xs) * np.sin(np.pi ** 2 * xs))]
+    for x, y, expected in cases:
+        h = t.hadamard(x, y)
+        assert np.allclose(o.qtt_to_vector(h), expected, atol=1e-12)
+        z = t.hadamard_ttm(x, y)
+        assert np.allclose(o.qtt_to_vector(z), expected, atol=1e-10)
+        assert t.norm(t.sub(z, h)) / t.norm(h) < 1e-5
+    x, y, expected = cases[1]
+    assert np.allclose(o.qtt_to_vector(t.hadamard_ttm(x, y, tol=1e-8)), expected, atol=1e-3)

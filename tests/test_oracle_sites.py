@@ -65,3 +65,21 @@ def test_to_qtt_dense():
     full = o.ttv_to_tensor(x)
     # big-endian split: the first factor is the coarsest digit  ->  C-order reshape of each axis
     assert np.allclose(o.ttv_to_tensor(q), full.reshape(2, 2, 2, 4, 3, 2), atol=1e-12)
+
+
+def _hadamard_cases(d=8):
+    """test/test_tt_operations.jl:41-104 (the exp / sin / cos cases; λ = π means sin(π² x))."""
+    xs = np.linspace(0.0, 1.0, 2 ** d)
+    A1, A2, A3 = o.qtt_exp(d), o.qtt_sin(d, lam=np.pi), o.qtt_cos(d, lam=np.pi)
+    return [(A2, A3, np.cos(np.pi ** 2 * xs) * np.sin(np.pi ** 2 * xs)), (A1, A2, np.exp(xs) * np.sin(np.pi ** 2 * xs))]
+
+
+def test_hadamard_function_reconstruction():
+    for x, y, expected in _hadamard_cases():
+        assert np.allclose(o.qtt_to_vector(o.hadamard(x, y)), expected, atol=1e-12)            # :51-58
+        z = o.hadamard_ttm(x, y)
+        assert np.allclose(o.qtt_to_vector(z), expected, atol=1e-10)                            # :84-88
+        h = o.hadamard(x, y)
+        assert o.euclidean_distance(z, h) / o.norm(h) < 1e-5                                    # :98-99
+    x, y, expected = _hadamard_cases()[1]
+    assert np.allclose(o.qtt_to_vector(o.hadamard_ttm(x, y, tol=1e-8)), expected, atol=1e-3)    # :103-104
