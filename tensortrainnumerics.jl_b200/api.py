@@ -399,8 +399,13 @@ def tt_compress_(x, max_bond: int, truncerr: float = 0.0, sweeps: int = 1, verbo
     check(lib.ttn_compress(xd._h, int(max_bond), float(truncerr), int(sweeps), sig, int(stride)))
     if host:
         y = xd.download()
-        x.ttv_vec = y.ttv_vec          # same object mutated, `ttv_ot` untouched (test/test_tt_tools.jl:514)
-        x.ttv_rks = y.ttv_rks
+        # the same object and the same `ttv_vec` / `ttv_rks` lists are mutated (tt_tools.jl:754-767 writes element-wise, which
+        # is what lets the QTTvector wrapper of qtt_tools.jl:783-786 share them); `ttv_ot` untouched (test_tt_tools.jl:514)
+        if isinstance(x.ttv_vec, list) and isinstance(x.ttv_rks, list):
+            x.ttv_vec[:] = y.ttv_vec
+            x.ttv_rks[:] = y.ttv_rks
+        else:
+            x.ttv_vec, x.ttv_rks = y.ttv_vec, y.ttv_rks
         res = x
     else:
         res = xd

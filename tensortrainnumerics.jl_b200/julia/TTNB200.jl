@@ -126,8 +126,12 @@ function tt_compress!(ψ::TTvector, max_bond::Int; truncerr::Real = 0.0, sweeps:
     check(ccall((:ttn_compress, LIB[]), Cint, (Ptr{Cvoid}, Int64, Float64, Cint, Ptr{Float64}, Int64),
                 xd.h, max_bond, truncerr, sweeps, C_NULL, 0))
     y = download(xd)
-    ψ.ttv_vec = y.ttv_vec          # same object mutated, ttv_ot untouched (src/tt_tools.jl:754-767)
-    ψ.ttv_rks = y.ttv_rks
+    # element-wise writes into the SAME `ttv_vec` / `ttv_rks` vectors, as src/tt_tools.jl:754-767 does: the QTTvector method
+    # (src/qtt_tools.jl:783-786) relies on `TTvector(q)` sharing those vectors with `q`; ttv_ot stays untouched
+    for k in 1:ψ.N
+        ψ.ttv_vec[k] = y.ttv_vec[k]
+    end
+    ψ.ttv_rks .= y.ttv_rks
     return ψ
 end
 
@@ -327,6 +331,27 @@ function override!()
         mals_eigsolve(A::TToperator, x0::TTvector; kwargs...) = $(mals_eigsolve)(A, x0; kwargs...)
         tdvp(H::TToperator, u0::TTvector, steps::Vector{Float64}; kwargs...) = $(tdvp)(H, u0, steps; kwargs...)
         tdvp2(H::TToperator, u0::TTvector, steps::Vector{Float64}; kwargs...) = $(tdvp2)(H, u0, steps; kwargs...)
+        hadamard_ttm(x::TTvector{T, N}, y::TTvector{T, N}; kwargs...) where {T <: Union{Float64, ComplexF64}, N} =
+            $(hadamard_ttm)(x, y; kwargs...)
+        to_qtt(tt::TTvector{T, N}, split_dims::Vector{Vector{Int}}; kwargs...) where {T <: Union{Float64, ComplexF64}, N} =
+            $(to_qtt)(tt, split_dims; kwargs...)
+        # QTTvector / QTToperator methods (src/qtt_tools.jl:526-534, 590-598, 783-786) delegate to the TTvector / TToperator
+        # methods re-pointed above and re-wrap the result themselves, so they need no entries of their own; `reorder`
+        # (src/qtt_tools.jl:731-774) keeps its permutation logic and only its swap loop moves to the device:
+        function reorder(q::QTTvector, new_ordering::Symbol; threshold::Real = 0.0)
+            @assert new_ordering ∈ (:interleaved, :serial) "ordering must be :interleaved or :serial"
+            q.ordering == new_ordering && return copy(q)
+            perm = zeros(Int, q.N)
+            for d in 1:q.n_dims, b in 0:(q.bits_per_dim - 1)
+                if q.ordering == :serial
+                    perm[(d - 1) * q.bits_per_dim + b + 1] = b * q.n_dims + (d - 1)
+                else
+                    perm[b * q.n_dims + (d - 1) + 1] = (d - 1) * q.bits_per_dim + b
+                end
+            end
+            y = $(apply_swaps)(TTvector(q), _bubble_sort_swaps(perm); threshold = threshold)
+            return QTTvector(y, q.n_dims, q.bits_per_dim, new_ordering)
+        end
     end
     return nothing
 end
