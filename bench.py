@@ -537,7 +537,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="skip the cfg4 matvec / DMRG sweep / cfg5 batch extras")
     ap.add_argument("--dmrg-chi", type=int, default=1024, help="bond cap of the DMRG sweep extra (cfg4: 1024)")
-    ap.add_argument("--batch-vectors", type=int, default=128, help="cfg5 vectors per rank in the batch extra")
+    ap.add_argument("--batch-vectors", type=int, default=256, help="cfg5 vectors per rank in the batch extra")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
