@@ -141,6 +141,9 @@ int ttn_solver_params_default(ttn_solver_params* p);
 int ttn_als_linsolve(ttn_tto A, ttn_ttv b, ttn_ttv x0, const ttn_solver_params* p, ttn_ttv* x, double* residual);
 /* als_eigsolve(A, x0; sweep_schedule, rmax_schedule)  src/solvers/als.jl:251-321;  E: capacity cap_E, n_E written */
 int ttn_als_eigsolve(ttn_tto A, ttn_ttv x0, const ttn_solver_params* p, ttn_ttv* x, double* E, int cap_E, int* n_E);
+/* als_gen_eigsolv(A, S, x0; sweep_schedule, rmax_schedule): lowest pair of A x = lambda S x, S Hermitian positive definite.
+ * The local pencil is solved densely as the reference's K_eiggenmin does (src/solvers/als.jl:89-102, driver :344-440). */
+int ttn_als_gen_eigsolv(ttn_tto A, ttn_tto S, ttn_ttv x0, const ttn_solver_params* p, ttn_ttv* x, double* E, int cap_E, int* n_E);
 /* mals_linsolve(A, b, x0; tol, rmax)             src/solvers/mals.jl:240-309 */
 int ttn_mals_linsolve(ttn_tto A, ttn_ttv b, ttn_ttv x0, const ttn_solver_params* p, ttn_ttv* x, double* residual);
 /* mals_eigsolve(A, x0; tol, sweep_schedule, rmax_schedule)   src/solvers/mals.jl:335-425 */

@@ -26,7 +26,7 @@ from .generators import (toeplitz_to_qtto, laplace_dd, id_tto, heisenberg_xyz_tt
                          qtt_exp)
 from .ops import (apply, add, scale, sub, dot, norm, orthogonalize, svdtrunc, svdtrunc_abs,
                   tt_bond_truncate, tt_compress, euclidean_distance, rel_distance, norm_stable, hadamard)
-from .als import als_linsolve, als_eigsolve
+from .als import als_linsolve, als_eigsolve, als_gen_eigsolv, K_eiggenmin
 from .mals import mals_linsolve, mals_eigsolve, sv_trunc
 from .dmrg import dmrg_linsolve, dmrg_eigsolve, cut_off_index, dmrg_matvec2, dmrg_matvec2_blas, dmrg_update_G, dmrg_update_H, amid
 from .tdvp import tdvp, tdvp2, apply_H1_lsr, apply_H0, apply_H2_lsr, update_left_env, update_right_env

@@ -176,3 +176,60 @@ def als_eigsolve(A: TToperator, tt_start: TTvector, sweep_schedule=(2,), rmax_sc
             x = left_core_move(x, V, i, x.ttv_rks)
             H[i - 2] = update_H(x.ttv_vec[i - 1], A.tto_vec[i - 1], H[i - 1])
     return np.array(E), x
+
+
+def K_eiggenmin(Gi, Hi, Ki, Li):
+    """als.jl:89-102, dense branch: `eigen(K, S)` of the general (non-symmetric) LAPACK driver, eigenvalues in Julia's default
+    order (by real part, then imaginary part), first pair returned.  Note the index order `Gi[d,e,a,b,z] * Hi[z,f,c]` (:91-92):
+    the matrices are the transposes of `K_full`'s."""
+    dims = (Gi.shape[0], Gi.shape[1], Hi.shape[1])
+    n = int(np.prod(dims))
+    K = np.reshape(np.einsum("deabz,zfc->abcdef", Gi, Hi), (n, n), order="F")
+    S = np.reshape(np.einsum("deabz,zfc->abcdef", Ki, Li), (n, n), order="F")
+    w, v = sla.eig(K, S)
+    order = sorted(range(n), key=lambda j: (w[j].real, w[j].imag))
+    j = order[0]
+    return float(np.real(w[j])), np.reshape(v[:, j], dims, order="F")
+
+
+def als_gen_eigsolv(A: TToperator, S: TToperator, tt_start: TTvector, sweep_schedule=(2,), rmax_schedule=None):
+    """als.jl:344-440 (dense local solves): lowest pair of A x = λ S x by ALS sweeps with two sets of environments."""
+    d = A.N
+    if rmax_schedule is None:
+        rmax_schedule = [max(tt_start.ttv_rks)]
+    x = orthogonalize(tt_start)
+    dims = tt_start.ttv_dims
+    T = np.result_type(tt_start.dtype, A.tto_vec[0].dtype, S.tto_vec[0].dtype)
+    E = []
+    G = [None] * d
+    Kc = [None] * d
+    G[0] = np.reshape(A.tto_vec[0][:, :, 0, :], (dims[0], 1, dims[0], 1, -1), order="F").astype(T)
+    Kc[0] = np.reshape(S.tto_vec[0][:, :, 0, :], (dims[0], 1, dims[0], 1, -1), order="F").astype(T)
+    H = init_H(x, A)
+    L = init_H(x, S)
+    nsweeps = 0
+    i_sched = 1
+    while i_sched <= len(sweep_schedule):
+        nsweeps += 1
+        if nsweeps == sweep_schedule[i_sched - 1]:
+            i_sched += 1
+            if i_sched > len(sweep_schedule):
+                return np.array(E), x
+            x = increase_ranks(x, rmax_schedule[i_sched - 1])
+            x = orthogonalize(x)
+            H = init_H(x, A)
+            L = init_H(x, S)
+        for i in range(1, d):
+            if x.ttv_ot[i - 1] == 0:                                              # :404
+                lam, V = K_eiggenmin(G[i - 1], H[i - 1], Kc[i - 1], L[i - 1])
+                E.append(lam)
+                x = right_core_move(x, V.astype(T), i, x.ttv_rks)
+            G[i] = update_G(x.ttv_vec[i - 1], A.tto_vec[i], G[i - 1])
+            Kc[i] = update_G(x.ttv_vec[i - 1], S.tto_vec[i], Kc[i - 1])
+        for i in range(d, 1, -1):
+            lam, V = K_eiggenmin(G[i - 1], H[i - 1], Kc[i - 1], L[i - 1])
+            E.append(lam)
+            x = left_core_move(x, V.astype(T), i, x.ttv_rks)
+            H[i - 2] = update_H(x.ttv_vec[i - 1], A.tto_vec[i - 1], H[i - 1])
+            L[i - 2] = update_H(x.ttv_vec[i - 1], S.tto_vec[i - 1], L[i - 1])
+    return np.array(E), x

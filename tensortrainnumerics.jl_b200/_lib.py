@@ -79,6 +79,7 @@ def load():
         "ttn_solver_params_default": [C.POINTER(SolverParams)], "ttn_tdvp_params_default": [C.POINTER(TdvpParams)],
         "ttn_als_linsolve": [vp, vp, vp, C.POINTER(SolverParams), vpp, dp],
         "ttn_als_eigsolve": [vp, vp, C.POINTER(SolverParams), vpp, dp, C.c_int, ip],
+        "ttn_als_gen_eigsolv": [vp, vp, vp, C.POINTER(SolverParams), vpp, dp, C.c_int, ip],
         "ttn_mals_linsolve": [vp, vp, vp, C.POINTER(SolverParams), vpp, dp],
         "ttn_mals_eigsolve": [vp, vp, C.POINTER(SolverParams), vpp, dp, i64p, C.c_int, ip],
         "ttn_dmrg_linsolve": [vp, vp, vp, C.POINTER(SolverParams), vpp, dp],

@@ -29,7 +29,7 @@ from ._lib import TTN_F64, TTN_C128, SolverParams, TdvpParams, check
 
 __all__ = [
     "TTvector", "TToperator", "DeviceTT", "DeviceTTO", "apply", "dot", "norm", "add", "scale", "sub",
-    "orthogonalize", "tt_compress_", "tt_bond_truncate_", "als_linsolve", "als_eigsolve", "mals_linsolve",
+    "orthogonalize", "tt_compress_", "tt_bond_truncate_", "als_linsolve", "als_eigsolve", "als_gen_eigsolv", "mals_linsolve",
     "mals_eigsolve", "dmrg_linsolve", "dmrg_eigsolve", "tdvp", "tdvp2", "matvec2", "env_left", "env_right",
     "shard_range", "shard_batch", "assemble_slices", "ShardedMatvec", "svdtrunc", "qr_thin", "gemm_host", "launch_count", "reset_launch_count", "synchronize", "library_path", "profile", "profile_read", "stream_handle",
     "KERNEL_FAMILIES",
@@ -497,6 +497,31 @@ def als_eigsolve(A, tt_start, sweep_schedule=(2,), rmax_schedule=None, noise_sch
     cap = 2 * xd.N * (int(sweep_schedule[-1]) + 1) + 8
     E, nE, out = (C.c_double * cap)(), C.c_int(), C.c_void_p()
     check(_lib.lib().ttn_als_eigsolve(Ad._h, xd._h, C.byref(p), C.byref(out), E, cap, C.byref(nE)))
+    return np.array(E[:nE.value]), _ret(DeviceTT(out), host)
+
+
+def als_gen_eigsolv(A, S, tt_start, sweep_schedule=(2,), rmax_schedule=None, tol=1e-10, it_solver=False, itslv_thresh=2500,
+                    maxiter=500, linsolv_tol=1e-12, krylovdim=40):
+    """`als_gen_eigsolv(A, S, tt_start; sweep_schedule, rmax_schedule, …)`, src/solvers/als.jl:344-440 → (E, tt_opt): lowest
+    pair of A x = λ S x (S Hermitian positive definite).  The local pencil is solved densely on the device as the reference's
+    `K_eiggenmin` does (als.jl:89-102; its `lobpcg` branch works on the same dense matrices), so `it_solver` / `itslv_thresh`
+    only select between two routes to the same eigenpair and are accepted for signature compatibility."""
+    xd, host = _dev(tt_start)
+    if rmax_schedule is None:
+        rmax_schedule = [max(xd.ttv_rks)]
+    if len(rmax_schedule) != len(sweep_schedule):
+        raise AssertionError("Sweep schedule error")
+    Ad = _devo(A, xd.dtype)
+    Sd = _devo(S, Ad.dtype)
+    if Sd.dtype == np.complex128 and Ad.dtype != np.complex128:
+        Ad = Ad.complex()
+    if Ad.dtype == np.complex128 and xd.dtype != np.complex128:
+        xd = xd.complex()
+    p, keep = _params(sweep_schedule=sweep_schedule, rmax_schedule=rmax_schedule, linsolv_maxiter=int(maxiter),
+                      linsolv_tol=float(linsolv_tol), krylovdim=int(krylovdim))
+    cap = 2 * xd.N * (int(sweep_schedule[-1]) + 1) + 8
+    E, nE, out = (C.c_double * cap)(), C.c_int(), C.c_void_p()
+    check(_lib.lib().ttn_als_gen_eigsolv(Ad._h, Sd._h, xd._h, C.byref(p), C.byref(out), E, cap, C.byref(nE)))
     return np.array(E[:nE.value]), _ret(DeviceTT(out), host)
 
 

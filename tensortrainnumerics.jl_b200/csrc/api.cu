@@ -447,6 +447,21 @@ int ttn_als_eigsolve(ttn_tto A, ttn_ttv x0, const ttn_solver_params* p, ttn_ttv*
   *x = h;
   API_END
 }
+int ttn_als_gen_eigsolv(ttn_tto A, ttn_tto S, ttn_ttv x0, const ttn_solver_params* p, ttn_ttv* x, double* E, int cap_E, int* n_E) {
+  API_BEGIN
+  SOLVER_PROLOGUE(A, x0)
+  try {
+    ttn_assert(S != nullptr, TTN_EARG, "null argument");
+    same_dtype(A->dtype, S->dtype);
+    std::vector<double> Ev;
+    if (x0->dtype == TTN_F64) als_gen_eigsolve(A->r, S->r, x0->r, *p, h->r, Ev);
+    else als_gen_eigsolve(A->c, S->c, x0->c, *p, h->c, Ev);
+    if (n_E) *n_E = (int)Ev.size();
+    if (E) for (int i = 0; i < (int)Ev.size() && i < cap_E; ++i) E[i] = Ev[i];
+  } catch (...) { delete h; throw; }
+  *x = h;
+  API_END
+}
 int ttn_mals_linsolve(ttn_tto A, ttn_ttv b, ttn_ttv x0, const ttn_solver_params* p, ttn_ttv* x, double* residual) {
   API_BEGIN
   SOLVER_PROLOGUE(A, x0)

@@ -197,6 +197,61 @@ void dense_solve(LocalOp<T>& op, const T* rhs, T* x) {
   TTN_CUDA(cudaStreamSynchronize(ctx().stream));     // K / tau are released when this scope ends
 }
 
+// Lowest eigenpair of the Hermitian-definite pencil (K, M):  K v = lambda M v.  Dense, like the reference's `K_eiggenmin`
+// (src/solvers/als.jl:89-102), which assembles both local matrices in full before `eigen(K, S)` / `lobpcg`:
+//   M = U Sigma U^H (the SVD of a Hermitian positive definite matrix is its eigen-decomposition; Jacobi SVD of svd.cu),
+//   W = U Sigma^{-1/2}  so that  W^H M W = I,   C = W^H K W (two DMMA GEMMs),  lowest pair (theta, y) of C by Lanczos,  v = W y.
+template <class T>
+double gen_eig_lowest(LocalOp<T>& opK, LocalOp<T>& opM, T* v, int krylovdim, int maxiter, double tol) {
+  const int64_t n64 = opK.size();
+  ttn_assert(n64 == opM.size(), 1, "Incompatible dimensions");
+  ttn_assert(n64 <= 4096, 7, "als_gen_eigsolv: local problem too large for the dense generalized eigen-solve");
+  const int N = (int)n64;
+  const size_t NN = (size_t)N * N;
+  DevBuf K(sizeof(T) * NN), M(sizeof(T) * NN);
+  {
+    DevBuf Id(sizeof(T) * NN);
+    set_identity<T>(Id.as<T>(), N, N, N);
+    opK.apply_batch(Id.as<T>(), K.as<T>(), N);          // column j = K e_j
+    opM.apply_batch(Id.as<T>(), M.as<T>(), N);
+  }
+  SvdLeft sv;
+  svd_left<T>(M.as<T>(), N, N, 1, N, false, sv, 1, 0);
+  std::vector<double> sc(N);
+  std::vector<int> perm(sv.perm.begin(), sv.perm.begin() + N);
+  for (int j = 0; j < N; ++j) {
+    const double sg = sv.sigma[j];
+    ttn_assert(sg > sv.sigma[0] * 1e-14 && sg > 0.0, 5, "als_gen_eigsolv: S is numerically singular on the local subspace");
+    sc[j] = 1.0 / (sg * std::sqrt(sg));                   // X_j = u_j sigma_j  ->  u_j sigma_j^{-1/2}
+  }
+  DevBuf dperm(sizeof(int) * N), dsc(sizeof(double) * N), W(sizeof(T) * NN), T1(sizeof(T) * NN), Cm(sizeof(T) * NN);
+  TTN_CUDA(cudaMemcpyAsync(dperm.p, perm.data(), sizeof(int) * N, cudaMemcpyHostToDevice, ctx().stream));
+  TTN_CUDA(cudaMemcpyAsync(dsc.p, sc.data(), sizeof(double) * N, cudaMemcpyHostToDevice, ctx().stream));
+  gather_cols<T>(sv.X.as<T>(), N, N, dperm.as<int>(), dsc.as<double>(), N, W.as<T>(), 1, N);
+  auto mm = [&](const T* A, bool hA, const T* B, int ncol, T* Cc) {   // Cc (N x ncol) = op(A) B,  A: N x N
+    GemmArgs g;
+    g.M = N; g.N = ncol; g.K = N;
+    g.A = A; g.sAm = hA ? N : 1; g.sAk = hA ? 1 : N; g.conjA = hA;
+    g.B = B; g.sBk = 1; g.sBn = N;
+    g.C = Cc; g.sCm = 1; g.sCn = N;
+    gemm<T>(g);
+  };
+  mm(K.as<T>(), false, W.as<T>(), N, T1.as<T>());
+  mm(W.as<T>(), true, T1.as<T>(), N, Cm.as<T>());
+  DevBuf t(sizeof(T) * N), y(sizeof(T) * N);
+  mm(M.as<T>(), false, v, 1, t.as<T>());                 // y0 = W^-1 v = W^H M v
+  mm(W.as<T>(), true, t.as<T>(), 1, y.as<T>());
+  if (!(nrm2<T>(N, y.as<T>()) > 0.0)) fill<T>(y.as<T>(), N, t_one<T>());
+  LocalOp<T> opC;
+  opC.chi_l = N; opC.nn = 1; opC.chi_r = 1;
+  const T* Cp = Cm.as<T>();
+  opC.ext_apply = [&mm, Cp](const T* a, T* b) { mm(Cp, false, a, 1, b); };
+  const double theta = lanczos_lowest<T>(opC, y.as<T>(), krylovdim, maxiter, tol, nullptr);
+  mm(W.as<T>(), false, y.as<T>(), 1, v);
+  TTN_CUDA(cudaStreamSynchronize(ctx().stream));
+  return theta;
+}
+
 template <class T>
 void local_linsolve(LocalOp<T>& op, const T* rhs, T* x, int krylovdim, int maxiter, double tol, const ttn_solver_params& p) {
   const int64_t dense_max = std::max<int64_t>(p.itslv_thresh, 2048);
@@ -367,6 +422,7 @@ void lanczos_expm(LocalOp<T>& op, T* x, double tre, double tim, int krylovdim, i
   template double lanczos_lowest<T>(LocalOp<T>&, T*, int, int, double, KrylovInfo*);                    \
   template void gmres_solve<T>(LocalOp<T>&, const T*, T*, int, int, double, KrylovInfo*);               \
   template void dense_solve<T>(LocalOp<T>&, const T*, T*);                                                \
+  template double gen_eig_lowest<T>(LocalOp<T>&, LocalOp<T>&, T*, int, int, double);                      \
   template void local_linsolve<T>(LocalOp<T>&, const T*, T*, int, int, double, const ttn_solver_params&); \
   template void lanczos_expm<T>(LocalOp<T>&, T*, double, double, int, int, double, KrylovInfo*);
 INST(double)

@@ -58,6 +58,8 @@ template <class T> void gmres_solve(LocalOp<T>& op, const T* rhs, T* x, int kryl
 // dense direct solve K x = rhs for small windows (`K_full` + `\\`: als.jl:58-70, mals.jl:148-169, dmrg.jl:49-54,173-174):
 // K assembled by applying the operator to the identity (one batched three-GEMM pass), Householder QR, back substitution
 template <class T> void dense_solve(LocalOp<T>& op, const T* rhs, T* x);
+// lowest eigenpair of the Hermitian-definite pencil (K, M), dense (`K_eiggenmin`, als.jl:89-102); v: start vector in, eigenvector out
+template <class T> double gen_eig_lowest(LocalOp<T>& opK, LocalOp<T>& opM, T* v, int krylovdim, int maxiter, double tol);
 // dense when the window has at most max(itslv_thresh, 2048) unknowns and it_solver is off, GMRES otherwise
 template <class T>
 void local_linsolve(LocalOp<T>& op, const T* rhs, T* x, int krylovdim, int maxiter, double tol, const ttn_solver_params& p);
@@ -72,6 +74,10 @@ template <class T>
 void als_linsolve(const TTO<T>& A, const TT<T>& b, const TT<T>& x0, const ttn_solver_params& p, TT<T>& x, double* residual);
 template <class T>
 void als_eigsolve(const TTO<T>& A, const TT<T>& x0, const ttn_solver_params& p, TT<T>& x, std::vector<double>& E);
+// als_gen_eigsolv(A, S, x0): A x = lambda S x                                   (src/solvers/als.jl:344-440)
+template <class T>
+void als_gen_eigsolve(const TTO<T>& A, const TTO<T>& Sop, const TT<T>& x0, const ttn_solver_params& p, TT<T>& x,
+                      std::vector<double>& E);
 template <class T>
 void mals_linsolve(const TTO<T>& A, const TT<T>& b, const TT<T>& x0, const ttn_solver_params& p, TT<T>& x, double* residual);
 template <class T>

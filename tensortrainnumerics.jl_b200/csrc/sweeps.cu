@@ -457,6 +457,69 @@ void als_eigsolve(const TTO<T>& A, const TT<T>& x0, const ttn_solver_params& p, 
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// als_gen_eigsolv (src/solvers/als.jl:344-440): A x = lambda S x.  Two sets of environments over the same train
+// (G/H for A, K/L for S in the reference); the local pencil is solved densely like `K_eiggenmin` (als.jl:89-102).
+// ---------------------------------------------------------------------------------------------------------
+template <class T>
+void als_gen_eigsolve(const TTO<T>& A, const TTO<T>& Sop, const TT<T>& x0, const ttn_solver_params& p, TT<T>& x,
+                      std::vector<double>& E) {
+  check_schedules(p);
+  tt_orthogonalize(x0, 1, x);
+  E.clear();
+  const int kd = std::max(p.krylovdim, 2), maxit = std::max(p.linsolv_maxiter, 1);
+  std::unique_ptr<Sweeper<T>> SA(new Sweeper<T>(A, nullptr, x)), SS(new Sweeper<T>(Sop, nullptr, x));
+  const int d = x.d;
+  SA->init_right(1);
+  SS->init_right(1);
+  auto eig_site = [&](int k, DevBuf& V) {
+    LocalOp<T> opK, opM; DevBuf WK, WM;
+    SA->setup_op(opK, WK, k, 1, false);
+    SS->setup_op(opM, WM, k, 1, false);
+    SA->window(k, 1, V);
+    const double lam = gen_eig_lowest<T>(opK, opM, V.as<T>(), kd, maxit, p.linsolv_tol);
+    if (std::is_same<T, zc>::value) {
+      // `K_eiggenmin` contracts `Gi[d,e,a,b,z] * Hi[z,f,c]` (als.jl:91-92), the TRANSPOSE of `K_full`'s matrix (als.jl:60); for a
+      // Hermitian pencil that is the complex-conjugate problem, whose eigenvector is conj(v).  Reproduced as is.
+      DevBuf Vc(V.bytes);
+      Copy4 c; c.n0 = (int64_t)opK.size(); c.conj = true;
+      copy4<T>(V.as<T>(), Vc.as<T>(), c);
+      V = std::move(Vc);
+    }
+    return lam;
+  };
+  int nsweeps = 0, i_sched = 1;
+  while (i_sched <= p.n_sweep_schedule) {
+    ++nsweeps;
+    if (nsweeps == p.sweep_schedule[i_sched - 1]) {
+      ++i_sched;
+      if (i_sched > p.n_sweep_schedule) return;
+      increase_ranks(x, p.rmax_schedule[i_sched - 1]);
+      TT<T> y;
+      tt_orthogonalize(x, 1, y);
+      x.cores = std::move(y.cores); x.rks = y.rks; x.ot = y.ot;
+      SA.reset(new Sweeper<T>(A, nullptr, x));
+      SS.reset(new Sweeper<T>(Sop, nullptr, x));
+      SA->init_right(1);
+      SS->init_right(1);
+    }
+    for (int k = 0; k < d - 1; ++k) {
+      DevBuf V;
+      E.push_back(eig_site(k, V));
+      als_right_move(*SA, k, V);
+      SA->update_left(k);
+      SS->update_left(k);
+    }
+    for (int k = d - 1; k >= 1; --k) {
+      DevBuf V;
+      E.push_back(eig_site(k, V));
+      als_left_move(*SA, k, V);
+      SA->update_right(k);
+      SS->update_right(k);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // MALS (src/solvers/mals.jl:240-309, :335-425)
 // ---------------------------------------------------------------------------------------------------------
 template <class T>
@@ -733,6 +796,8 @@ void dmrg_eigsolve(const TTO<T>& A, const TT<T>& x0, const ttn_solver_params& p,
   template void tto_copy<T>(const TTO<T>&, TTO<T>&);                                                                      \
   template void als_linsolve<T>(const TTO<T>&, const TT<T>&, const TT<T>&, const ttn_solver_params&, TT<T>&, double*);     \
   template void als_eigsolve<T>(const TTO<T>&, const TT<T>&, const ttn_solver_params&, TT<T>&, std::vector<double>&);      \
+  template void als_gen_eigsolve<T>(const TTO<T>&, const TTO<T>&, const TT<T>&, const ttn_solver_params&, TT<T>&,          \
+                                    std::vector<double>&);                                                                \
   template void mals_linsolve<T>(const TTO<T>&, const TT<T>&, const TT<T>&, const ttn_solver_params&, TT<T>&, double*);    \
   template void mals_eigsolve<T>(const TTO<T>&, const TT<T>&, const ttn_solver_params&, TT<T>&, std::vector<double>&,      \
                                  std::vector<int64_t>&);                                                                   \

@@ -245,6 +245,19 @@ function _eigsolve(sym::Symbol, A, x0, p, keep, cap)
     return E[1:nE[]], download(DevTT(out[])), rh[1:nE[]]
 end
 
+# als_gen_eigsolv(A, S, tt_start; ...)                            src/solvers/als.jl:344-440
+function als_gen_eigsolv(A, S, tt_start; sweep_schedule = [2], rmax_schedule = [maximum(tt_start.ttv_rks)], tol = 1.0e-10,
+                         it_solver = false, itslv_thresh = 2500)
+    p, keep = params(; sweep_schedule, rmax_schedule, linsolv_maxiter = 500, linsolv_tol = 1.0e-12, krylovdim = 40)
+    Ad, Sd, xd = upload(A), upload(S), upload(tt_start)
+    cap = 2 * tt_start.N * (sweep_schedule[end] + 1) + 8
+    out, nE, E = Ref{Ptr{Cvoid}}(C_NULL), Ref{Cint}(0), zeros(Float64, cap)
+    GC.@preserve keep check(ccall((:ttn_als_gen_eigsolv, LIB[]), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{SolverParams}, Ptr{Ptr{Cvoid}}, Ptr{Float64}, Cint, Ptr{Cint}),
+        Ad.h, Sd.h, xd.h, Ref(p), out, E, cap, nE))
+    return E[1:nE[]], download(DevTT(out[]))
+end
+
 function dmrg_eigsolve(A, tt_start; N = 2, tol = 1.0e-12, sweep_schedule = [2],
                        rmax_schedule = [isqrt(prod(tt_start.ttv_dims))], it_solver = false, linsolv_maxiter = 200,
                        linsolv_tol = max(sqrt(tol), 1.0e-8), itslv_thresh = 256)

@@ -240,3 +240,64 @@ def test_als_linsolve_complex_dense_local_solve():
     x = t.als_linsolve(A, b, x0, sweep_count=6)
     ref = np.linalg.solve(o.tto_to_matrix(A), dv(b))
     assert relerr(dv(x), ref) < 1e-10
+
+
+def _spd_mass(d, eps=0.3):
+    return o.tto_add(o.id_tto(d), o.tto_scale(-eps / 2.0, o.tto_add(o.laplace_dd(d), o.tto_scale(-2.0, o.id_tto(d)))))
+
+
+@pytest.mark.gpu
+def test_als_gen_eigsolv_vs_oracle_and_dense():
+    """`als_gen_eigsolv` (als.jl:344-440; test/test_als.jl:153-197): the energies of every local solve equal the oracle's, the
+    final Rayleigh quotient equals the lowest eigenvalue of the dense pencil, S = I reproduces `als_eigsolve`."""
+    import ttn_b200 as t
+    d = 5
+    rng = np.random.default_rng(21)
+    A = spd_op(d, 2.0)
+    x0 = o.rand_tt((2,) * d, 4, rng=rng, normalise=True)
+    S = _spd_mass(d)
+    Am, Sm = o.tto_to_matrix(A), o.tto_to_matrix(S)
+    lam = sla.eigh(Am, Sm, eigvals_only=True)[0]
+    E, x = t.als_gen_eigsolv(A, S, x0, sweep_schedule=[6], rmax_schedule=[4])
+    Eo, xo = o.als_gen_eigsolv(A, S, x0, sweep_schedule=[6], rmax_schedule=[4])
+    assert len(E) == len(Eo) and abs(E[-1] - Eo[-1]) < 1e-9
+    # step-by-step energies at rank 2, where every local eigenvector has a full-rank unfolding (with over-parametrised ranks the
+    # QR of a rank-deficient unfolding completes the basis from rounding noise and the trajectory is not reproducible)
+    x2 = o.rand_tt((2,) * d, 2, rng=rng, normalise=True)
+    E2s, _ = t.als_gen_eigsolv(A, S, x2, sweep_schedule=[3], rmax_schedule=[2])
+    E2o, _ = o.als_gen_eigsolv(A, S, x2, sweep_schedule=[3], rmax_schedule=[2])
+    assert len(E2s) == len(E2o) and np.max(np.abs(E2s - E2o)) < 1e-9
+    assert abs(E[-1] - lam) < 1e-9
+    v = dv(x)
+    assert abs((v @ Am @ v) / (v @ Sm @ v) - lam) < 1e-9
+    vo = dv(xo)
+    assert 1.0 - abs(v @ Sm @ vo) / np.sqrt((v @ Sm @ v) * (vo @ Sm @ vo)) < 1e-9
+    E_gen, _ = t.als_gen_eigsolv(A, o.id_tto(d), x0, sweep_schedule=[4], rmax_schedule=[4])
+    E_std, _ = t.als_eigsolve(A, x0, sweep_schedule=[4], rmax_schedule=[4], linsolv_tol=1e-13)
+    assert abs(E_gen[-1] - E_std[-1]) < 1e-10
+    # rank growth through the schedule (test_als.jl:184-197) and the schedule check
+    E2, x2 = t.als_gen_eigsolv(spd_op(3, 2.0), o.id_tto(3), o.rand_tt((2,) * 3, 1, rng=rng), sweep_schedule=[1, 2], rmax_schedule=[1, 2])
+    assert max(x2.ttv_rks) <= 2 and np.all(np.isfinite(E2))
+    with pytest.raises(AssertionError):
+        t.als_gen_eigsolv(A, S, x0, sweep_schedule=[2, 3], rmax_schedule=[4])
+
+
+@pytest.mark.gpu
+def test_als_gen_eigsolv_complex_follows_reference_transpose():
+    """ComplexF64 pencil: `K_eiggenmin` builds the transposed local matrices (als.jl:91-92), so the local eigenvector is the
+    conjugate of the mathematical one; the device path reproduces the reference's energies step by step."""
+    import ttn_b200 as t
+    d = 4
+    rng = np.random.default_rng(22)
+    def phased(Areal, phis):                        # D^H A D with D = kron_k diag(1, exp(i phi_k)): Hermitian, complex
+        Ac = o.complex_tto(Areal)
+        for k, phi in enumerate(phis):
+            dk = np.array([1.0, np.exp(1j * phi)])
+            Ac.tto_vec[k] = np.conj(dk)[:, None, None, None] * Ac.tto_vec[k] * dk[None, :, None, None]
+        return Ac
+    A = phased(spd_op(d, 2.0), [0.3, 1.1, -0.7, 2.0])
+    S = phased(_spd_mass(d), [0.3, 1.1, -0.7, 2.0])
+    x0 = o.rand_tt((2,) * d, 2, rng=rng, dtype=np.complex128, normalise=True)
+    E, x = t.als_gen_eigsolv(A, S, x0, sweep_schedule=[3], rmax_schedule=[2])
+    Eo, xo = o.als_gen_eigsolv(A, S, x0, sweep_schedule=[3], rmax_schedule=[2])
+    assert len(E) == len(Eo) and np.max(np.abs(E - Eo)) < 1e-9

@@ -233,3 +233,30 @@ def test_matvec_blas_restatement_equals_einsum():
     G = rng.standard_normal((3, 6, 6)); H = rng.standard_normal((4, 5, 5))
     Am = rng.standard_normal((3, 4, 4, 4)); V = rng.standard_normal((6, 4, 5))
     assert np.allclose(o.dmrg_matvec2_blas(G, Am, V, H), o.dmrg_matvec2(G, Am, V, H, symmetrize=False), rtol=1e-13, atol=1e-13)
+
+
+def _spd_mass(d, eps=0.3):
+    # a well-conditioned SPD "overlap" operator: I + eps * (shift + shift^T) as a rank-3 TTO sum
+    S = o.tto_add(o.id_tto(d), o.tto_scale(-eps / 2.0, o.tto_add(o.laplace_dd(d), o.tto_scale(-2.0, o.id_tto(d)))))
+    return S
+
+
+def test_als_gen_eigsolv_vs_dense_and_reference_tests():
+    # test/test_als.jl:153-197: structure, S = I agreement with als_eigsolve, rank growth; tightened against scipy eigh(A, S)
+    d = 5
+    rng = np.random.default_rng(21)
+    A = spd_op(d, 2.0)
+    x0 = o.rand_tt((2,) * d, 4, rng=rng, normalise=True)
+    E_gen, xg = o.als_gen_eigsolv(A, o.id_tto(d), x0, sweep_schedule=[4], rmax_schedule=[4])
+    E_std, _ = o.als_eigsolve(A, x0, sweep_schedule=[4], rmax_schedule=[4])
+    assert abs(E_gen[-1] - E_std[-1]) < 1e-10                                   # test_als.jl:168-181 (rtol 0.05 there)
+    S = _spd_mass(d)
+    Am, Sm = o.tto_to_matrix(A), o.tto_to_matrix(S)
+    assert np.all(sla.eigvalsh(Sm) > 0.2)
+    lam = sla.eigh(Am, Sm, eigvals_only=True)[0]
+    E, x = o.als_gen_eigsolv(A, S, x0, sweep_schedule=[6], rmax_schedule=[4])
+    assert abs(E[-1] - lam) < 1e-9
+    v = dv(x)
+    assert abs((v @ Am @ v) / (v @ Sm @ v) - lam) < 1e-9
+    E2, x2 = o.als_gen_eigsolv(spd_op(3, 2.0), o.id_tto(3), o.rand_tt((2,) * 3, 1, rng=rng), sweep_schedule=[1, 2], rmax_schedule=[1, 2])
+    assert max(x2.ttv_rks) <= 2 and np.all(np.isfinite(E2))                     # test_als.jl:184-197
