@@ -28,7 +28,8 @@ from . import _lib
 from ._lib import TTN_F64, TTN_C128, SolverParams, TdvpParams, check
 
 __all__ = [
-    "TTvector", "TToperator", "DeviceTT", "DeviceTTO", "apply", "dot", "norm", "add", "scale", "sub",
+    "TTvector", "TToperator", "DeviceTT", "DeviceTTO", "apply", "dot", "norm", "add", "add_", "scale", "sub", "euclidean_distance",
+    "euclidean_distance_normalized",
     "orthogonalize", "tt_compress_", "tt_bond_truncate_", "als_linsolve", "als_eigsolve", "als_gen_eigsolv", "mals_linsolve",
     "mals_eigsolve", "dmrg_linsolve", "dmrg_eigsolve", "tdvp", "tdvp2", "matvec2", "env_left", "env_right",
     "shard_range", "shard_batch", "assemble_slices", "ShardedMatvec", "svdtrunc", "qr_thin", "gemm_host", "launch_count", "reset_launch_count", "synchronize", "library_path", "profile", "profile_read", "stream_handle",
@@ -371,6 +372,34 @@ def sub(x, y):
     xd, host = _dev(x)
     yd, _ = _dev(y)
     return _ret(add(scale(-1.0, yd), xd), host)
+
+
+def add_(x, y):
+    """`add!(x, y)`, src/tt_operations.jl:36-66: x <- x + y in place (host TTvector fields overwritten, `ttv_ot` zeroed);
+    a DeviceTT cannot change identity, so the sum is returned for it."""
+    z = add(x, y)
+    if isinstance(x, DeviceTT):
+        return z
+    x.ttv_vec, x.ttv_rks, x.ttv_ot = z.ttv_vec, z.ttv_rks, [0] * x.N
+    return x
+
+
+def euclidean_distance(a, b):
+    """src/tt_operations.jl:452-455: sqrt(max(<a,a> - 2 Re<b,a> + <b,b>, 0)) from three transfer-matrix chains."""
+    ad, _ = _dev(a)
+    bd, _ = _dev(b)
+    assert tuple(ad.ttv_dims) == tuple(bd.ttv_dims), "TT dimensions must match"
+    return math.sqrt(max(float(np.real(dot(ad, ad) - 2.0 * np.real(dot(bd, ad)) + dot(bd, bd))), 0.0))
+
+
+def euclidean_distance_normalized(a, b):
+    """src/tt_operations.jl:457-460: sqrt(1 + <a,a>/<b,b> - 2 Re<b,a>/<b,b>)."""
+    ad, _ = _dev(a)
+    bd, _ = _dev(b)
+    assert tuple(ad.ttv_dims) == tuple(bd.ttv_dims), "TT dimensions must match"
+    bb = dot(bd, bd)
+    v = 1.0 + dot(ad, ad) / bb - 2.0 * np.real(dot(bd, ad)) / bb
+    return float(np.sqrt(np.real(v))) if np.real(v) >= 0 else float("nan")
 
 
 # ------------------------------------------------------------------------------------------------------

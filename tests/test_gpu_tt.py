@@ -365,3 +365,23 @@ def test_apply_large_mpo_cores(R):
     ref = o.ttv_to_tensor(o.apply(A, x))
     assert list(y.ttv_rks) == [1, 2 * R, 2 * R, 1]
     assert np.linalg.norm(o.ttv_to_tensor(y) - ref) / np.linalg.norm(ref) < 1e-13
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cplx", [False, True])
+def test_distances_and_add_inplace(cplx):
+    """`euclidean_distance`, `euclidean_distance_normalized` (tt_operations.jl:452-460) and `add!` (:36-66; test_tt_operations.jl
+    :106-114) against the dense tensors."""
+    import ttn_b200 as t
+    rng = np.random.default_rng(41)
+    dt = np.complex128 if cplx else np.float64
+    a = o.rand_tt((2, 3, 2, 2), 3, rng=rng, dtype=dt); b = o.rand_tt((2, 3, 2, 2), 2, rng=rng, dtype=dt)
+    A, B = o.ttv_to_tensor(a), o.ttv_to_tensor(b)
+    assert abs(t.euclidean_distance(a, b) - np.linalg.norm(A - B)) < 1e-12 * np.linalg.norm(A)
+    assert abs(t.euclidean_distance_normalized(a, b) - np.linalg.norm(A - B) / np.linalg.norm(B)) < 1e-12
+    assert t.euclidean_distance(a, a) < 1e-7 * np.linalg.norm(A)           # cancellation floor sqrt(eps) of the formula
+    x = o.copy_tt(a)
+    y = t.add_(x, b)
+    assert y is x and list(x.ttv_rks) == [1] + [p + q for p, q in zip(a.ttv_rks[1:-1], b.ttv_rks[1:-1])] + [1]
+    assert all(v == 0 for v in x.ttv_ot)
+    assert np.allclose(o.ttv_to_tensor(x), A + B, atol=1e-12)
