@@ -97,9 +97,28 @@ def bubble_sort_swaps(perm):
     return swaps
 
 
-def reorder(x, n_dims: int, bits_per_dim: int, ordering: str, new_ordering: str, threshold: float = 0.0):
-    """`reorder(q::QTTvector, new_ordering; threshold)`, qtt_tools.jl:731-774.  The QTT metadata of the reference's
-    `QTTvector` wrapper (n_dims, bits_per_dim, ordering) is passed explicitly; returns a new train."""
+class QTTvector(_a.TTvector):
+    """src/qtt_tools.jl:370-379: a TTvector with the multi-dimensional QTT metadata (`n_dims`, `bits_per_dim`, `ordering` in
+    {"serial", "interleaved"}).  Every TTvector routine accepts it (same field names); `reorder` and `tt_compress_`
+    return it re-wrapped like qtt_tools.jl:731-786."""
+
+    def __init__(self, tt, n_dims: int, bits_per_dim: int, ordering: str):
+        assert ordering in ("interleaved", "serial"), "ordering must be :interleaved or :serial"
+        assert tt.N == n_dims * bits_per_dim, "QTTvector: N must equal n_dims * bits_per_dim"
+        super().__init__(tt.N, tt.ttv_vec, tt.ttv_dims, tt.ttv_rks, tt.ttv_ot)
+        self.n_dims, self.bits_per_dim, self.ordering = int(n_dims), int(bits_per_dim), ordering
+
+
+def reorder(x, *args, threshold: float = 0.0):
+    """`reorder(q::QTTvector, new_ordering; threshold)`, qtt_tools.jl:731-774.  Either `reorder(q, new_ordering)` with a
+    `QTTvector` (returns a QTTvector), or `reorder(x, n_dims, bits_per_dim, ordering, new_ordering)` with the metadata
+    passed explicitly for a plain TTvector / DeviceTT (returns a new train of the same kind)."""
+    if isinstance(x, QTTvector):
+        (new_ordering,) = args
+        y = reorder(_a.TTvector(x.N, x.ttv_vec, x.ttv_dims, x.ttv_rks, x.ttv_ot), x.n_dims, x.bits_per_dim, x.ordering,
+                    new_ordering, threshold=threshold)
+        return QTTvector(y, x.n_dims, x.bits_per_dim, new_ordering)
+    n_dims, bits_per_dim, ordering, new_ordering = args
     assert ordering in ("interleaved", "serial") and new_ordering in ("interleaved", "serial"), \
         "ordering must be :interleaved or :serial"
     xd, host = _a._dev(x)

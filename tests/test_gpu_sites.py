@@ -152,3 +152,25 @@ def test_hadamard_function_reconstruction_on_device():
         assert t.norm(t.sub(z, h)) / t.norm(h) < 1e-5
     x, y, expected = cases[1]
     assert np.allclose(o.qtt_to_vector(t.hadamard_ttm(x, y, tol=1e-8)), expected, atol=1e-3)
+
+
+def test_qttvector_wrapper_reorder_and_compress():
+    """`QTTvector` (qtt_tools.jl:370-379): `reorder(q, new_ordering)` and `tt_compress!(q, …)` come back re-wrapped with the
+    metadata (qtt_tools.jl:731-786); the serial -> interleaved -> serial round trip returns the tensor."""
+    import ttn_b200 as t
+    rng = np.random.default_rng(37)
+    x = o.rand_tt((2,) * 6, 4, rng=rng)
+    q = t.QTTvector(x, 2, 3, "serial")
+    qi = t.reorder(q, "interleaved")
+    assert isinstance(qi, t.QTTvector) and qi.ordering == "interleaved" and (qi.n_dims, qi.bits_per_dim) == (2, 3)
+    ref = o.reorder(x, 2, 3, "serial", "interleaved")
+    assert _rel(o.ttv_to_tensor(qi), o.ttv_to_tensor(ref)) < TOL
+    back = t.reorder(qi, "serial")
+    assert _rel(o.ttv_to_tensor(back), o.ttv_to_tensor(x)) < TOL
+    same = t.reorder(q, "serial")
+    assert isinstance(same, t.QTTvector) and _rel(o.ttv_to_tensor(same), o.ttv_to_tensor(x)) < 1e-15
+    vec_list = qi.ttv_vec
+    out = t.tt_compress_(qi, 3)
+    assert out is qi and qi.ttv_vec is vec_list and max(qi.ttv_rks) <= 3       # same object, same lists mutated
+    with pytest.raises(AssertionError):
+        t.QTTvector(x, 2, 3, "zigzag")
