@@ -94,9 +94,13 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
+            t0 = time.time()                      # nvidia-smi needs ~0.1-0.3 s to print its first row: wait for it (bounded)
+            while not self.rows and time.time() - t0 < 1.5:
+                time.sleep(0.01)
+            self.rows.clear()                     # rows printed before the timed region starts are not under load
         except Exception:
             self.proc = None
 
