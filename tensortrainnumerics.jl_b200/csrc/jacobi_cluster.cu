@@ -40,7 +40,7 @@ __device__ __forceinline__ void next_slot(int c, bool top, int& dc, bool& dtop) 
 
 
 // One plane rotation of the column pair held in registers (rp, rq: RPL rows per lane of a GL-lane group) with maintained
-// squared norms an, bn.  Returns 0 (skipped), 1 (rotated, |x_p^H x_q|^2 <= 1e-18 a b) or 2 (rotated).
+// squared norms an, bn.  Returns 0 (skipped), 1 (rotated, |x_p^H x_q|^2 <= 1e-18 a b and sin^2 <= 1e-10) or 2 (rotated).
 template <class T, int GL, int RPL>
 __device__ __forceinline__ int rotate_pair(T (&rp)[RPL], T (&rq)[RPL], double& an, double& bn, double tol2, double floor2) {
   T c2v[2] = {t_zero<T>(), t_zero<T>()};
@@ -83,7 +83,10 @@ __device__ __forceinline__ int rotate_pair(T (&rp)[RPL], T (&rq)[RPL], double& a
     rp[k] = t_sub(t_scale(pv, cs), t_mul(phc, qv));
     rq[k] = t_add(t_mul(ph, pv), t_scale(qv, cs));
   }
-  return cc > 1e-18 * ab ? 2 : 1;
+  // level 1 = "second-order" rotation: the pair was orthogonal to ~1e-9 AND the angle is small.  A large angle (clustered or
+  // degenerate singular values: tan 2θ = 2|c|/(b-a)) re-fills already-zeroed inner products (p,k) with sn * (q,k), which stays
+  // below the tolerance m*eps/2 only when |sn| <~ 1e-5 — so such a rotation still asks for a confirming sweep.
+  return (cc > 1e-18 * ab || sn * sn > 1e-10) ? 2 : 1;
 }
 
 // writes local column j (registers) into the shared memory of the CTA that owns it in the next block step

@@ -259,3 +259,23 @@ def test_svdtrunc_two_panel_cholqr(shape, cplx, cond):
     assert np.abs(sg - s).max() < 1e-12
     assert relerr((Ug * sg) @ Vtg, A) < 1e-12
     assert np.abs(Ug.conj().T @ Ug - np.eye(k)).max() < 1e-11
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(128, 128), (96, 200), (256, 192), (700, 660)])
+def test_svdtrunc_degenerate_multiplets(shape):
+    """Exactly degenerate singular values (multiplets, as symmetric DMRG states produce): the Jacobi rotations inside a
+    multiplet have large angles however small the inner product is, so the "all rotations were second order" shortcut of the
+    cluster / Gram-block kernels must not fire on them; U stays orthonormal to 1e-11 and the reconstruction exact."""
+    import ttn_b200 as t
+    rng = np.random.default_rng(shape[0] * 7 + shape[1])
+    m, n = shape
+    k = min(m, n)
+    U, _ = np.linalg.qr(rng.standard_normal((m, k)))
+    V, _ = np.linalg.qr(rng.standard_normal((n, k)))
+    s = np.repeat(np.logspace(0, -6, (k + 3) // 4), 4)[:k]
+    A = np.asfortranarray((U * s) @ V.T)
+    Ug, sg, Vtg = t.svdtrunc(A)
+    assert np.abs(sg - s).max() < 1e-12
+    assert relerr((Ug * sg) @ Vtg, A) < 1e-12
+    assert np.abs(Ug.T @ Ug - np.eye(k)).max() < 1e-11
