@@ -15,6 +15,12 @@
 #include "ttn_internal.h"
 
 namespace ttn {
+
+// TTN_DEBUG_SVD=1 prints one line per factorisation (read once)
+static inline bool debug_svd() {
+  static const bool on = getenv("TTN_DEBUG_SVD") != nullptr;
+  return on;
+}
 namespace {
 
 constexpr int CQ_T = 256;
@@ -302,7 +308,7 @@ bool cholqr2_two_panel(const T* A, int m, int k, int64_t lda, int64_t bA, T* R, 
   for (int b = 0; b < batch; ++b) {
     const double ratio = std::min(d1[2 * b], d2[2 * b]) / std::max(d1[2 * b + 1], d2[2 * b + 1]);
     if (!(ratio >= 1e-4)) {
-      if (getenv("TTN_DEBUG_SVD")) fprintf(stderr, "[ttn] cholqr2 %d x %d (two panels): min/max diag(R) = %.3g -> rejected\n", m, k, ratio);
+      if (debug_svd()) fprintf(stderr, "[ttn] cholqr2 %d x %d (two panels): min/max diag(R) = %.3g -> rejected\n", m, k, ratio);
       return false;
     }
   }
@@ -369,7 +375,7 @@ bool cholqr2_impl(const T* A, int m, int k, int64_t lda, int64_t bA, T* R, T* Q,
   // min/max diag(R1) >= 0.3 means cond(A) of a few units (cfg2's bonds: 0.39 ... 0.78), i.e. a few tens of eps — the level of
   // the rounding of the K = 512 GEMMs around it.
   const bool single = worst >= 0.3;
-  if (getenv("TTN_DEBUG_SVD")) fprintf(stderr, "[ttn] cholqr2 %d x %d batch %d: min/max diag(R1) = %.3g -> %s\n", m, k, batch, worst, single ? "one pass" : "two passes");
+  if (debug_svd()) fprintf(stderr, "[ttn] cholqr2 %d x %d batch %d: min/max diag(R1) = %.3g -> %s\n", m, k, batch, worst, single ? "one pass" : "two passes");
   if (single) {
     TTN_CUDA(cudaMemcpyAsync(R, R1.p, sizeof(T) * kk * batch, cudaMemcpyDeviceToDevice, ctx().stream));
     if (Q != nullptr) {
@@ -415,7 +421,7 @@ bool cholqr2_impl(const T* A, int m, int k, int64_t lda, int64_t bA, T* R, T* Q,
   for (int b = 0; b < batch; ++b) {
     const double v = h[2 * b];
     if (!(v >= 0.9)) {
-      if (getenv("TTN_DEBUG_SVD")) fprintf(stderr, "[ttn] cholqr2 %d x %d: second pass min/max diag(R2) = %.3g -> rejected\n", m, k, v);
+      if (debug_svd()) fprintf(stderr, "[ttn] cholqr2 %d x %d: second pass min/max diag(R2) = %.3g -> rejected\n", m, k, v);
       return false;
     }
   }

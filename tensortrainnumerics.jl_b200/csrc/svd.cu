@@ -10,6 +10,12 @@
 #include "ttn_internal.h"
 
 namespace ttn {
+
+// TTN_DEBUG_SVD=1 prints one line per factorisation (read once)
+static inline bool debug_svd() {
+  static const bool on = getenv("TTN_DEBUG_SVD") != nullptr;
+  return on;
+}
 namespace {
 
 // squared column norms of W (m x n, ld m): one warp per column
@@ -141,7 +147,7 @@ void svd_left(const T* Theta, int p, int q, int64_t rs, int64_t cs, bool conj, S
     }
   }
 
-  if (getenv("TTN_DEBUG_SVD")) fprintf(stderr, "[ttn] svd_left %d x %d batch %d: %d Jacobi sweeps\n", p, q, batch, out.sweeps);
+  if (debug_svd()) fprintf(stderr, "[ttn] svd_left %d x %d batch %d: %d Jacobi sweeps\n", p, q, batch, out.sweeps);
   // singular values to the host, sorted descending per batch element
   std::vector<double> h((size_t)k * batch);
   TTN_CUDA(cudaMemcpyAsync(h.data(), out.norms.p, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, ctx().stream));
