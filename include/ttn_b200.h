@@ -26,6 +26,7 @@
 #ifndef TTN_B200_H
 #define TTN_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus

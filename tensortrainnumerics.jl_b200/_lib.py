@@ -45,6 +45,7 @@ class TdvpParams(C.Structure):
 
 
 _lib = None
+_signatures = {}
 _inited_device = None
 
 
@@ -107,6 +108,8 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = C.c_int
+    global _signatures
+    _signatures = {k: list(v) for k, v in sig.items()}
     lib.ttn_last_error.restype = C.c_char_p
     lib.ttn_last_error.argtypes = []
     lib.ttn_launch_count.restype = C.c_longlong
@@ -115,6 +118,12 @@ def load():
     lib.ttn_stream.argtypes = []
     _lib = lib
     return lib
+
+
+def signatures():
+    """name -> ctypes argument list of every bound entry point (tests compare the arities with include/ttn_b200.h)."""
+    load()
+    return dict(_signatures)
 
 
 def check(status: int):

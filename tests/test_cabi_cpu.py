@@ -2,6 +2,7 @@
 and the product path fails loudly (no fallback) when no CUDA device is present."""
 import os
 import re
+import sys
 
 import pytest
 
@@ -45,3 +46,28 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".h", ".cpp", ".jl")):
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "ttn_oracle" not in src, f"{f} references the oracle"
+
+
+def test_header_is_plain_c_and_matches_ctypes_table(tmp_path):
+    """`include/ttn_b200.h` must compile as C (the reference-side binding is a plain `ccall`; no C++ or torch types in the
+    signatures), and every function it declares must have a ctypes signature in the host mirror with the same arity."""
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = os.path.join(root, "include", "ttn_b200.h")
+    src = tmp_path / "chk.c"
+    src.write_text('#include "ttn_b200.h"\nint main(void) { ttn_solver_params p; (void)p; return 0; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.dirname(hdr), str(src)])
+    text = re.sub(r"/\*.*?\*/", "", open(hdr).read(), flags=re.S)
+    decls = re.findall(r"\b(?:int|const char\s*\*|void)\s+(ttn_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text)
+    assert len(decls) > 40
+    sys.path.insert(0, root)
+    import ttn_b200 as t
+    table = t._lib.signatures() if hasattr(t._lib, "signatures") else None
+    if table is None:
+        pytest.skip("host mirror does not expose its signature table")
+    for name, args in decls:
+        if name not in table:
+            continue                      # entry points the Python mirror does not bind (bound from Julia only)
+        nargs = 0 if args.strip() in ("", "void") else len([a for a in args.split(",")])
+        assert len(table[name]) == nargs, (name, nargs, len(table[name]))
