@@ -245,6 +245,21 @@ function _eigsolve(sym::Symbol, A, x0, p, keep, cap)
     return E[1:nE[]], download(DevTT(out[])), rh[1:nE[]]
 end
 
+# als_eigsolve(A, tt_start; sweep_schedule, rmax_schedule, ...)    src/solvers/als.jl:251-321 (noise_schedule == 0 only)
+function als_eigsolve(A, tt_start; sweep_schedule = [2], rmax_schedule = [maximum(tt_start.ttv_rks)],
+                      noise_schedule = zeros(length(rmax_schedule)), it_solver = false, itslv_thresh = 1024, maxiter = 200,
+                      linsolv_tol = 1.0e-8)
+    all(iszero, noise_schedule) || error("noise_schedule != 0 draws from the host RNG and is not on the device path")
+    p, keep = params(; sweep_schedule, rmax_schedule, linsolv_maxiter = maxiter, linsolv_tol, krylovdim = 30)
+    Ad, xd = upload(A), upload(tt_start)
+    cap = 2 * tt_start.N * (sweep_schedule[end] + 1) + 8
+    out, nE, E = Ref{Ptr{Cvoid}}(C_NULL), Ref{Cint}(0), zeros(Float64, cap)
+    GC.@preserve keep check(ccall((:ttn_als_eigsolve, LIB[]), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Ref{SolverParams}, Ptr{Ptr{Cvoid}}, Ptr{Float64}, Cint, Ptr{Cint}),
+        Ad.h, xd.h, Ref(p), out, E, cap, nE))
+    return E[1:nE[]], download(DevTT(out[]))
+end
+
 # als_gen_eigsolv(A, S, tt_start; ...)                            src/solvers/als.jl:344-440
 function als_gen_eigsolv(A, S, tt_start; sweep_schedule = [2], rmax_schedule = [maximum(tt_start.ttv_rks)], tol = 1.0e-10,
                          it_solver = false, itslv_thresh = 2500)
@@ -340,6 +355,8 @@ function override!()
         als_linsolve(A::TToperator, b::TTvector, x0::TTvector; kwargs...) = $(als_linsolve)(A, b, x0; kwargs...)
         mals_linsolve(A::TToperator, b::TTvector, x0::TTvector; kwargs...) = $(mals_linsolve)(A, b, x0; kwargs...)
         dmrg_linsolve(A::TToperator, b::TTvector, x0::TTvector; kwargs...) = $(dmrg_linsolve)(A, b, x0; kwargs...)
+        als_eigsolve(A::TToperator, x0::TTvector; kwargs...) = $(als_eigsolve)(A, x0; kwargs...)
+        als_gen_eigsolv(A::TToperator, S::TToperator, x0::TTvector; kwargs...) = $(als_gen_eigsolv)(A, S, x0; kwargs...)
         dmrg_eigsolve(A::TToperator, x0::TTvector; kwargs...) = $(dmrg_eigsolve)(A, x0; kwargs...)
         mals_eigsolve(A::TToperator, x0::TTvector; kwargs...) = $(mals_eigsolve)(A, x0; kwargs...)
         tdvp(H::TToperator, u0::TTvector, steps::Vector{Float64}; kwargs...) = $(tdvp)(H, u0, steps; kwargs...)

@@ -71,3 +71,53 @@ def test_header_is_plain_c_and_matches_ctypes_table(tmp_path):
             continue                      # entry points the Python mirror does not bind (bound from Julia only)
         nargs = 0 if args.strip() in ("", "void") else len([a for a in args.split(",")])
         assert len(table[name]) == nargs, (name, nargs, len(table[name]))
+
+
+def test_julia_shim_ccall_arities_match_header():
+    """Julia is not in the build image, so the `ccall` stubs of `TTNB200.jl` cannot be executed here; their argument-type
+    tuples are checked statically against the arities declared in `include/ttn_b200.h`."""
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "ttn_b200.h")).read(), flags=re.S)
+    decls = {n: (0 if a.strip() in ("", "void") else len(a.split(",")))
+             for n, a in re.findall(r"\b(?:int|const char\s*\*|void)\s+(ttn_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text)}
+    jl = open(os.path.join(ROOT, "tensortrainnumerics.jl_b200", "julia", "TTNB200.jl")).read()
+    calls = re.findall(r"ccall\(\(\s*:?(\w+)\s*,\s*LIB(?:\[\])?\s*\)\s*,\s*\w+\s*,\s*\(([^()]*)\)", jl)
+    assert len(calls) >= 20
+    seen = set()
+    for name, types in calls:
+        if name == "sym":                 # generic helper: the symbol is a variable, checked through its callers' tables
+            continue
+        assert name in decls, f"{name} is called from the Julia shim but not declared in the header"
+        n = len([x for x in types.split(",") if x.strip()])
+        assert n == decls[name], (name, n, decls[name])
+        seen.add(name)
+    assert {"ttn_ttv_upload", "ttn_compress", "ttn_apply", "ttn_swap_sites", "ttn_als_gen_eigsolv"} <= seen
+
+
+def test_param_struct_layouts_agree_across_bindings():
+    """`ttn_solver_params` / `ttn_tdvp_params`: the field order of the C header, of the Julia `struct`s and of the ctypes
+    mirrors must be identical (the structs are passed by pointer and read field by field)."""
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "ttn_b200.h")).read(), flags=re.S)
+    jl = open(os.path.join(ROOT, "tensortrainnumerics.jl_b200", "julia", "TTNB200.jl")).read()
+    sys.path.insert(0, ROOT)
+    import ttn_b200 as t
+
+    def c_fields(name):
+        body = re.search(r"typedef struct \{((?:(?!typedef struct).)*?)\}\s*" + name + r"\s*;", hdr, flags=re.S).group(1)
+        out = []
+        for stmt in body.split(";"):
+            stmt = stmt.strip()
+            if not stmt:
+                continue
+            for part in stmt.split(","):
+                out.append(re.findall(r"[A-Za-z_][A-Za-z0-9_]*", part)[-1])
+        return out
+
+    def jl_fields(name):
+        body = re.search(r"struct " + name + r"\n(.*?)\nend", jl, flags=re.S).group(1)
+        return [ln.split("::")[0].strip() for ln in body.splitlines() if "::" in ln]
+
+    for cname, jname, pycls in (("ttn_solver_params", "SolverParams", t._lib.SolverParams),
+                                ("ttn_tdvp_params", "TdvpParams", t._lib.TdvpParams)):
+        cf = c_fields(cname)
+        assert cf == jl_fields(jname), (cname, cf, jl_fields(jname))
+        assert cf == [f[0] for f in pycls._fields_], (cname, cf, [f[0] for f in pycls._fields_])
