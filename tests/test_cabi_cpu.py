@@ -48,6 +48,24 @@ def test_product_does_not_import_oracle():
                 assert "ttn_oracle" not in src, f"{f} references the oracle"
 
 
+def _c_kind(decl):
+    """scalar class of one C parameter declaration of the header"""
+    if "*" in decl or re.match(r"\s*(const\s+)?ttn_(ttv|tto|matvec|shard_matvec)\b", decl):
+        return "ptr"
+    words = re.findall(r"[A-Za-z_][A-Za-z0-9_]*", decl)
+    for w, k in (("int64_t", "i64"), ("size_t", "size"), ("double", "f64"), ("int", "i32")):
+        if w in words[:-1] or (len(words) == 1 and w == words[0]):
+            return k
+    raise AssertionError("unclassified C parameter: " + decl)
+
+
+def _ctypes_kind(tp):
+    import ctypes as C
+    if tp in (C.c_void_p, C.c_char_p) or hasattr(tp, "contents") or getattr(tp, "_type_", None) is not None and not isinstance(tp._type_, str):
+        return "ptr"
+    return {C.c_int: "i32", C.c_int64: "i64", C.c_longlong: "i64", C.c_double: "f64", C.c_size_t: "size"}[tp]
+
+
 def test_header_is_plain_c_and_matches_ctypes_table(tmp_path):
     """`include/ttn_b200.h` must compile as C (the reference-side binding is a plain `ccall`; no C++ or torch types in the
     signatures), and every function it declares must have a ctypes signature in the host mirror with the same arity."""
@@ -71,6 +89,8 @@ def test_header_is_plain_c_and_matches_ctypes_table(tmp_path):
             continue                      # entry points the Python mirror does not bind (bound from Julia only)
         nargs = 0 if args.strip() in ("", "void") else len([a for a in args.split(",")])
         assert len(table[name]) == nargs, (name, nargs, len(table[name]))
+        for pos, (carg, ctype) in enumerate(zip([a.strip() for a in args.split(",")] if nargs else [], table[name])):
+            assert _c_kind(carg) == _ctypes_kind(ctype), (name, pos, carg, ctype)
 
 
 def test_julia_shim_ccall_arities_match_header():
@@ -78,6 +98,8 @@ def test_julia_shim_ccall_arities_match_header():
     tuples are checked statically against the arities declared in `include/ttn_b200.h`."""
     text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "ttn_b200.h")).read(), flags=re.S)
     decls = {n: (0 if a.strip() in ("", "void") else len(a.split(",")))
+             for n, a in re.findall(r"\b(?:int|const char\s*\*|void)\s+(ttn_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text)}
+    cargs = {n: ([x.strip() for x in a.split(",")] if a.strip() not in ("", "void") else [])
              for n, a in re.findall(r"\b(?:int|const char\s*\*|void)\s+(ttn_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text)}
     jl = open(os.path.join(ROOT, "tensortrainnumerics.jl_b200", "julia", "TTNB200.jl")).read()
     calls = re.findall(r"ccall\(\(\s*:?(\w+)\s*,\s*LIB(?:\[\])?\s*\)\s*,\s*\w+\s*,\s*\(([^()]*)\)", jl)
@@ -87,8 +109,12 @@ def test_julia_shim_ccall_arities_match_header():
         if name == "sym":                 # generic helper: the symbol is a variable, checked through its callers' tables
             continue
         assert name in decls, f"{name} is called from the Julia shim but not declared in the header"
-        n = len([x for x in types.split(",") if x.strip()])
-        assert n == decls[name], (name, n, decls[name])
+        jt = [x.strip() for x in types.split(",") if x.strip()]
+        assert len(jt) == decls[name], (name, len(jt), decls[name])
+        for pos, (carg, jtype) in enumerate(zip(cargs[name], jt)):
+            kind = "ptr" if jtype.startswith(("Ptr{", "Ref{")) else {"Cint": "i32", "Int64": "i64", "Float64": "f64",
+                                                                      "Cdouble": "f64", "Csize_t": "size"}[jtype]
+            assert _c_kind(carg) == kind, (name, pos, carg, jtype)
         seen.add(name)
     assert {"ttn_ttv_upload", "ttn_compress", "ttn_apply", "ttn_swap_sites", "ttn_als_gen_eigsolv"} <= seen
 
