@@ -78,6 +78,57 @@ def main():
     s = np.logspace(0, -9, 10)
     g["svd_A"] = (U * s) @ Vv.T
     g["svd_s"] = s
+    # 8. hadamard_ttm (tt_operations.jl:399-422), tol 1e-12: result against the element-wise product of the dense tensors
+    rng = np.random.default_rng(8)
+    hx = o.rand_tt((2, 3, 2, 2, 2, 2), 3, rng=rng); hy = o.rand_tt((2, 3, 2, 2, 2, 2), 2, rng=rng)
+    hz = o.hadamard_ttm(hx, hy, tol=1e-12)
+    href = o.ttv_to_tensor(hx) * o.ttv_to_tensor(hy)
+    assert np.linalg.norm(o.ttv_to_tensor(hz) - href) / np.linalg.norm(href) < 1e-11
+    cores_to_dict("had_x", hx, g); cores_to_dict("had_y", hy, g)
+    g["had_dims"] = np.array(hx.ttv_dims)
+    g["had_out"] = dense(hz)
+    g["had_out_rks"] = np.array(hz.ttv_rks)
+    # 9. reorder serial -> interleaved (qtt_tools.jl:731-774), 2 dims x 3 bits: the dense tensor with its axes permuted
+    rx = o.rand_tt((2,) * 6, 4, rng=np.random.default_rng(9))
+    ry = o.reorder(rx, 2, 3, "serial", "interleaved")
+    axes = [0] * 6
+    for src, tgt in enumerate(o.reorder_perm(2, 3, "serial")):
+        axes[tgt] = src
+    assert np.allclose(o.ttv_to_tensor(ry), np.transpose(o.ttv_to_tensor(rx), axes), atol=1e-12)
+    cores_to_dict("reo_x", rx, g)
+    g["reo_out"] = dense(ry)
+    g["reo_out_rks"] = np.array(ry.ttv_rks)
+    # 10. to_qtt (qtt_tools.jl:254-310): (8, 4, 6) -> (2, 2, 2, 4, 3, 2)
+    qx = o.rand_tt((8, 4, 6), 3, rng=np.random.default_rng(10))
+    qq = o.to_qtt(qx, [[2, 2, 2], [4], [3, 2]])
+    assert np.allclose(o.ttv_to_tensor(qq), o.ttv_to_tensor(qx).reshape(qq.ttv_dims), atol=1e-12)
+    cores_to_dict("qtt_x", qx, g)
+    g["qtt_dims"] = np.array(qx.ttv_dims)
+    g["qtt_out"] = dense(qq)
+    g["qtt_out_rks"] = np.array(qq.ttv_rks)
+    # 11. als_gen_eigsolv (als.jl:344-440): energies of every local solve, rank-2 start (full-rank unfoldings), and the
+    #     lowest eigenvalue of the dense pencil the sweeps converge to
+    import scipy.linalg as sla
+    d = 5
+    Ag = o.tto_add(o.laplace_dd(d), o.tto_scale(2.0, o.id_tto(d)))
+    Sg = o.tto_add(o.id_tto(d), o.tto_scale(-0.15, o.tto_add(o.laplace_dd(d), o.tto_scale(-2.0, o.id_tto(d)))))
+    gx0 = o.rand_tt((2,) * d, 2, rng=np.random.default_rng(11), normalise=True)
+    Eg, xg = o.als_gen_eigsolv(Ag, Sg, gx0, sweep_schedule=[4], rmax_schedule=[2])
+    lam = sla.eigh(o.tto_to_matrix(Ag), o.tto_to_matrix(Sg), eigvals_only=True)[0]
+    assert Eg[-1] >= lam - 1e-12 and Eg[-1] - lam < 1e-3          # rank 2 is not exact for this pencil, but close
+    cores_to_dict("gen_x0", gx0, g)
+    g["gen_E"] = np.array(Eg)
+    g["gen_lam"] = np.array(lam)
+    # 12. examples/dft.jl:5-25: spectrum of a 12-mode signal through A*x + tt_compress!(., 100) with the rank-51 QFT operator
+    d, K, r = 10, 50, 12
+    rng = np.random.default_rng(1234)
+    coeffs = rng.standard_normal(r) + 1j * rng.standard_normal(r)
+    f = lambda x: np.sum(coeffs * np.exp(2j * np.pi * np.arange(r) * x))
+    F, fx = o.fourier_qtto(d, K=K, sign=-1.0, normalize=True), o.function_to_qtt_uniform(f, d)
+    spec = o.matricize(o.tt_compress(o.apply(F, fx), 100), d)
+    assert np.linalg.norm(spec[:r] - 32.0 * coeffs) / (32.0 * np.linalg.norm(coeffs)) < 1e-8
+    g["dft_coeffs"] = coeffs
+    g["dft_spec"] = spec
     np.savez_compressed(os.path.join(HERE, "hotpath_golden.npz"), **g)
     print("wrote", os.path.join(HERE, "hotpath_golden.npz"), len(g), "arrays")
 

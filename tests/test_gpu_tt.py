@@ -246,9 +246,10 @@ def test_cuda_matches_golden():
     import ttn_b200 as t
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hotpath_golden.npz"))
 
-    def tt_from(prefix, d):
+    def tt_from(prefix, d, dims=None):
         rks = [int(v) for v in g[prefix + "_rks"]]
-        return o.TTvector(d, [np.asfortranarray(g[f"{prefix}_core{k}"]) for k in range(d)], (2,) * d, rks, [0] * d)
+        dims = (2,) * d if dims is None else tuple(int(v) for v in dims)
+        return o.TTvector(d, [np.asfortranarray(g[f"{prefix}_core{k}"]) for k in range(d)], dims, rks, [0] * d)
 
     def dense(x):
         return o.ttv_to_tensor(x).reshape(-1)
@@ -277,6 +278,21 @@ def test_cuda_matches_golden():
     assert abs(E[-1] - float(g["heis_e0"])) < 1e-9 * abs(float(g["heis_e0"]))
     U, s, Vt = t.svdtrunc(np.asfortranarray(g["svd_A"]))
     assert np.abs(s[:10] - g["svd_s"]).max() < 1e-12 and np.abs(s[10:]).max() < 1e-12
+    # cases 8-12: hadamard_ttm, reorder, to_qtt, als_gen_eigsolv, the QFT example
+    hz = t.hadamard_ttm(tt_from("had_x", 6, g["had_dims"]), tt_from("had_y", 6, g["had_dims"]), tol=1e-12)
+    assert list(hz.ttv_rks) == [int(v) for v in g["had_out_rks"]] and rel(dense(hz), g["had_out"]) < 1e-10
+    ry = t.reorder(tt_from("reo_x", 6), 2, 3, "serial", "interleaved")
+    assert list(ry.ttv_rks) == [int(v) for v in g["reo_out_rks"]] and rel(dense(ry), g["reo_out"]) < 1e-10
+    qq = t.to_qtt(tt_from("qtt_x", 3, g["qtt_dims"]), [[2, 2, 2], [4], [3, 2]])
+    assert list(qq.ttv_rks) == [int(v) for v in g["qtt_out_rks"]] and rel(dense(qq), g["qtt_out"]) < 1e-10
+    Ag = o.tto_add(o.laplace_dd(5), o.tto_scale(2.0, o.id_tto(5)))
+    Sg = o.tto_add(o.id_tto(5), o.tto_scale(-0.15, o.tto_add(o.laplace_dd(5), o.tto_scale(-2.0, o.id_tto(5)))))
+    Eg, _ = t.als_gen_eigsolv(Ag, Sg, tt_from("gen_x0", 5), sweep_schedule=[4], rmax_schedule=[2])
+    assert len(Eg) == len(g["gen_E"]) and np.abs(Eg - g["gen_E"]).max() < 1e-9
+    coeffs = g["dft_coeffs"]
+    f = lambda xx: np.sum(coeffs * np.exp(2j * np.pi * np.arange(12) * xx))
+    F, fx = o.fourier_qtto(10, K=50, sign=-1.0, normalize=True), o.function_to_qtt_uniform(f, 10)
+    assert rel(o.matricize(t.tt_compress_(t.apply(F, fx), 100), 10), g["dft_spec"]) < 1e-10
 
 
 @pytest.mark.gpu

@@ -282,9 +282,10 @@ def _golden():
     return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hotpath_golden.npz"))
 
 
-def _tt_from(g, prefix, d):
+def _tt_from(g, prefix, d, dims=None):
     rks = [int(v) for v in g[prefix + "_rks"]]
-    return o.TTvector(d, [g[f"{prefix}_core{k}"] for k in range(d)], (2,) * d, rks, [0] * d)
+    dims = (2,) * d if dims is None else tuple(int(v) for v in dims)
+    return o.TTvector(d, [g[f"{prefix}_core{k}"] for k in range(d)], dims, rks, [0] * d)
 
 
 def test_oracle_reproduces_golden():
@@ -306,6 +307,21 @@ def test_oracle_reproduces_golden():
     U, S, Vt = o.svdtrunc(g["svd_A"])
     sv = np.diag(np.asarray(S)) if np.ndim(S) == 2 else np.asarray(S)
     assert np.abs(sv[:10] - g["svd_s"]).max() < 1e-14 and np.abs(sv[10:]).max() < 1e-14
+    # site surgery, generalized ALS and the QFT example (cases 8-12 of make_golden.py)
+    rel = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)
+    hz = o.hadamard_ttm(_tt_from(g, "had_x", 6, g["had_dims"]), _tt_from(g, "had_y", 6, g["had_dims"]), tol=1e-12)
+    assert list(hz.ttv_rks) == [int(v) for v in g["had_out_rks"]] and rel(o.ttv_to_tensor(hz).reshape(-1), g["had_out"]) < 1e-12
+    ry = o.reorder(_tt_from(g, "reo_x", 6), 2, 3, "serial", "interleaved")
+    assert list(ry.ttv_rks) == [int(v) for v in g["reo_out_rks"]] and rel(o.ttv_to_tensor(ry).reshape(-1), g["reo_out"]) < 1e-12
+    qq = o.to_qtt(_tt_from(g, "qtt_x", 3, g["qtt_dims"]), [[2, 2, 2], [4], [3, 2]])
+    assert list(qq.ttv_rks) == [int(v) for v in g["qtt_out_rks"]] and rel(o.ttv_to_tensor(qq).reshape(-1), g["qtt_out"]) < 1e-12
+    Ag = o.tto_add(o.laplace_dd(5), o.tto_scale(2.0, o.id_tto(5)))
+    Sg = o.tto_add(o.id_tto(5), o.tto_scale(-0.15, o.tto_add(o.laplace_dd(5), o.tto_scale(-2.0, o.id_tto(5)))))
+    Eg, _ = o.als_gen_eigsolv(Ag, Sg, _tt_from(g, "gen_x0", 5), sweep_schedule=[4], rmax_schedule=[2])
+    assert np.abs(Eg - g["gen_E"]).max() < 1e-11
+    d, r, coeffs, F, x = _dft_example()
+    assert np.array_equal(coeffs, g["dft_coeffs"])
+    assert rel(o.matricize(o.tt_compress(o.apply(F, x), 100), d), g["dft_spec"]) < 1e-11
 
 
 def test_hadamard_vs_dense():
