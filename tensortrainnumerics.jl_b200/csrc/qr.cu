@@ -138,6 +138,142 @@ __global__ void __launch_bounds__(PANEL_T) qr_panel_kernel(T* __restrict__ A, in
   }
 }
 
+// Tall panels (one matrix, m - j0 >= 512): the same NB-column panel factorisation with the working set in shared memory.
+// The unblocked kernel above streams the (m - j0) x NB panel through one SM three times per column (~8.8 us per column at
+// m = 2048: single-SM L2 bandwidth); here the panel is processed in sub-panels of SW columns that fit in shared memory
+// (SW * (m - j0) elements): a sub-panel is loaded once, receives the reflectors of the earlier sub-panels of this panel
+// (read from global memory, where they were written back), is factored column by column entirely in shared memory, and is
+// written back once.  Requires the whole panel inside min(m, n) (the host checks).
+constexpr int PSW_MAX = 8;
+template <class T, int NB>
+__global__ void __launch_bounds__(PANEL_T) qr_panel_smem_kernel(T* __restrict__ A, int m, int64_t lda, T* __restrict__ tau,
+                                                                int j0, int SW, int64_t bA, int64_t btau) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* Ab = A + blockIdx.x * bA;
+  T* taub = tau + blockIdx.x * btau;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = PANEL_T / 32;
+  const int L = m - j0;                          // local row i' = i - j0
+  T* Ps = reinterpret_cast<T*>(smem_raw);        // [SW][L]
+  __shared__ double s_red[NW];
+  __shared__ T s_part[NW][PSW_MAX];
+  __shared__ T s_w[PSW_MAX];
+  __shared__ T s_scal, s_tau;
+
+  for (int c0 = j0; c0 < j0 + NB; c0 += SW) {
+    const int sw = (c0 + SW <= j0 + NB) ? SW : j0 + NB - c0;
+    for (int q = 0; q < sw; ++q)
+      for (int il = tid; il < L; il += PANEL_T) Ps[(size_t)q * L + il] = Ab[(j0 + il) + (int64_t)(c0 + q) * lda];
+    __syncthreads();
+    // reflectors of the earlier sub-panels: Ps <- H_r^H Ps,  r = j0 .. c0-1
+    for (int r = j0; r < c0; ++r) {
+      const T* vcol = Ab + (int64_t)r * lda;
+      const T tc = t_conj(taub[r]);
+      T acc[PSW_MAX];
+#pragma unroll
+      for (int q = 0; q < PSW_MAX; ++q) acc[q] = t_zero<T>();
+      for (int il = tid; il < L; il += PANEL_T) {
+        const int gi = j0 + il;
+        if (gi < r) continue;
+        const T vc = (gi == r) ? t_one<T>() : t_conj(vcol[gi]);
+#pragma unroll
+        for (int q = 0; q < PSW_MAX; ++q)
+          if (q < sw) t_fma(acc[q], vc, Ps[(size_t)q * L + il]);
+      }
+#pragma unroll
+      for (int q = 0; q < PSW_MAX; ++q)
+        if (q < sw) {
+          const T sm = wsum(acc[q]);
+          if (lane == 0) s_part[warp][q] = sm;
+        }
+      __syncthreads();
+      if (tid < sw) {
+        T sm = s_part[0][tid];
+        for (int w = 1; w < NW; ++w) sm = t_add(sm, s_part[w][tid]);
+        s_w[tid] = t_mul(tc, sm);
+      }
+      __syncthreads();
+      for (int il = tid; il < L; il += PANEL_T) {
+        const int gi = j0 + il;
+        if (gi < r) continue;
+        const T vi = (gi == r) ? t_one<T>() : vcol[gi];
+#pragma unroll
+        for (int q = 0; q < PSW_MAX; ++q)
+          if (q < sw) {
+            T* p2 = Ps + (size_t)q * L + il;
+            *p2 = t_sub(*p2, t_mul(s_w[q], vi));
+          }
+      }
+      // s_part / s_w of the next reflector are rewritten only after the two barriers of its own reduction
+    }
+    __syncthreads();
+    // factor the sub-panel in shared memory
+    for (int qc = 0; qc < sw; ++qc) {
+      const int c = c0 + qc, cl = c - j0;        // global column / local diagonal row
+      T* col = Ps + (size_t)qc * L;
+      double p = 0.0;
+      for (int il = cl + 1 + tid; il < L; il += PANEL_T) p += t_abs2(col[il]);
+      p = wsum(p);
+      if (lane == 0) s_red[warp] = p;
+      __syncthreads();
+      if (tid == 0) {
+        double xn2 = 0.0;
+        for (int w = 0; w < NW; ++w) xn2 += s_red[w];
+        T beta, tv, sc;
+        larfg(col[cl], xn2, beta, tv, sc);
+        taub[c] = tv;
+        s_tau = tv;
+        s_scal = sc;
+        col[cl] = beta;
+      }
+      __syncthreads();
+      const T scal = s_scal;
+      const T tauc = t_conj(s_tau);
+      const int nrem = sw - 1 - qc;
+      T acc[PSW_MAX];
+#pragma unroll
+      for (int q = 0; q < PSW_MAX; ++q) acc[q] = t_zero<T>();
+      for (int il = cl + tid; il < L; il += PANEL_T) {
+        T vi;
+        if (il == cl) vi = t_one<T>();
+        else { vi = t_mul(col[il], scal); col[il] = vi; }
+        const T vc = t_conj(vi);
+#pragma unroll
+        for (int q = 0; q < PSW_MAX; ++q)
+          if (q < nrem) t_fma(acc[q], vc, Ps[(size_t)(qc + 1 + q) * L + il]);
+      }
+      if (nrem > 0) {
+#pragma unroll
+        for (int q = 0; q < PSW_MAX; ++q)
+          if (q < nrem) {
+            const T sm = wsum(acc[q]);
+            if (lane == 0) s_part[warp][q] = sm;
+          }
+        __syncthreads();
+        if (tid < nrem) {
+          T sm = s_part[0][tid];
+          for (int w = 1; w < NW; ++w) sm = t_add(sm, s_part[w][tid]);
+          s_w[tid] = t_mul(tauc, sm);
+        }
+        __syncthreads();
+        for (int il = cl + tid; il < L; il += PANEL_T) {
+          const T vi = (il == cl) ? t_one<T>() : col[il];
+#pragma unroll
+          for (int q = 0; q < PSW_MAX; ++q)
+            if (q < nrem) {
+              T* p2 = Ps + (size_t)(qc + 1 + q) * L + il;
+              *p2 = t_sub(*p2, t_mul(s_w[q], vi));
+            }
+        }
+      }
+      __syncthreads();
+    }
+    for (int q = 0; q < sw; ++q)
+      for (int il = tid; il < L; il += PANEL_T) Ab[(j0 + il) + (int64_t)(c0 + q) * lda] = Ps[(size_t)q * L + il];
+    __syncthreads();                             // the next sub-panel reads these reflectors back from global memory
+  }
+}
+
 // Applies reflectors j in [jlo, jhi) of (A, tau) to columns [c0, c0+nc) of C, rows >= jlo.
 //   trans = true : C <- H_{jhi-1}^H ... H_{jlo}^H C   (forward order, conj(tau))   -> Q^H C
 //   trans = false: C <- H_{jlo} ... H_{jhi-1} C        (backward order, tau)        -> Q C
@@ -253,7 +389,25 @@ template <class T>
 void qr_factor(T* A, int m, int n, int64_t lda, T* tau, int batch, int64_t bA, int64_t btau) {
   const int k = std::min(m, n);
   if (k <= 0 || batch <= 0) return;
+  static const bool smem_panel_env = !(getenv("TTN_QR_SMEM_PANEL") && atoi(getenv("TTN_QR_SMEM_PANEL")) == 0);
+  static bool attr_done = false;
   for (int j0 = 0; j0 < k; j0 += PANEL_NB) {
+    // tall single matrix, whole panel inside min(m, n): shared-memory sub-panel kernel
+    int SW = 0;
+    if (smem_panel_env && batch == 1 && m - j0 >= 512 && j0 + PANEL_NB <= k)
+      for (int c : {8, 4, 2})
+        if (sizeof(T) * (size_t)c * (m - j0) <= 200 * 1024) { SW = c; break; }
+    if (SW > 0) {
+      if (!attr_done) {
+        TTN_CUDA(cudaFuncSetAttribute(qr_panel_smem_kernel<T, PANEL_NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_done = true;
+      }
+      ProfScope prof_scope_(KF_QR_PANEL);
+      qr_panel_smem_kernel<T, PANEL_NB><<<1, PANEL_T, sizeof(T) * (size_t)SW * (m - j0), ctx().stream>>>(A, m, lda, tau, j0, SW, bA,
+                                                                                                       btau);
+      TTN_CHECK_LAUNCH();
+      ctx().launches++;
+    } else
     for (int b0 = 0; b0 < batch; b0 += 65535) {
       const int nb = std::min(65535, batch - b0);
       ProfScope prof_scope_(KF_QR_PANEL);

@@ -279,3 +279,21 @@ def test_svdtrunc_degenerate_multiplets(shape):
     assert np.abs(sg - s).max() < 1e-12
     assert relerr((Ug * sg) @ Vtg, A) < 1e-12
     assert np.abs(Ug.T @ Ug - np.eye(k)).max() < 1e-11
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("shape", [(1500, 700), (2100, 530), (600, 600), (5000, 96)])
+def test_qr_tall_single_matrix_smem_panels(shape, cplx):
+    """Householder QR of tall single matrices (the shared-memory sub-panel kernel of qr.cu: sub-panels of 8 / 4 / 2 columns
+    depending on the panel height and element size, then the unblocked kernel once fewer than 512 rows remain)."""
+    import ttn_b200 as t
+    rng = np.random.default_rng(shape[0] + shape[1])
+    m, n = shape
+    A = rng.standard_normal((m, n)) + (1j * rng.standard_normal((m, n)) if cplx else 0.0)
+    A = np.asfortranarray(A * np.logspace(0, -6, n)[None, :])            # graded columns
+    Q, R = t.qr_thin(A)
+    k = min(m, n)
+    assert np.abs(np.tril(R, -1)).max() == 0.0
+    assert relerr(Q @ R, A) < 1e-13
+    assert np.abs(Q.conj().T @ Q - np.eye(k)).max() < 1e-12
