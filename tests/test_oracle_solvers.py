@@ -260,3 +260,34 @@ def test_als_gen_eigsolv_vs_dense_and_reference_tests():
     assert abs((v @ Am @ v) / (v @ Sm @ v) - lam) < 1e-9
     E2, x2 = o.als_gen_eigsolv(spd_op(3, 2.0), o.id_tto(3), o.rand_tt((2,) * 3, 1, rng=rng), sweep_schedule=[1, 2], rmax_schedule=[1, 2])
     assert max(x2.ttv_rks) <= 2 and np.all(np.isfinite(E2))                     # test_als.jl:184-197
+
+
+def test_reference_property_tests_of_the_solver_drivers():
+    """Ports of the remaining loose property tests of the reference's solver test files, run on the oracle:
+    test_mals.jl:55-77 (rmax respected; looser tol never needs more than 2 extra ranks), test_dmrg.jl:54-98 (two-stage
+    schedule, identity operator, N = 1 with residual info), test_als.jl:66-78,109-117 (single half sweep; energies do not
+    increase)."""
+    rng = np.random.default_rng(31)
+    d = 4
+    A = spd_op(d, 5.0)
+    b = o.rand_tt((2,) * d, 2, rng=rng)
+    x = o.mals_linsolve(A, b, o.rand_tt((2,) * d, 1, rng=rng), tol=1e-10, rmax=4)
+    assert max(x.ttv_rks) <= 4
+    A3 = spd_op(d, 3.0)
+    x0 = o.rand_tt((2,) * d, 2, rng=rng)
+    x_loose = o.mals_linsolve(A3, b, x0, tol=1e-2, rmax=8)
+    x_tight = o.mals_linsolve(A3, b, x0, tol=0.0, rmax=8)
+    assert max(x_loose.ttv_rks) <= max(x_tight.ttv_rks) + 2
+    y = o.dmrg_linsolve(A, b, o.rand_tt((2,) * d, 1, rng=rng), N=2, sweep_schedule=[2, 4], rmax_schedule=[2, 8])
+    assert tuple(y.ttv_dims) == tuple(b.ttv_dims)
+    b1 = o.rand_tt((2,) * d, 1, rng=rng)
+    z = o.dmrg_linsolve(o.id_tto(d), b1, o.rand_tt((2,) * d, 1, rng=rng), N=2, sweep_schedule=[4], rmax_schedule=[4])
+    assert np.linalg.norm(dv(z) - dv(b1)) / np.linalg.norm(dv(b1)) < 0.05
+    A5 = spd_op(3, 5.0)
+    w, info = o.dmrg_linsolve(A5, o.rand_tt((2,) * 3, 1, rng=rng), o.rand_tt((2,) * 3, 1, rng=rng), N=1, sweep_schedule=[2],
+                              rmax_schedule=[2], return_info=True)
+    assert np.isfinite(info["residual"])
+    v = o.als_linsolve(A5, o.rand_tt((2,) * 3, 2, rng=rng), o.rand_tt((2,) * 3, 2, rng=rng), sweep_count=1)
+    assert tuple(v.ttv_dims) == (2, 2, 2)
+    E, _ = o.als_eigsolve(spd_op(d, 2.0), o.rand_tt((2,) * d, 2, rng=rng, normalise=True), sweep_schedule=[4], rmax_schedule=[2])
+    assert E[-1] <= E[0] + 1e-8
