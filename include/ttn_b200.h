@@ -213,6 +213,12 @@ int ttn_svdtrunc_host(int dtype, int m, int n, const void* A, int64_t max_bond, 
                       int* r_out);
 /* thin QR of a host matrix (column-major m x n): Q (m x k), R (k x n), k = min(m,n) */
 int ttn_qr_host(int dtype, int m, int n, const void* A, void* Q, void* R);
+/* The truncation rules of the path on a host spectrum `s` (sorted descending, `len` values); pure host code, callable without
+ * a device.  rule 0: `_svdtrunc` tail-norm rule + `max_bond` cap (src/tt_cross_interpolation.jl:149-166); 1: `sv_trunc`
+ * (src/solvers/mals.jl:42-56), number of retained values; 2: `cut_off_index` (src/solvers/dmrg.jl:179-185); 3: relative
+ * threshold `s_j > tol * s_1` (src/qtt_tools.jl:680-685). */
+int ttn_rank_rule(int rule, const double* s, int len, double tol, int64_t max_bond, int* r);
+
 /* device memory helpers for benchmarks */
 int ttn_dev_alloc(size_t bytes, void** out);
 int ttn_dev_free(void* p);

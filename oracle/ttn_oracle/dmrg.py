@@ -87,7 +87,10 @@ def cut_off_index(s, tol, degen_tol=1e-10):
     """dmrg.jl:179-185."""
     s = np.asarray(s, dtype=float)
     k = int(np.sum(s > np.linalg.norm(s) * tol))
-    while k < len(s) and np.isclose(s[k - 1], s[k], rtol=degen_tol, atol=degen_tol):
+    if k == 0 and len(s) > 0:
+        raise IndexError("cut_off_index: no singular value above the threshold (Julia: BoundsError at s[0])")
+    # Julia's isapprox(x, y; rtol, atol): |x - y| <= max(atol, rtol * max(|x|, |y|))   (not numpy.isclose's atol + rtol |y|)
+    while k < len(s) and abs(s[k - 1] - s[k]) <= max(degen_tol, degen_tol * max(abs(s[k - 1]), abs(s[k]))):
         k += 1
     return k
 

@@ -711,6 +711,25 @@ int ttn_qr_host(int dtype, int m, int n, const void* A, void* Q, void* R) {
   API_END
 }
 
+// The four truncation rules of the path evaluated on a host spectrum (pure host code, no device needed: CPU parity tests).
+int ttn_rank_rule(int rule, const double* s, int len, double tol, int64_t max_bond, int* r) {
+  API_BEGIN
+  ttn_assert(s != nullptr && r != nullptr && len >= 1, TTN_EARG, "rank_rule: bad arguments");
+  switch (rule) {
+    case 0: *r = rank_tailnorm(s, len, max_bond, tol); break;                       // _svdtrunc
+    case 1: *r = std::min(sv_trunc_count(s, len, tol), len); break;                  // sv_trunc (count)
+    case 2: *r = cut_off_index(s, len, tol); break;                                  // cut_off_index
+    case 3: {                                                                        // relative threshold (qtt_tools.jl:680-685)
+      int k = len;
+      if (tol > 0) { k = 0; for (int j = 0; j < len; ++j) k += s[j] > tol * s[0]; k = std::max(1, k); }
+      *r = k;
+      break;
+    }
+    default: ttn_assert(false, TTN_EARG, "rank_rule: unknown rule");
+  }
+  API_END
+}
+
 int ttn_dev_alloc(size_t bytes, void** out) {
   API_BEGIN
   need_init();

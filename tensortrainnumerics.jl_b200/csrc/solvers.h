@@ -67,6 +67,11 @@ void local_linsolve(LocalOp<T>& op, const T* rhs, T* x, int krylovdim, int maxit
 template <class T>
 void lanczos_expm(LocalOp<T>& op, T* x, double tre, double tim, int krylovdim, int maxiter, double tol, KrylovInfo* info);
 
+// rank rules of the core moves (host): `sv_trunc` (mals.jl:42-56, number of retained values) and `cut_off_index`
+// (dmrg.jl:179-185); the `_svdtrunc` tail-norm rule is rank_tailnorm (tt.h)
+int sv_trunc_count(const double* s, int len, double tol);
+int cut_off_index(const double* s, int len, double tol);
+
 // ---------------------------------------------------------------------------------------------------------
 // sweep drivers
 // ---------------------------------------------------------------------------------------------------------

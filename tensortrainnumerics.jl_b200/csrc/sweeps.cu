@@ -33,7 +33,7 @@ static std::vector<int64_t> r_and_d_to_rks(const std::vector<int64_t>& rks, cons
   return out;
 }
 // src/solvers/mals.jl:42-56 (returns the number of retained singular values)
-static int sv_trunc_count(const double* s, int len, double tol) {
+int sv_trunc_count(const double* s, int len, double tol) {
   if (tol == 0.0) return len;
   int i = 0;
   double weight = 0.0, norm2 = 0.0;
@@ -42,7 +42,7 @@ static int sv_trunc_count(const double* s, int len, double tol) {
   return len - i + 1;
 }
 // src/solvers/dmrg.jl:179-185
-static int cut_off_index(const double* s, int len, double tol) {
+int cut_off_index(const double* s, int len, double tol) {
   double n2 = 0.0;
   for (int j = 0; j < len; ++j) n2 += s[j] * s[j];
   const double thr = std::sqrt(n2) * tol;

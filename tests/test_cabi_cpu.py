@@ -147,3 +147,44 @@ def test_param_struct_layouts_agree_across_bindings():
         cf = c_fields(cname)
         assert cf == jl_fields(jname), (cname, cf, jl_fields(jname))
         assert cf == [f[0] for f in pycls._fields_], (cname, cf, [f[0] for f in pycls._fields_])
+
+
+def test_truncation_rules_host_code_vs_oracle():
+    """The four rank rules of the path ("reproduce exactly") are host code in the library; `ttn_rank_rule`
+    evaluates them without a device, so they are compared here with the oracle's restatements on random, flat, decaying and
+    nearly degenerate spectra, on the reference's own KATs (test_dmrg.jl:20-25, mals.jl:42-56) and at the rule boundaries."""
+    import ctypes as C
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ttn_b200 as t
+    import ttn_oracle as o
+    lib = t._lib.load()
+
+    def rule(which, s, tol, max_bond=1 << 62):
+        s = np.ascontiguousarray(s, dtype=np.float64)
+        r = C.c_int()
+        t._lib.check(lib.ttn_rank_rule(which, s.ctypes.data_as(C.POINTER(C.c_double)), len(s), float(tol), int(max_bond), C.byref(r)))
+        return r.value
+
+    rng = np.random.default_rng(5)
+    spectra = [np.sort(rng.random(n))[::-1] for n in (1, 2, 7, 33)]
+    spectra += [np.ones(9), np.logspace(0, -15, 16), np.array([1.0, 1.0 - 5.0e-11, 0.1]),
+                np.array([1.0, 0.5, 0.5 * (1 - 1e-11), 0.5 * (1 - 2e-11), 1e-3]), np.array([1.0, 0.1, 1e-3, 1e-7])]
+    tols = [0.0, 1e-15, 1e-12, 1e-10, 1e-6, 1e-3, 0.3, 0.9]
+    for s in spectra:
+        for tol in tols:
+            for mb in (None, 1, 3):
+                U, sv, Vt = o.svdtrunc(np.diag(s), max_bond=mb, truncerr=tol)
+                assert rule(0, s, tol, (1 << 62) if mb is None else mb) == len(sv), (s, tol, mb)
+            assert rule(1, s, tol) == len(o.sv_trunc(s, tol)), (s, tol)
+            k_ref = int(np.sum(s > np.linalg.norm(s) * tol))
+            if k_ref >= 1:                                   # k = 0 is a BoundsError in the reference
+                assert rule(2, s, tol) == o.cut_off_index(s, tol), (s, tol)
+            thr = max(1, int(np.sum(s > tol * s[0]))) if tol > 0 else len(s)
+            assert rule(3, s, tol) == thr
+    # the reference's KATs
+    s = np.array([1.0, 1.0 - 5.0e-11, 0.1])
+    assert rule(2, s, (1.0 - 2.0e-11) / np.linalg.norm(s)) == 2                      # test/test_dmrg.jl:20-25
+    s = np.array([1.0, 0.1, 1e-3, 1e-7])
+    assert [rule(1, s, tol) for tol in (0.0, 1e-15, 1e-12, 1e-10, 1e-3)] == [4, 4, 3, 3, 2]
