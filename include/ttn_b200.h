@@ -218,6 +218,8 @@ int ttn_qr_host(int dtype, int m, int n, const void* A, void* Q, void* R);
  * (src/solvers/mals.jl:42-56), number of retained values; 2: `cut_off_index` (src/solvers/dmrg.jl:179-185); 3: relative
  * threshold `s_j > tol * s_1` (src/qtt_tools.jl:680-685). */
 int ttn_rank_rule(int rule, const double* s, int len, double tol, int64_t max_bond, int* r);
+/* r_and_d_to_rks(rks, dims; rmax), src/tt_tools.jl:407-425 (host; `rks` and `out` hold d + 1 values) */
+int ttn_r_and_d_to_rks(const int64_t* rks, const int64_t* dims, int d, int64_t rmax, int64_t* out);
 
 /* device memory helpers for benchmarks */
 int ttn_dev_alloc(size_t bytes, void** out);

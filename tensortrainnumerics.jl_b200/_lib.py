@@ -102,6 +102,7 @@ def load():
         "ttn_svdtrunc_host": [C.c_int, C.c_int, C.c_int, vp, C.c_int64, C.c_double, vp, dp, vp, ip],
         "ttn_qr_host": [C.c_int, C.c_int, C.c_int, vp, vp, vp],
         "ttn_rank_rule": [C.c_int, dp, C.c_int, C.c_double, C.c_int64, ip],
+        "ttn_r_and_d_to_rks": [i64p, i64p, C.c_int, C.c_int64, i64p],
         "ttn_dev_alloc": [C.c_size_t, vpp], "ttn_dev_free": [vp], "ttn_h2d": [vp, vp, C.c_size_t],
         "ttn_d2h": [vp, vp, C.c_size_t],
     }

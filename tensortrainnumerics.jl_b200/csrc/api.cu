@@ -730,6 +730,15 @@ int ttn_rank_rule(int rule, const double* s, int len, double tol, int64_t max_bo
   API_END
 }
 
+// r_and_d_to_rks(rks, dims; rmax) on the host (rank schedules of the eigen-solvers); `rks`, `out`: d + 1 values
+int ttn_r_and_d_to_rks(const int64_t* rks, const int64_t* dims, int d, int64_t rmax, int64_t* out) {
+  API_BEGIN
+  ttn_assert(rks && dims && out && d >= 1, TTN_EARG, "r_and_d_to_rks: bad arguments");
+  const std::vector<int64_t> r = r_and_d_to_rks(std::vector<int64_t>(rks, rks + d + 1), std::vector<int64_t>(dims, dims + d), rmax);
+  for (int i = 0; i <= d; ++i) out[i] = r[i];
+  API_END
+}
+
 int ttn_dev_alloc(size_t bytes, void** out) {
   API_BEGIN
   need_init();

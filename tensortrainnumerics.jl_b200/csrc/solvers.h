@@ -71,6 +71,8 @@ void lanczos_expm(LocalOp<T>& op, T* x, double tre, double tim, int krylovdim, i
 // (dmrg.jl:179-185); the `_svdtrunc` tail-norm rule is rank_tailnorm (tt.h)
 int sv_trunc_count(const double* s, int len, double tol);
 int cut_off_index(const double* s, int len, double tol);
+// src/tt_tools.jl:407-425, including the overflow-tolerant `prod(...) > 0` tests (Int64 products wrap around)
+std::vector<int64_t> r_and_d_to_rks(const std::vector<int64_t>& rks, const std::vector<int64_t>& dims, int64_t rmax);
 
 // ---------------------------------------------------------------------------------------------------------
 // sweep drivers

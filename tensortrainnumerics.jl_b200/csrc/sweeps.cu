@@ -20,7 +20,7 @@ static int64_t prod_wrap(const std::vector<int64_t>& v, int lo, int hi) {  // Ju
   return (int64_t)p;
 }
 // src/tt_tools.jl:407-425
-static std::vector<int64_t> r_and_d_to_rks(const std::vector<int64_t>& rks, const std::vector<int64_t>& dims, int64_t rmax) {
+std::vector<int64_t> r_and_d_to_rks(const std::vector<int64_t>& rks, const std::vector<int64_t>& dims, int64_t rmax) {
   std::vector<int64_t> out(rks.size(), 1);
   const int d = (int)dims.size();
   for (int i = 0; i < d; ++i) {

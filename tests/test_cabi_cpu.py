@@ -188,3 +188,26 @@ def test_truncation_rules_host_code_vs_oracle():
     assert rule(2, s, (1.0 - 2.0e-11) / np.linalg.norm(s)) == 2                      # test/test_dmrg.jl:20-25
     s = np.array([1.0, 0.1, 1e-3, 1e-7])
     assert [rule(1, s, tol) for tol in (0.0, 1e-15, 1e-12, 1e-10, 1e-3)] == [4, 4, 3, 3, 2]
+
+
+def test_r_and_d_to_rks_host_code_vs_oracle():
+    """`r_and_d_to_rks` (tt_tools.jl:407-425) with its overflow-tolerant `prod(...) > 0` tests (d = 64 and d = 70 sites of
+    dimension 2 wrap Int64 to 0; mixed dimensions wrap to negative values): library host code against the oracle."""
+    import ctypes as C
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ttn_b200 as t
+    import ttn_oracle as o
+    lib = t._lib.load()
+    rng = np.random.default_rng(6)
+    cases = [((2,) * 4, [8] * 5, 1024), ((2,) * 40, [512] * 41, 64), ((2,) * 64, [1024] * 65, 1024), ((2,) * 70, [300] * 71, 1024),
+             ((3, 5, 7, 2, 4), [1, 9, 50, 50, 9, 1], 20), ((10,) * 19, [4000] * 20, 5000), ((7,) * 23, [77] * 24, 1000)]
+    for _ in range(5):
+        d = int(rng.integers(2, 30))
+        cases.append((tuple(int(v) for v in rng.integers(2, 12, d)), [int(v) for v in rng.integers(1, 400, d + 1)], int(rng.integers(1, 300))))
+    for dims, rks, rmax in cases:
+        d = len(dims)
+        a = (C.c_int64 * (d + 1))(*rks); b = (C.c_int64 * d)(*dims); out = (C.c_int64 * (d + 1))()
+        t._lib.check(lib.ttn_r_and_d_to_rks(a, b, d, rmax, out))
+        assert list(out) == o.r_and_d_to_rks(rks, dims, rmax=rmax), (dims, rks, rmax)
