@@ -211,3 +211,22 @@ def test_r_and_d_to_rks_host_code_vs_oracle():
         a = (C.c_int64 * (d + 1))(*rks); b = (C.c_int64 * d)(*dims); out = (C.c_int64 * (d + 1))()
         t._lib.check(lib.ttn_r_and_d_to_rks(a, b, d, rmax, out))
         assert list(out) == o.r_and_d_to_rks(rks, dims, rmax=rmax), (dims, rks, rmax)
+
+
+def test_error_convention_no_exception_crosses_the_abi():
+    """Status codes + `ttn_last_error()` (SURVEY.md section 8(b) "Error convention"): a bad argument comes back as TTN_EARG with a
+    message, is re-raised by the host mirror as the exception type the reference raises, and a following good call succeeds."""
+    import ctypes as C
+    sys.path.insert(0, ROOT)
+    import ttn_b200 as t
+    lib = t._lib.load()
+    s = (C.c_double * 3)(1.0, 0.5, 0.1)
+    r = C.c_int(-7)
+    st = lib.ttn_rank_rule(9, s, 3, 0.0, 1 << 62, C.byref(r))
+    assert st == 2 and b"unknown rule" in lib.ttn_last_error()
+    with pytest.raises(AssertionError, match="unknown rule"):
+        t._lib.check(st)
+    assert lib.ttn_rank_rule(0, None, 3, 0.0, 1 << 62, C.byref(r)) == 2           # null pointer: status, not a crash
+    assert lib.ttn_rank_rule(0, s, 3, 0.0, 2, C.byref(r)) == 0 and r.value == 2
+    defined = {int(v) for v in re.findall(r"#define TTN_E[A-Z]+ (\d+)", open(os.path.join(ROOT, "include", "ttn_b200.h")).read())}
+    assert defined == set(t._lib.STATUS_EXC)                                    # every status has a mapped exception type
