@@ -1,0 +1,82 @@
+"""CPU-only tests of the host-side mirror's pure-NumPy pieces (no device calls): the TToperator algebra used by the time
+steppers, `ttv_to_diag_tto`, `bubble_sort_swaps`, the `QTTvector` wrapper, batch sharding helpers — each against the oracle's
+restatement of the same reference function."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import ttn_b200 as t      # noqa: E402  (importing does not need a GPU; device calls would raise)
+import ttn_oracle as o    # noqa: E402
+
+
+def _mirror_tto(A):
+    return t.TToperator(A.N, [c.copy() for c in A.tto_vec], A.tto_dims, list(A.tto_rks))
+
+
+def _dense(A):
+    return o.tto_to_matrix(o.TToperator(A.N, list(A.tto_vec), tuple(A.tto_dims), list(A.tto_rks)))
+
+
+def test_operator_algebra_of_the_steppers_vs_oracle():
+    # tt_operators.jl:524-532 (id_tto), tt_operations.jl:71-96 (+), 268-278 (scalar *): I - h A as built by euler.jl:99-143
+    d, h = 5, 0.01
+    A = _mirror_tto(o.laplace_dd(d))
+    M = t.tto_add(t.id_tto(d), t.tto_scale(-h, A))
+    assert np.allclose(_dense(M), np.eye(2 ** d) - h * o.tto_to_matrix(o.laplace_dd(d)), atol=1e-14)
+    Mo = o.tto_add(o.id_tto(d), o.tto_scale(-h, o.laplace_dd(d)))
+    assert list(M.tto_rks) == list(Mo.tto_rks)
+    for a, b in zip(M.tto_vec, Mo.tto_vec):
+        assert np.array_equal(a, b)
+    Mc = t.tto_scale(1j, A)
+    assert Mc.tto_vec[0].dtype == np.complex128 and np.allclose(_dense(Mc), 1j * o.tto_to_matrix(o.laplace_dd(d)))
+    with pytest.raises(AssertionError):
+        t.tto_add(t.id_tto(4), t.id_tto(5))
+
+
+def test_ttv_to_diag_tto_vs_dense():
+    # tt_operations.jl:318-338; test_tt_operations.jl:4-37
+    rng = np.random.default_rng(2)
+    x = o.rand_tt((3, 2, 2), 2, rng=rng)
+    D = t.ttv_to_diag_tto(x)
+    assert tuple(D.tto_dims) == tuple(x.ttv_dims) and list(D.tto_rks) == list(x.ttv_rks)
+    assert np.allclose(_dense(D), np.diag(o.ttv_to_tensor(x).reshape(-1)), atol=1e-14)
+
+
+def test_bubble_sort_swaps_and_qttvector_wrapper():
+    # qtt_tools.jl:704-718, 370-379
+    rng = np.random.default_rng(3)
+    for _ in range(10):
+        perm = [int(v) for v in rng.permutation(9)]
+        assert t.bubble_sort_swaps(perm) == o.bubble_sort_swaps(perm)
+    x = o.rand_tt((2,) * 6, 2, rng=rng)
+    q = t.QTTvector(x, 3, 2, "interleaved")
+    assert (q.n_dims, q.bits_per_dim, q.ordering, q.N) == (3, 2, "interleaved", 6) and q.ttv_rks == list(x.ttv_rks)
+    with pytest.raises(AssertionError):
+        t.QTTvector(x, 4, 2, "serial")
+
+
+def test_batch_sharding_helpers():
+    # vectors split evenly over the ranks, no data-path collective
+    for n, world in ((4096, 8), (10, 3), (5, 8), (0, 2)):
+        parts = [t.shard_batch(n, r, world) for r in range(world)]
+        idx = [i for first, count in parts for i in range(first, first + count)]
+        assert idx == list(range(n))
+        sizes = [count for _, count in parts]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_device_calls_fail_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    rng = np.random.default_rng(4)
+    x = o.rand_tt((2, 2, 2), 2, rng=rng)
+    with pytest.raises(Exception):
+        t.tt_compress_(x, 1)
+    with pytest.raises(Exception):
+        t.hadamard_ttm(x, x)
