@@ -80,3 +80,25 @@ def test_device_calls_fail_loudly_without_gpu():
         t.tt_compress_(x, 1)
     with pytest.raises(Exception):
         t.hadamard_ttm(x, x)
+
+
+def test_committed_bench_line_follows_the_contract():
+    """`profiles/bench_end_of_round_r01.json` is the line `python bench.py` printed on a B200 at the end of the round: it must
+    carry every key of the bench contract (metric/config of BASELINE.json, e2e with host<->device bytes, roofline against the
+    measured peak, CPU baseline with its sample, clocks sampled under load, launch count)."""
+    import json
+    d = json.load(open(os.path.join(ROOT, "profiles", "bench_end_of_round_r01.json")))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "e2e", "roofline", "cpu_baseline", "clocks", "gpu_launches"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["dtype"] == "f64" and d["data"] == "synthetic" and "cfg2" in d["config"]["workload"] and "model" not in d["config"]
+    assert abs(d["value"] - 1000.0 / d["ms_per_step"]) < 1e-6 * d["value"]
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] > 9e7 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] <= d["value"] * 1.02
+    r = d["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["unit"] in ("GB/s", "TFLOP/s")
+    c = d["cpu_baseline"]
+    assert c["kind"] in ("port", "reference") and c["cores"] >= 1 and c["sample"] and c["value"] > 0
+    assert d["gpu_launches"] > 0
+    assert d["clocks"]["samples"] >= 1 and not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
