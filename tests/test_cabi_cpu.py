@@ -40,12 +40,14 @@ def test_no_cpu_fallback_without_gpu():
 
 
 def test_product_does_not_import_oracle():
-    pkg = os.path.join(ROOT, "tensortrainnumerics.jl_b200")
-    for dirpath, _, files in os.walk(pkg):
-        for f in files:
-            if f.endswith((".py", ".cu", ".h", ".cpp", ".jl")):
-                src = open(os.path.join(dirpath, f), errors="ignore").read()
-                assert "ttn_oracle" not in src, f"{f} references the oracle"
+    """Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may use oracle/: neither the package nor tools/ does."""
+    for top in ("tensortrainnumerics.jl_b200", "tools", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".h", ".cpp", ".jl")):
+                    src = open(os.path.join(dirpath, f), errors="ignore").read()
+                    assert "ttn_oracle" not in src, f"{top}/{f} references the oracle"
+    assert "ttn_oracle" not in open(os.path.join(ROOT, "ttn_b200.py")).read()
 
 
 def _c_kind(decl):

@@ -1,5 +1,5 @@
-"""Timing of the site-surgery compositions on the GPU; CPU oracle timed beside on the same input.
-usage: python tools/sites_bench.py [--cpu]"""
+"""Timing of the site-surgery compositions on the GPU (own input builder; the oracle is not used).
+usage: python tools/sites_bench.py"""
 import json
 import os
 import sys
@@ -9,16 +9,21 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 
 def main():
     import torch
     import ttn_b200 as t
-    import ttn_oracle as o
-    cpu = "--cpu" in sys.argv
     rng = np.random.default_rng(0)
     out = {}
+
+    def rand_tt(dims, rmax):
+        d = len(dims)
+        rks = [1] * (d + 1)
+        for k in range(1, d):
+            rks[k] = int(min(rmax, np.prod([float(n) for n in dims[:k]]), np.prod([float(n) for n in dims[k:]])))
+        cores = [np.asfortranarray(rng.standard_normal((dims[k], rks[k], rks[k + 1]))) for k in range(d)]
+        return t.TTvector(d, cores, dims, rks)
 
     def timed(fn, reps=3):
         fn()
@@ -30,19 +35,15 @@ def main():
 
     # reorder: 2 dims x 12 bits, rank 32, serial -> interleaved (66 swaps) with a 1e-10 relative threshold
     bits = 12
-    x = o.rand_tt((2,) * (2 * bits), 32, rng=rng)
+    x = rand_tt((2,) * (2 * bits), 32)
     xd = t.DeviceTT.upload(x)
     out["reorder_2x12_r32_s"] = timed(lambda: t.reorder(xd, 2, bits, "serial", "interleaved", threshold=1e-10))
     y = t.reorder(xd, 2, bits, "serial", "interleaved", threshold=1e-10)
     out["reorder_max_rank"] = max(y.ttv_rks)
-    if cpu:
-        t0 = time.perf_counter(); o.reorder(x, 2, bits, "serial", "interleaved", threshold=1e-10); out["reorder_cpu_s"] = time.perf_counter() - t0
 
     # hadamard_ttm: d = 16, ranks 24 x 24, tol 1e-10, rmax 64
-    a = o.rand_tt((2,) * 16, 24, rng=rng); b = o.rand_tt((2,) * 16, 24, rng=rng)
+    a = rand_tt((2,) * 16, 24); b = rand_tt((2,) * 16, 24)
     out["hadamard_ttm_d16_r24_s"] = timed(lambda: t.hadamard_ttm(a, b, tol=1e-10, rmax=64), reps=2)
-    if cpu:
-        t0 = time.perf_counter(); o.hadamard_ttm(a, b, tol=1e-10, rmax=64); out["hadamard_ttm_cpu_s"] = time.perf_counter() - t0
 
     # exact hadamard + rounding (the route the apply + rounding kernels serve)
     ad, bd = a, t.DeviceTT.upload(b)
