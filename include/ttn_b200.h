@@ -60,6 +60,11 @@ void* ttn_stream(void);                   /* cudaStream_t the library launches o
 /* per-kernel-family CUDA-event timing on the library stream (bench.py's roofline pass; adds two event records per launch).
  * families: 0 gemm, 1 copy/permute, 2 apply, 3 qr panel, 4 qr reflector apply, 5 jacobi, 6 reductions/axpy, 7 gather/norms */
 #define TTN_NFAMILIES 8
+/* run-time switches, also readable from the environment at ttn_init: "gram_compress" (1: Gram path of tt_compress! for
+ * truncerr == 0, csrc/heig.cu), "gram_jacobi_min" (columns from which the Gram-block Jacobi serves large SVDs),
+ * "use_cholqr", "use_cluster_jacobi" */
+int ttn_set_option(const char* key, double value);
+int ttn_get_option(const char* key, double* value);
 int ttn_last_jacobi_sweeps(void);        /* diagnostics: sweeps of the most recent Jacobi SVD */
 int ttn_profile(int enable);              /* clears the records and switches profiling on/off */
 int ttn_profile_read(double* ms /* 8 */, long long* counts /* 8 */);
@@ -195,7 +200,11 @@ int ttn_shard_matvec_create(int dtype, int w_l, int w_r, int chi_l, int chi_r, i
                             const void* H, int rank, int nranks, ttn_shard_matvec* out);
 int ttn_shard_matvec_handles(ttn_shard_matvec mv, void* handles192);
 int ttn_shard_matvec_bind(ttn_shard_matvec mv, const void* all_handles);
-int ttn_shard_matvec_apply(ttn_shard_matvec mv, const void* V_dev, void** Y_dev);   /* *Y_dev: library-owned full vector */
+/* *Y_dev: library-owned full vector.  The exchange waits for every peer's epoch flag for at most TTN_SHARD_TIMEOUT_S
+ * seconds (default 60); after a timeout the sticky error of ttn_shard_matvec_error is set and Y is INVALID — callers of
+ * this kernel-level entry point must poll it before consuming Y (ttn_shard_eigsolve checks it itself and fails with
+ * TTN_ECUDA). */
+int ttn_shard_matvec_apply(ttn_shard_matvec mv, const void* V_dev, void** Y_dev);
 /* lowest eigenpair of the sharded operator (KrylovKit.eigsolve(..., :SR) stand-in, dmrg.jl:245): x_dev start vector in,
  * eigenvector out (identical on every rank); the Lanczos recurrence is replicated, only the matvec is distributed */
 int ttn_shard_eigsolve(ttn_shard_matvec mv, void* x_dev, int krylovdim, int maxiter, double tol, double* theta, int* matvecs);
@@ -212,6 +221,10 @@ int ttn_env_right_host(int dtype, int n, int w_l, int w_r, int r_l, int r_r, con
 int ttn_svdtrunc_host(int dtype, int m, int n, const void* A, int64_t max_bond, double truncerr, void* U, double* s, void* Vt,
                       int* r_out);
 /* thin QR of a host matrix (column-major m x n): Q (m x k), R (k x n), k = min(m,n) */
+/* Top `nev` eigenpairs (descending) of `batch` Hermitian PSD matrices G (n x n column-major each, host): the engine of the
+ * Gram path of tt_compress! (csrc/heig.cu; replaces `svd` of src/tt_cross_interpolation.jl:150 when truncerr == 0).
+ * flags[b] != 0: the fast path declines this matrix (clusters / accuracy), callers fall back to the Jacobi SVD. */
+int ttn_heig_host(int dtype, int n, int nev, int batch, const void* G, double* lam, void* U, int* flags);
 int ttn_qr_host(int dtype, int m, int n, const void* A, void* Q, void* R);
 /* The truncation rules of the path on a host spectrum `s` (sorted descending, `len` values); pure host code, callable without
  * a device.  rule 0: `_svdtrunc` tail-norm rule + `max_bond` cap (src/tt_cross_interpolation.jl:149-166); 1: `sv_trunc`

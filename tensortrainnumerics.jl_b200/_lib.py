@@ -99,6 +99,9 @@ def load():
         "ttn_shard_matvec_slice": [vp, ip, ip], "ttn_shard_matvec_error": [vp, ip], "ttn_shard_matvec_free": [vp],
         "ttn_env_left_host": [C.c_int] * 6 + [vp, vp, vp, vp],
         "ttn_env_right_host": [C.c_int] * 6 + [vp, vp, vp, vp],
+        "ttn_set_option": [C.c_char_p, C.c_double],
+        "ttn_get_option": [C.c_char_p, dp],
+        "ttn_heig_host": [C.c_int, C.c_int, C.c_int, C.c_int, vp, dp, vp, ip],
         "ttn_svdtrunc_host": [C.c_int, C.c_int, C.c_int, vp, C.c_int64, C.c_double, vp, dp, vp, ip],
         "ttn_qr_host": [C.c_int, C.c_int, C.c_int, vp, vp, vp],
         "ttn_rank_rule": [C.c_int, dp, C.c_int, C.c_double, C.c_int64, ip],

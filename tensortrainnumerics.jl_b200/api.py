@@ -32,7 +32,7 @@ __all__ = [
     "euclidean_distance_normalized",
     "orthogonalize", "tt_compress_", "tt_bond_truncate_", "als_linsolve", "als_eigsolve", "als_gen_eigsolv", "mals_linsolve",
     "mals_eigsolve", "dmrg_linsolve", "dmrg_eigsolve", "tdvp", "tdvp2", "matvec2", "env_left", "env_right",
-    "shard_range", "shard_batch", "assemble_slices", "ShardedMatvec", "svdtrunc", "qr_thin", "gemm_host", "launch_count", "reset_launch_count", "synchronize", "library_path", "profile", "profile_read", "stream_handle",
+    "shard_range", "shard_batch", "assemble_slices", "ShardedMatvec", "svdtrunc", "heig_top", "set_option", "get_option", "qr_thin", "gemm_host", "launch_count", "reset_launch_count", "synchronize", "library_path", "profile", "profile_read", "stream_handle",
     "KERNEL_FAMILIES",
 ]
 
@@ -66,6 +66,17 @@ def profile_read():
     ms, cnt = (C.c_double * 8)(), (C.c_longlong * 8)()
     check(_lib.lib().ttn_profile_read(ms, cnt))
     return {KERNEL_FAMILIES[i]: (float(ms[i]), int(cnt[i])) for i in range(8)}
+
+
+def set_option(key: str, value) -> None:
+    """run-time switch of the library (`ttn_set_option`): gram_compress, gram_jacobi_min, use_cholqr, use_cluster_jacobi"""
+    check(_lib.lib().ttn_set_option(key.encode(), float(value)))
+
+
+def get_option(key: str) -> float:
+    v = C.c_double()
+    check(_lib.lib().ttn_get_option(key.encode(), C.byref(v)))
+    return float(v.value)
 
 
 def stream_handle() -> int:
@@ -814,6 +825,26 @@ def svdtrunc(A, max_bond=None, truncerr=0.0):
     r = r.value
     return (np.asfortranarray(U.reshape(-1, order="F")[: m * r].reshape(m, r, order="F")), np.array(s[:r]),
             Vt[: r * n].reshape(r, n, order="F"))
+
+
+def heig_top(G, nev):
+    """Top `nev` eigenpairs (descending) of a batch of Hermitian PSD matrices `G` (batch, n, n) or (n, n) — test hook of
+    csrc/heig.cu (the Gram-path SVD engine of `tt_compress!`).  → (lam (batch, nev), U (batch, n, nev), flags (batch,))."""
+    G = np.asarray(G)
+    single = G.ndim == 2
+    if single:
+        G = G[None]
+    dt = np.complex128 if np.iscomplexobj(G) else np.float64
+    b, n, _ = G.shape
+    Gf = np.ascontiguousarray(np.transpose(G, (0, 2, 1)).astype(dt))      # each matrix column-major
+    lam = np.empty((b, nev), dtype=np.float64)
+    U = np.empty((b, nev, n), dtype=dt)                                    # column-major n x nev per matrix
+    flags = np.zeros((b,), dtype=np.int32)
+    check(_lib.lib().ttn_heig_host(_dtype_code(dt), n, int(nev), b, Gf.ctypes.data,
+                                   lam.ctypes.data_as(C.POINTER(C.c_double)), U.ctypes.data,
+                                   flags.ctypes.data_as(C.POINTER(C.c_int))))
+    U = np.transpose(U, (0, 2, 1))
+    return (lam[0], U[0], flags[0]) if single else (lam, U, flags)
 
 
 def qr_thin(A):

@@ -50,6 +50,7 @@ int ttn_init(int device) {
     TTN_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
     c.use_cluster_jacobi = getenv("TTN_NO_CLUSTER_JACOBI") == nullptr;
     c.use_cholqr = getenv("TTN_NO_CHOLQR") == nullptr;
+    c.gram_compress = !(getenv("TTN_GRAM_COMPRESS") && atoi(getenv("TTN_GRAM_COMPRESS")) == 0);
     if (const char* e = getenv("TTN_GRAM_JACOBI")) c.gram_jacobi_min = (atoi(e) != 0) ? 128 : (1 << 30);
     c.inited = true;
   }
@@ -66,6 +67,34 @@ int ttn_shutdown(void) {
     c.stream = nullptr;
     c.inited = false;
   }
+  API_END
+}
+
+// run-time switches (the environment variables of DESIGN.md section 3, settable after ttn_init: A/B timing and tests)
+int ttn_set_option(const char* key, double value) {
+  API_BEGIN
+  need_init();
+  ttn_assert(key != nullptr, TTN_EARG, "null argument");
+  const std::string k(key);
+  Context& c = ctx();
+  if (k == "gram_compress") c.gram_compress = value != 0.0;
+  else if (k == "gram_jacobi_min") c.gram_jacobi_min = (int)value;
+  else if (k == "use_cholqr") c.use_cholqr = value != 0.0;
+  else if (k == "use_cluster_jacobi") c.use_cluster_jacobi = value != 0.0;
+  else throw Error(TTN_EARG, "ttn_set_option: unknown key " + k);
+  API_END
+}
+int ttn_get_option(const char* key, double* value) {
+  API_BEGIN
+  need_init();
+  ttn_assert(key != nullptr && value != nullptr, TTN_EARG, "null argument");
+  const std::string k(key);
+  const Context& c = ctx();
+  if (k == "gram_compress") *value = c.gram_compress;
+  else if (k == "gram_jacobi_min") *value = c.gram_jacobi_min;
+  else if (k == "use_cholqr") *value = c.use_cholqr;
+  else if (k == "use_cluster_jacobi") *value = c.use_cluster_jacobi;
+  else throw Error(TTN_EARG, "ttn_get_option: unknown key " + k);
   API_END
 }
 
@@ -689,6 +718,29 @@ int ttn_svdtrunc_host(int dtype, int m, int n, const void* A, int64_t max_bond, 
 }
 
 }  // extern "C"
+// Test / benchmark hook of the small Hermitian eigensolver behind the Gram path of tt_compress! (csrc/heig.cu)
+template <class T>
+static void heig_host(int n, int nev, int batch, const void* G, double* lam, void* U, int* flags) {
+  DevBuf dG(sizeof(T) * (size_t)n * n * batch), dl(sizeof(double) * (size_t)nev * batch), dU(sizeof(T) * (size_t)n * nev * batch),
+      df(sizeof(int) * (size_t)batch);
+  TTN_CUDA(cudaMemcpyAsync(dG.p, G, dG.bytes, cudaMemcpyHostToDevice, ctx().stream));
+  TTN_CUDA(cudaMemsetAsync(df.p, 0, df.bytes, ctx().stream));
+  ttn_assert(heig_top<T>(dG.as<T>(), n, n, (int64_t)n * n, 1, 0, nev, batch, dl.as<double>(), dU.as<T>(), df.as<int>()), TTN_EARG,
+             "heig: shape not served");
+  TTN_CUDA(cudaMemcpyAsync(lam, dl.p, dl.bytes, cudaMemcpyDeviceToHost, ctx().stream));
+  TTN_CUDA(cudaMemcpyAsync(U, dU.p, dU.bytes, cudaMemcpyDeviceToHost, ctx().stream));
+  TTN_CUDA(cudaMemcpyAsync(flags, df.p, df.bytes, cudaMemcpyDeviceToHost, ctx().stream));
+  TTN_CUDA(cudaStreamSynchronize(ctx().stream));
+}
+extern "C" {
+int ttn_heig_host(int dtype, int n, int nev, int batch, const void* G, double* lam, void* U, int* flags) {
+  API_BEGIN
+  need_init();
+  ttn_assert(n >= 1 && nev >= 1 && nev <= n && batch >= 1, TTN_EARG, "heig: bad shape");
+  if (dtype == TTN_F64) heig_host<double>(n, nev, batch, G, lam, U, flags); else heig_host<zc>(n, nev, batch, G, lam, U, flags);
+  API_END
+}
+}
 template <class T>
 static void qr_host(int m, int n, const void* A, void* Q, void* R) {
   const int k = std::min(m, n);

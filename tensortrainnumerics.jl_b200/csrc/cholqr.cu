@@ -344,10 +344,10 @@ bool cholqr2_impl(const T* A, int m, int k, int64_t lda, int64_t bA, T* R, T* Q,
     for (int s : {8, 4, 2})
       if (m % s == 0 && m / s >= 64) { nsplit = s; break; }
   const size_t smem = chol_smem<T>(k);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static int attr_dev = -1;   // function attributes are per device (ttn_init may re-bind)
+  if (attr_dev != ctx().device) {
     TTN_CUDA(cudaFuncSetAttribute(chol_inv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    attr_done = true;
+    attr_dev = ctx().device;
   }
   const size_t kk = (size_t)k * k;
   DevBuf Gp(sizeof(T) * kk * nsplit * batch), R1(sizeof(T) * kk * batch), X(sizeof(T) * kk * batch), st(sizeof(double) * 2 * batch);
@@ -374,7 +374,10 @@ bool cholqr2_impl(const T* A, int m, int k, int64_t lda, int64_t bA, T* R, T* Q,
   // One pass is enough when cond(A) is small: the loss of CholeskyQR is eps*cond^2 (relative, in R and in Q^H Q - I);
   // min/max diag(R1) >= 0.3 means cond(A) of a few units (cfg2's bonds: 0.39 ... 0.78), i.e. a few tens of eps — the level of
   // the rounding of the K = 512 GEMMs around it.
-  const bool single = worst >= 0.3;
+  // An explicit Q always takes the second pass: diag(R1) bounds cond(A) from one side only (a Kahan-like matrix has equal
+  // diagonals and a growing R^-1), and only the second Gram matrix verifies Q1^H Q1 = I.  The R-only call feeds the Jacobi
+  // SVD, whose result is checked through the singular values themselves.
+  const bool single = worst >= 0.3 && Q == nullptr;
   if (debug_svd()) fprintf(stderr, "[ttn] cholqr2 %d x %d batch %d: min/max diag(R1) = %.3g -> %s\n", m, k, batch, worst, single ? "one pass" : "two passes");
   if (single) {
     TTN_CUDA(cudaMemcpyAsync(R, R1.p, sizeof(T) * kk * batch, cudaMemcpyDeviceToDevice, ctx().stream));

@@ -160,10 +160,10 @@ void launch_cfg(const GemmArgs& g) {
   constexpr int PAD = Pad<T>::v;
   const size_t smem = sizeof(T) * NSTAGE * BK * ((BM + PAD) + (BN + PAD));
   auto kern = gemm_kernel<T, BM, BN, WM, WN, AMAJ, BMAJ>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static int attr_dev = -1;   // function attributes are per device (ttn_init may re-bind)
+  if (attr_dev != ctx().device) {
     TTN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
+    attr_dev = ctx().device;
   }
   const int64_t nb = (int64_t)g.batch1 * g.batch2;
   // grid.z is limited to 65535: split the outer batch dimension if needed

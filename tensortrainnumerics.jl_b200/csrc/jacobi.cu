@@ -413,13 +413,13 @@ int jacobi_orth(T* X, int m, int n, int64_t ldx, double* norms, int batch, int64
   const bool fullm = m == Cfg::GL * Cfg::RPL;
   auto kern = regs ? (fullm ? jacobi_kernel<T, Cfg::GL, Cfg::RPL, true> : jacobi_kernel<T, Cfg::GL, Cfg::RPL, false>)
                    : jacobi_kernel<T, Cfg::GLG, 0, false>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static int attr_dev = -1;   // function attributes are per device (ttn_init may re-bind)
+  if (attr_dev != ctx().device) {
     const int mx = 224 * 1024;
     TTN_CUDA(cudaFuncSetAttribute(jacobi_kernel<T, Cfg::GL, Cfg::RPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     TTN_CUDA(cudaFuncSetAttribute(jacobi_kernel<T, Cfg::GL, Cfg::RPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     TTN_CUDA(cudaFuncSetAttribute(jacobi_kernel<T, Cfg::GLG, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-    attr_done = true;
+    attr_dev = ctx().device;
   }
   const size_t col_bytes = sizeof(T) * (size_t)(m + (is_cplx<T>::value ? 0 : 4)) + sizeof(double);   // column + its norm
   const int threads = JAC_T;

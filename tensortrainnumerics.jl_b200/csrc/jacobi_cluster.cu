@@ -250,10 +250,10 @@ bool launch_cluster(T* X, int m, int n, int64_t ldx, int batch, int64_t bX, doub
   const size_t smem = sizeof(T) * (size_t)(DB ? 2 : 1) * 2 * W * GL * RPL + sizeof(double) * (DB ? 2 : 1) * 2 * W + sizeof(int) * CL;
   if (smem > 224 * 1024) return false;
   auto kern = jacobi_cluster_kernel<T, CL, GL, RPL, DB>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static int attr_dev = -1;   // function attributes are per device (ttn_init may re-bind)
+  if (attr_dev != ctx().device) {
     TTN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-    attr_done = true;
+    attr_dev = ctx().device;
   }
   for (int b0 = 0; b0 < batch; b0 += 8192) {
     const int nb = std::min(8192, batch - b0);

@@ -354,7 +354,15 @@ int jacobi_gram(T* X, int m, int n, int64_t ldx, double tol, const double* frob2
   constexpr int NGMAX = 4;
   static cudaStream_t strm[NGMAX] = {nullptr, nullptr, nullptr, nullptr};   // strm[0] is the library stream
   static cudaEvent_t ev_grp[NGMAX], ev_join = nullptr;
+  static int strm_dev = -1;   // streams and events belong to a device: rebuild them when ttn_init re-binds the library
+  if (ev_join != nullptr && strm_dev != ctx().device) {
+    for (int g = 1; g < NGMAX; ++g) { cudaStreamDestroy(strm[g]); strm[g] = nullptr; }
+    for (int g = 0; g < NGMAX; ++g) cudaEventDestroy(ev_grp[g]);
+    cudaEventDestroy(ev_join);
+    ev_join = nullptr;
+  }
   if (ev_join == nullptr) {
+    strm_dev = ctx().device;
     for (int g = 1; g < NGMAX; ++g) TTN_CUDA(cudaStreamCreateWithFlags(&strm[g], cudaStreamNonBlocking));
     for (int g = 0; g < NGMAX; ++g) TTN_CUDA(cudaEventCreateWithFlags(&ev_grp[g], cudaEventDisableTiming));
     TTN_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
@@ -384,12 +392,12 @@ int jacobi_gram(T* X, int m, int n, int64_t ldx, double tol, const double* frob2
   const size_t smem_g = sizeof(T) * 2 * PW * (GK + 4);
   const size_t smem_u = sizeof(T) * ((size_t)2 * PW * (UM / 2 + 4) + (size_t)PW * (PW + 4));
   const size_t smem_e = sizeof(T) * 2 * PW * (PW + 1);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static int attr_dev = -1;   // function attributes are per device (ttn_init may re-bind)
+  if (attr_dev != ctx().device) {
     TTN_CUDA(cudaFuncSetAttribute(gram_eig_kernel<T, GE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
     TTN_CUDA(cudaFuncSetAttribute(gram_pairs_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
     TTN_CUDA(cudaFuncSetAttribute(update_pairs_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_u));
-    attr_done = true;
+    attr_dev = ctx().device;
   }
   int sweeps = 0;
   auto group = [&](int g, const int* pa, const int* pb, int cnt, int cross) {

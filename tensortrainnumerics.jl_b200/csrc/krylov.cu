@@ -186,10 +186,10 @@ void dense_solve(LocalOp<T>& op, const T* rhs, T* x) {
   qr_factor<T>(K.as<T>(), N, N, N, tau.as<T>());
   TTN_CUDA(cudaMemcpyAsync(x, rhs, sizeof(T) * (size_t)N, cudaMemcpyDeviceToDevice, ctx().stream));
   qr_apply<T>(K.as<T>(), N, N, N, tau.as<T>(), x, 1, N, true);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static int attr_dev = -1;   // function attributes are per device (ttn_init may re-bind)
+  if (attr_dev != ctx().device) {
     TTN_CUDA(cudaFuncSetAttribute(trsv_upper_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * (int)sizeof(T)));
-    attr_done = true;
+    attr_dev = ctx().device;
   }
   trsv_upper_kernel<T><<<1, 256, sizeof(T) * (size_t)N, ctx().stream>>>(K.as<T>(), N, N, x);
   TTN_CHECK_LAUNCH();

@@ -390,7 +390,7 @@ void qr_factor(T* A, int m, int n, int64_t lda, T* tau, int batch, int64_t bA, i
   const int k = std::min(m, n);
   if (k <= 0 || batch <= 0) return;
   static const bool smem_panel_env = !(getenv("TTN_QR_SMEM_PANEL") && atoi(getenv("TTN_QR_SMEM_PANEL")) == 0);
-  static bool attr_done = false;
+  static int attr_dev = -1;   // function attributes are per device (ttn_init may re-bind)
   for (int j0 = 0; j0 < k; j0 += PANEL_NB) {
     // tall single matrix, whole panel inside min(m, n): shared-memory sub-panel kernel
     int SW = 0;
@@ -398,9 +398,9 @@ void qr_factor(T* A, int m, int n, int64_t lda, T* tau, int batch, int64_t bA, i
       for (int c : {8, 4, 2})
         if (sizeof(T) * (size_t)c * (m - j0) <= 200 * 1024) { SW = c; break; }
     if (SW > 0) {
-      if (!attr_done) {
+      if (attr_dev != ctx().device) {
         TTN_CUDA(cudaFuncSetAttribute(qr_panel_smem_kernel<T, PANEL_NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_done = true;
+        attr_dev = ctx().device;
       }
       ProfScope prof_scope_(KF_QR_PANEL);
       qr_panel_smem_kernel<T, PANEL_NB><<<1, PANEL_T, sizeof(T) * (size_t)SW * (m - j0), ctx().stream>>>(A, m, lda, tau, j0, SW, bA,

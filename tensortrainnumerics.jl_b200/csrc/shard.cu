@@ -60,16 +60,30 @@ __global__ void shard_signal_kernel(unsigned* const* flag_peer, int nranks, int 
   __threadfence_system();
 }
 
-// waits until every rank has published `epoch` in this rank's flag array; bounded spin (about 2 s) -> error flag
-__global__ void shard_wait_kernel(volatile unsigned* flags, int nranks, unsigned epoch, int* err) {
+// waits until every rank has published `epoch` in this rank's flag array; bounded spin (`timeout_ns` of the global timer,
+// default 60 s, TTN_SHARD_TIMEOUT_S overrides) -> sticky error flag.  Once the flag is set the gathered vector is invalid:
+// shard_eigsolve throws, and callers of ttn_shard_matvec_apply must poll ttn_shard_matvec_error before using Y.
+__global__ void shard_wait_kernel(volatile unsigned* flags, int nranks, unsigned epoch, int* err, unsigned long long timeout_ns) {
   const int i = threadIdx.x;
   if (i >= nranks) return;
-  const long long t0 = clock64();
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
   while ((int)(flags[i] - epoch) < 0) {
-    if (clock64() - t0 > 4000000000LL) { *err = 1; break; }
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > timeout_ns) { *err = 1; break; }
     __nanosleep(200);
   }
   __threadfence_system();
+}
+
+unsigned long long shard_timeout_ns() {
+  static const unsigned long long v = [] {
+    const char* e = getenv("TTN_SHARD_TIMEOUT_S");
+    const double s = e ? atof(e) : 60.0;
+    return (unsigned long long)((s > 0.001 ? s : 60.0) * 1e9);
+  }();
+  return v;
 }
 
 }  // namespace
@@ -195,7 +209,7 @@ static T* shard_apply(ShardOp<T>& op, const T* V) {
   if (op.bound && op.nranks > 1) {
     shard_signal_kernel<<<1, 32, 0, ctx().stream>>>(op.flag_peer_d.template as<unsigned*>(), op.nranks, op.rank, op.epoch);
     TTN_CHECK_LAUNCH();
-    shard_wait_kernel<<<1, 32, 0, ctx().stream>>>(op.flags, op.nranks, op.epoch, op.err.template as<int>());
+    shard_wait_kernel<<<1, 32, 0, ctx().stream>>>(op.flags, op.nranks, op.epoch, op.err.template as<int>(), shard_timeout_ns());
     TTN_CHECK_LAUNCH();
     ctx().launches += 2;
   }
@@ -285,6 +299,13 @@ static double shard_eig_t(ShardOp<T>& op, T* x, int krylovdim, int maxiter, doub
   KrylovInfo info;
   const double th = lanczos_lowest<T>(lop, x, krylovdim, maxiter, tol, &info);
   if (matvecs) *matvecs = info.matvecs;
+  if (op.bound && op.nranks > 1) {
+    int e = 0;
+    TTN_CUDA(cudaMemcpyAsync(&e, op.err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
+    TTN_CUDA(cudaStreamSynchronize(ctx().stream));
+    if (e) throw Error(6, "sharded matvec: a peer did not publish its slice within the epoch timeout (TTN_SHARD_TIMEOUT_S); "
+                          "the gathered vector and the eigenpair are invalid");
+  }
   return th;
 }
 

@@ -83,6 +83,8 @@ void svd_left(const T* Theta, int p, int q, int64_t rs, int64_t cs, bool conj, S
       std::vector<double> hn(p);
       TTN_CUDA(cudaMemcpyAsync(hn.data(), n2.p, sizeof(double) * p, cudaMemcpyDeviceToHost, ctx().stream));
       TTN_CUDA(cudaStreamSynchronize(ctx().stream));
+      for (double& v : hn)
+        if (!std::isfinite(v)) v = 0.0;   // keeps the comparator a strict weak order; the Jacobi stage reports the NaN
       std::vector<int> perm(p);
       for (int j = 0; j < p; ++j) perm[j] = j;
       std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return hn[a] > hn[b]; });
@@ -152,6 +154,8 @@ void svd_left(const T* Theta, int p, int q, int64_t rs, int64_t cs, bool conj, S
   std::vector<double> h((size_t)k * batch);
   TTN_CUDA(cudaMemcpyAsync(h.data(), out.norms.p, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, ctx().stream));
   TTN_CUDA(cudaStreamSynchronize(ctx().stream));
+  for (double v : h)
+    if (!std::isfinite(v)) throw Error(5, "svd_left: the Jacobi SVD produced a non-finite singular value (non-finite input?)");
   out.sigma.resize(h.size());
   out.perm.resize(h.size());
   std::vector<int> idx(k);

@@ -250,7 +250,8 @@ int rank_tailnorm(const double* s, int len, int64_t max_bond, double truncerr) {
 
 // src/tt_tools.jl:743-768 (without the discarded orthogonalize of :769)
 template <class T>
-void tt_bond_truncate(TT<T>& x, int k1, int64_t max_bond, double truncerr, double* sigma_out, int64_t sigma_cap) {
+void tt_bond_truncate(TT<T>& x, int k1, int64_t max_bond, double truncerr, double* sigma_out, int64_t sigma_cap,
+                      std::vector<RetiredCore>* retired) {
   ttn_assert(1 <= k1 && k1 < x.d, 2, "k must be in 1:(N-1)");
   ttn_assert(max_bond >= 1, 2, "max_bond must be >= 1");
   const int k = k1 - 1, batch = x.batch;
@@ -319,9 +320,12 @@ void tt_bond_truncate(TT<T>& x, int k1, int64_t max_bond, double truncerr, doubl
     const double smax = sv.sigma[(size_t)b * kk];
     for (int j = 0; j < rc; ++j) {
       const double s = sv.sigma[(size_t)b * kk + j];
-      const bool ok = s > 1e-290 && s > smax * 1e-140;
-      s1[(size_t)b * rc + j] = ok ? 1.0 / std::sqrt(s) : 0.0;
-      s2[(size_t)b * rc + j] = ok ? 1.0 / (s * std::sqrt(s)) : 0.0;
+      // X_j = u_j sigma_j: core k <- X_j sigma^{-1/2}, G2 <- X_j sigma^{-3/2}; formed as (1/sigma)(1/sqrt(sigma)) so that
+      // sigma^{3/2} cannot underflow on small-norm trains, and gated on a finite result
+      const double is = 1.0 / std::sqrt(s), s2v = (1.0 / s) * is;
+      const bool ok = s > 1e-290 && s > smax * 1e-140 && std::isfinite(is) && std::isfinite(s2v);
+      s1[(size_t)b * rc + j] = ok ? is : 0.0;
+      s2[(size_t)b * rc + j] = ok ? s2v : 0.0;
       perm[(size_t)b * rc + j] = sv.perm[(size_t)b * kk + j];
     }
   }
@@ -363,21 +367,234 @@ void tt_bond_truncate(TT<T>& x, int k1, int64_t max_bond, double truncerr, doubl
     gemm<T>(g);
   }
   TTN_CUDA(cudaStreamSynchronize(ctx().stream));
+  if (retired) {
+    retired->push_back(RetiredCore{k, std::move(x.cores[k])});
+    retired->push_back(RetiredCore{k + 1, std::move(x.cores[k + 1])});
+  }
   x.cores[k] = std::move(newA);
   x.cores[k + 1] = std::move(newB);
   x.rks[k + 1] = rn;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Gram path of tt_compress! for a pure rank cap (truncerr == 0): no host round trip inside the sweep.
+//   L->R bond:  Theta = A B,  G = Theta Theta^H (split-K partials, summed by the eigensolver's loader),  G = U S^2 U^H
+//               (heig.cu: tridiagonalisation + multisection + twisted factorisation),  core k <- U sqrt(S),
+//               core k+1 <- S^{-1/2} U^H Theta.
+//   R->L bond:  core k = U_k sqrt(S_k) was produced by the L->R step of the same bond and has orthogonal columns with known
+//               squared norms w = S_k, so its QR factor is diag(sqrt(w)):  Theta' = sqrt(w) B (r x q),  G' = Theta' Theta'^H
+//               = W S'^2 W^H,  core k <- A w^{-1/2} W sqrt(S'),  core k+1 <- S'^{-1/2} W^H Theta'.
+// Every eigen-decomposition raises a per-train flag when the fast path cannot vouch for it (clustered or non-positive kept
+// spectrum, sigma_r < 1e-5 sigma_1); the flags are read ONCE at the end of the call and a flagged call is redone from the
+// preserved input cores by the QR + one-sided-Jacobi path.  Bonds the eigensolver does not serve (more than 128 / 176
+// rows, tall Theta) take the classic step inside the same sweep.
+// ---------------------------------------------------------------------------------------------------------------------
+template <class T>
+struct GramSweep {
+  TT<T>& x;
+  int64_t max_bond;
+  DevBuf flags;                       // int per train, sticky
+  std::vector<DevBuf> colw;           // colw[k]: squared column norms of core k (batch x r) while it is U sqrt(S) of bond k
+  std::vector<DevBuf> orig;           // input cores (the first buffer replaced per site), alive until the flags are read
+  std::vector<char> have_orig;
+  std::vector<RetiredCore> retired;   // cores replaced by classic steps (absorbed into `orig` right after the step)
+  DevBuf sigdev;                      // steps x stride singular values of train 0
+  std::vector<int> gram_steps;
+  int64_t sigma_stride = 0;
+
+  GramSweep(TT<T>& x_, int64_t mb) : x(x_), max_bond(mb), colw(x_.d), orig(x_.d), have_orig(x_.d, 0) {
+    flags.alloc(sizeof(int) * (size_t)x.batch);
+    TTN_CUDA(cudaMemsetAsync(flags.p, 0, flags.bytes, ctx().stream));
+  }
+  void replace(int k, DevBuf&& nb) {
+    if (!have_orig[k]) { orig[k] = std::move(x.cores[k]); have_orig[k] = 1; }
+    x.cores[k] = std::move(nb);
+  }
+  void absorb_retired() {
+    for (auto& rc : retired)
+      if (!have_orig[rc.k]) { orig[rc.k] = std::move(rc.buf); have_orig[rc.k] = 1; }
+    retired.clear();
+  }
+  // split-K Gram matrix of Th (pe x q, ld pe, batch stride pe*q): partials [nsplit][batch][pe x pe]
+  int gram(const T* Th, int pe, int q, DevBuf& Gp) {
+    const int batch = x.batch;
+    int nsplit = 1;
+    if (batch * 4 < ctx().sm_count)
+      while (nsplit < 16 && q % (nsplit * 2) == 0 && q / (nsplit * 2) >= 64 && batch * nsplit * 4 < ctx().sm_count) nsplit *= 2;
+    const int kc = q / nsplit;
+    Gp.alloc(sizeof(T) * (size_t)pe * pe * batch * nsplit);
+    GemmArgs g;
+    g.M = pe; g.N = pe; g.K = kc;
+    g.A = Th; g.sAm = 1; g.sAk = pe; g.bA1 = (int64_t)pe * kc; g.bA2 = (int64_t)pe * q;
+    g.B = Th; g.sBk = pe; g.sBn = 1; g.conjB = true; g.bB1 = (int64_t)pe * kc; g.bB2 = (int64_t)pe * q;
+    g.C = Gp.p; g.sCm = 1; g.sCn = pe; g.bC1 = (int64_t)batch * pe * pe; g.bC2 = (int64_t)pe * pe;
+    g.batch1 = nsplit; g.batch2 = batch;
+    gemm<T>(g);
+    return nsplit;
+  }
+  // newB[s2,kappa,beta] = sum_row conj(G2[row,kappa]) Th[row,(s2,beta)]
+  void project(const DevBuf& G2, const DevBuf& Th, int pe, int rc, int rn, int n2, int rr, DevBuf& newB) {
+    const int batch = x.batch;
+    const int64_t q = (int64_t)n2 * rr;
+    GemmArgs g;
+    g.M = rc; g.N = rr; g.K = pe;
+    g.A = G2.p; g.sAm = pe; g.sAk = 1; g.conjA = true; g.bA1 = 0; g.bA2 = (int64_t)pe * rc;
+    g.B = Th.p; g.sBk = 1; g.sBn = (int64_t)pe * n2; g.bB1 = pe; g.bB2 = (int64_t)pe * q;
+    g.C = newB.p; g.sCm = n2; g.sCn = (int64_t)n2 * rn; g.bC1 = 1; g.bC2 = (int64_t)n2 * rn * rr;
+    g.batch1 = n2; g.batch2 = batch;
+    gemm<T>(g);
+  }
+  // one bond step; returns false when the shape is not served (caller takes the classic step)
+  bool step(int k, bool left_to_right, int64_t step_idx) {
+    const int batch = x.batch;
+    const int n1 = (int)x.dims[k], n2 = (int)x.dims[k + 1];
+    const int rl = (int)x.rks[k], r = (int)x.rks[k + 1], rr = (int)x.rks[k + 2];
+    const int p = n1 * rl, q = n2 * rr, kmin = std::min(p, q);
+    const int rn = (int)std::min<int64_t>(kmin, max_bond);
+    if (rn < 1) return false;
+    const bool have_w = !left_to_right && colw[k].p != nullptr && colw[k].bytes == sizeof(double) * (size_t)r * batch;
+    double* sig0 = sigdev.p ? sigdev.as<double>() + step_idx * sigma_stride : nullptr;
+    if (have_w) {
+      if (r > heig_max_n<T>() || r > q) return false;
+      const int nev = std::min(rn, r);
+      if ((int64_t)nev > sigma_stride && sig0) return false;
+      DevBuf Th(sizeof(T) * (size_t)r * q * batch);
+      Copy4 c;   // Th[gamma, s2 + n2*beta] = B[s2, gamma, beta]
+      c.n0 = r; c.s0 = n2; c.d0 = 1;
+      c.n1 = n2; c.s1 = 1; c.d1 = r;
+      c.n2 = rr; c.s2 = (int64_t)n2 * r; c.d2 = (int64_t)r * n2;
+      c.n3 = batch; c.s3 = x.core_elems(k + 1); c.d3 = (int64_t)r * q;
+      copy4<T>(x.core(k + 1), Th.as<T>(), c);
+      diag_scale<T>(Th.as<T>(), r, q, 1, r, colw[k].as<double>(), 1, 0, batch, (int64_t)r * q, r);
+      DevBuf Gp;
+      const int nsplit = gram(Th.as<T>(), r, q, Gp);
+      DevBuf lam(sizeof(double) * (size_t)nev * batch), W(sizeof(T) * (size_t)r * nev * batch);
+      if (!heig_top<T>(Gp.as<T>(), r, r, (int64_t)r * r, nsplit, (int64_t)batch * r * r, nev, batch, lam.as<double>(), W.as<T>(),
+                       flags.as<int>()))
+        return false;
+      DevBuf M1(sizeof(T) * (size_t)r * nev * batch), G2(sizeof(T) * (size_t)r * nev * batch);
+      heig_finalize<T>(W.as<T>(), r, nev, batch, lam.as<double>(), colw[k].as<double>(), M1.as<T>(), r, (int64_t)r * nev, G2.as<T>(),
+                       r, (int64_t)r * nev, nullptr, 0, sig0, flags.as<int>());
+      DevBuf newA(sizeof(T) * (size_t)p * rn * batch), newB(sizeof(T) * (size_t)n2 * rn * rr * batch);
+      if (nev < rn) {
+        fill<T>(newA.as<T>(), (int64_t)p * rn * batch, t_zero<T>());
+        fill<T>(newB.as<T>(), (int64_t)n2 * rn * rr * batch, t_zero<T>());
+      }
+      GemmArgs g;   // core k <- A M1
+      g.M = p; g.N = nev; g.K = r;
+      g.A = x.cores[k].p; g.sAm = 1; g.sAk = p; g.bA1 = x.core_elems(k);
+      g.B = M1.p; g.sBk = 1; g.sBn = r; g.bB1 = (int64_t)r * nev;
+      g.C = newA.p; g.sCm = 1; g.sCn = p; g.bC1 = (int64_t)p * rn;
+      g.batch1 = batch;
+      gemm<T>(g);
+      project(G2, Th, r, nev, rn, n2, rr, newB);
+      colw[k].release();
+      replace(k, std::move(newA));
+      replace(k + 1, std::move(newB));
+      x.rks[k + 1] = rn;
+      return true;
+    }
+    if (!left_to_right) return false;
+    if (p > q || p > heig_max_n<T>()) return false;
+    const int nev = std::min(rn, r);
+    if ((int64_t)nev > sigma_stride && sig0) return false;
+    DevBuf Th(sizeof(T) * (size_t)p * q * batch);
+    {
+      GemmArgs g;  // Theta[(s1,alpha),(s2,beta)] = sum_gamma A[s1,alpha,gamma] B[s2,gamma,beta]     (tt_tools.jl:749)
+      g.M = p; g.N = rr; g.K = r;
+      g.A = x.cores[k].p; g.sAm = 1; g.sAk = p; g.bA1 = 0; g.bA2 = x.core_elems(k);
+      g.B = x.cores[k + 1].p; g.sBk = n2; g.sBn = (int64_t)n2 * r; g.bB1 = 1; g.bB2 = x.core_elems(k + 1);
+      g.C = Th.p; g.sCm = 1; g.sCn = (int64_t)p * n2; g.bC1 = p; g.bC2 = (int64_t)p * q;
+      g.batch1 = n2; g.batch2 = batch;
+      gemm<T>(g);
+    }
+    DevBuf Gp;
+    const int nsplit = gram(Th.as<T>(), p, q, Gp);
+    DevBuf lam(sizeof(double) * (size_t)nev * batch), U(sizeof(T) * (size_t)p * nev * batch);
+    if (!heig_top<T>(Gp.as<T>(), p, p, (int64_t)p * p, nsplit, (int64_t)batch * p * p, nev, batch, lam.as<double>(), U.as<T>(),
+                     flags.as<int>()))
+      return false;
+    DevBuf newA(sizeof(T) * (size_t)p * rn * batch), newB(sizeof(T) * (size_t)n2 * rn * rr * batch), G2(sizeof(T) * (size_t)p * nev * batch);
+    DevBuf w(sizeof(double) * (size_t)rn * batch);
+    if (nev < rn) {
+      fill<T>(newA.as<T>(), (int64_t)p * rn * batch, t_zero<T>());
+      fill<T>(newB.as<T>(), (int64_t)n2 * rn * rr * batch, t_zero<T>());
+      TTN_CUDA(cudaMemsetAsync(w.p, 0, w.bytes, ctx().stream));
+    }
+    heig_finalize<T>(U.as<T>(), p, nev, batch, lam.as<double>(), nullptr, newA.as<T>(), p, (int64_t)p * rn, G2.as<T>(), p,
+                     (int64_t)p * nev, w.as<double>(), rn, sig0, flags.as<int>());
+    project(G2, Th, p, nev, rn, n2, rr, newB);
+    colw[k] = std::move(w);
+    replace(k, std::move(newA));
+    replace(k + 1, std::move(newB));
+    x.rks[k + 1] = rn;
+    return true;
+  }
+};
+
+// returns false (x restored to its input) when some eigen-decomposition declined; true when the sweep stands
+template <class T>
+bool tt_compress_gram(TT<T>& x, int64_t max_bond, int sweeps, double* sigma_out, int64_t sigma_stride) {
+  const std::vector<int64_t> rks0 = x.rks;
+  GramSweep<T> gs(x, max_bond);
+  const int64_t nsteps = (int64_t)sweeps * 2 * (x.d - 1);
+  gs.sigma_stride = sigma_stride;
+  if (sigma_out && sigma_stride > 0) {
+    gs.sigdev.alloc(sizeof(double) * (size_t)nsteps * sigma_stride);
+    TTN_CUDA(cudaMemsetAsync(gs.sigdev.p, 0, gs.sigdev.bytes, ctx().stream));
+  }
+  int64_t step = 0;
+  int ngram = 0;
+  auto one = [&](int k1, bool l2r) {
+    if (gs.step(k1 - 1, l2r, step)) { gs.gram_steps.push_back((int)step); ++ngram; }
+    else {
+      gs.colw[k1 - 1].release();
+      tt_bond_truncate<T>(x, k1, max_bond, 0.0, sigma_out ? sigma_out + step * sigma_stride : nullptr, sigma_stride, &gs.retired);
+      gs.absorb_retired();
+    }
+    ++step;
+  };
+  for (int sw = 0; sw < sweeps; ++sw) {
+    for (int k = 1; k <= x.d - 1; ++k) one(k, true);
+    for (int k = x.d - 1; k >= 1; --k) one(k, false);
+  }
+  if (ngram == 0) return true;    // every bond took the classic step: nothing to verify
+  std::vector<int> hf(x.batch);
+  std::vector<double> hs;
+  TTN_CUDA(cudaMemcpyAsync(hf.data(), gs.flags.p, gs.flags.bytes, cudaMemcpyDeviceToHost, ctx().stream));
+  if (gs.sigdev.p) {
+    hs.resize((size_t)nsteps * sigma_stride);
+    TTN_CUDA(cudaMemcpyAsync(hs.data(), gs.sigdev.p, gs.sigdev.bytes, cudaMemcpyDeviceToHost, ctx().stream));
+  }
+  TTN_CUDA(cudaStreamSynchronize(ctx().stream));
+  int any = 0;
+  for (int f : hf) any |= f;
+  if (any) {
+    if (getenv("TTN_DEBUG_SVD")) fprintf(stderr, "[ttn] tt_compress: Gram path declined (flags 0x%x), redoing with the Jacobi path\n", any);
+    for (int k = 0; k < x.d; ++k)
+      if (gs.have_orig[k]) x.cores[k] = std::move(gs.orig[k]);
+    x.rks = rks0;
+    return false;
+  }
+  if (sigma_out)
+    for (int st : gs.gram_steps)
+      std::memcpy(sigma_out + (int64_t)st * sigma_stride, hs.data() + (size_t)st * sigma_stride, sizeof(double) * sigma_stride);
+  return true;
 }
 
 // src/tt_tools.jl:772-789
 template <class T>
 void tt_compress(TT<T>& x, int64_t max_bond, double truncerr, int sweeps, double* sigma_out, int64_t sigma_stride) {
   ttn_assert(sweeps >= 1, 2, "sweeps must be >= 1");
+  if (ctx().gram_compress && truncerr == 0.0 && x.d >= 2 && max_bond >= 1) {
+    if (tt_compress_gram<T>(x, max_bond, sweeps, sigma_out, sigma_stride)) return;
+  }
   int64_t step = 0;
   for (int sw = 0; sw < sweeps; ++sw) {
     for (int k = 1; k <= x.d - 1; ++k, ++step)
-      tt_bond_truncate<T>(x, k, max_bond, truncerr, sigma_out ? sigma_out + step * sigma_stride : nullptr, sigma_stride);
+      tt_bond_truncate<T>(x, k, max_bond, truncerr, sigma_out ? sigma_out + step * sigma_stride : nullptr, sigma_stride, nullptr);
     for (int k = x.d - 1; k >= 1; --k, ++step)
-      tt_bond_truncate<T>(x, k, max_bond, truncerr, sigma_out ? sigma_out + step * sigma_stride : nullptr, sigma_stride);
+      tt_bond_truncate<T>(x, k, max_bond, truncerr, sigma_out ? sigma_out + step * sigma_stride : nullptr, sigma_stride, nullptr);
   }
 }
 
@@ -388,7 +605,7 @@ void tt_compress(TT<T>& x, int64_t max_bond, double truncerr, int sweeps, double
   template void tt_add<T>(const TT<T>&, const TT<T>&, TT<T>&);                                    \
   template void tt_scale<T>(const TT<T>&, T, TT<T>&);                                             \
   template void tt_orthogonalize<T>(const TT<T>&, int, TT<T>&);                                   \
-  template void tt_bond_truncate<T>(TT<T>&, int, int64_t, double, double*, int64_t);              \
+  template void tt_bond_truncate<T>(TT<T>&, int, int64_t, double, double*, int64_t, std::vector<RetiredCore>*); \
   template void tt_compress<T>(TT<T>&, int64_t, double, int, double*, int64_t);
 INST(double)
 INST(zc)

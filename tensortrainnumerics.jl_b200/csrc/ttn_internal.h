@@ -58,6 +58,7 @@ struct Context {
   bool use_cholqr = true;           // CholeskyQR2 fast path for tall-skinny QR (TTN_NO_CHOLQR=1 disables)
   bool jacobi_noise_floor = false;  // see JAC_FLOOR2 in jacobi.cu
   bool use_cluster_jacobi = true;   // single-matrix SVDs on an 8-SM cluster (TTN_NO_CLUSTER_JACOBI=1 disables; A/B timing)
+  bool gram_compress = true;        // Gram path of tt_compress! for truncerr == 0 (heig.cu); TTN_GRAM_COMPRESS=0 disables
   int gram_jacobi_min = 640;        // Gram-block Jacobi (DMMA, two streams) for matrices with min(m, n) >= this (measured crossover);
                                     // TTN_GRAM_JACOBI=1: from 128 columns up, TTN_GRAM_JACOBI=0: never
 };
@@ -231,6 +232,14 @@ template <class T> int jacobi_gram(T* X, int m, int n, int64_t ldx, double tol, 
 template <class T> void gather_cols(const T* X, int m, int64_t ldx, const int* perm, const double* scale, int r, T* dst,
                                     int64_t rs, int64_t cs, int batch = 1, int64_t bX = 0, int64_t bperm = 0,
                                     int64_t bdst = 0);
+
+// Top eigenpairs of small Hermitian PSD matrices (heig.cu): the SVD engine of the Gram path of tt_compress!.
+template <class T> int heig_max_n();
+template <class T>
+bool heig_top(const T* G, int n, int64_t ldg, int64_t bG, int nsplit, int64_t sG, int nev, int batch, double* lam, T* U, int* flags);
+template <class T>
+void heig_finalize(const T* U, int n, int nev, int batch, const double* lam, const double* w_in, T* out1, int64_t ld1, int64_t b1,
+                   T* out2, int64_t ld2, int64_t b2, double* sig_out, int64_t bsig, double* sig0, int* flags);
 
 // left singular vectors + singular values of a strided p x q matrix (svd.cu)
 struct SvdLeft {

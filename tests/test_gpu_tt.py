@@ -244,7 +244,9 @@ def test_cuda_matches_golden():
     K_matfree, the Heisenberg ground-state energy (examples/heisenberg_xyz_dmrg.jl:9-19) and a prescribed-spectrum SVD."""
     import os
     import ttn_b200 as t
-    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hotpath_golden.npz"))
+    import _golden
+    g = _golden.load()     # Julia-made outputs (tests/golden/make_golden.jl) take precedence over the oracle-made ones
+    print("golden provenance:", g["__provenance__"])
 
     def tt_from(prefix, d, dims=None):
         rks = [int(v) for v in g[prefix + "_rks"]]

@@ -1,0 +1,36 @@
+"""Times the Gram-path eigensolver (csrc/heig.cu) at the cfg2 / cfg5 shapes: python tools/heig_probe.py"""
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ttn_b200 as t
+import torch
+
+
+def run(n, nev, batch, cplx, reps=3):
+    rng = np.random.default_rng(0)
+    th = rng.standard_normal((n, 4 * n)) + (1j * rng.standard_normal((n, 4 * n)) if cplx else 0)
+    G = th @ th.conj().T
+    Gb = np.broadcast_to(G, (batch, n, n)).copy()
+    t.heig_top(Gb, nev)
+    best = 1e9
+    for _ in range(reps):
+        t.profile(True)
+        t.heig_top(Gb, nev)
+        best = min(best, t.profile_read()["jacobi"][0])     # the three kernels are bracketed as one family record
+        t.profile(False)
+    return best
+
+
+if __name__ == "__main__":
+    out = {}
+    cases = ((128, 64, 1, False), (64, 64, 1, False), (128, 64, 256, True)) if len(sys.argv) > 1 and sys.argv[1] == "short" else ((128, 64, 1, False), (64, 64, 1, False), (128, 64, 1, True), (128, 64, 256, True), (64, 64, 256, True),
+                                (128, 64, 148, True), (128, 64, 296, False))
+    for n, nev, batch, cplx in cases:
+        out[f"n{n}_nev{nev}_b{batch}_{'c' if cplx else 'r'}"] = run(n, nev, batch, cplx)
+    print(json.dumps(out))
