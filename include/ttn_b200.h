@@ -106,6 +106,11 @@ int ttn_orthogonalize(ttn_ttv x, int center, ttn_ttv* y);
  * is not executed.  sigma_out (optional, may be NULL) receives, for batch element 0, the retained singular
  * values of every bond step, each step padded to `sigma_stride` doubles (2*(d-1)*sweeps steps). */
 int ttn_compress(ttn_ttv x, int64_t max_bond, double truncerr, int sweeps, double* sigma_out, int64_t sigma_stride);
+/* y = tt_compress!(A * x, max_bond; truncerr, sweeps): `*(A, v)` (src/tt_operations.jl:101-111) fused into the first pass of
+ * `tt_compress!` (src/tt_tools.jl:772-789).  With truncerr == 0 the product cores (n, R r, R' r') are consumed by the two-site
+ * merges without being written to memory; results equal ttn_apply followed by ttn_compress (same sigma_out layout). */
+int ttn_apply_compress(ttn_tto A, ttn_ttv x, int64_t max_bond, double truncerr, int sweeps, double* sigma_out, int64_t sigma_stride,
+                       ttn_ttv* y);
 /* _tt_bond_truncate!(x, k; max_bond, truncerr), k 1-based; mutates x; if y != NULL also returns
  * orthogonalize(x; i = k) as the reference does.                src/tt_tools.jl:743-770 */
 int ttn_bond_truncate(ttn_ttv x, int k, int64_t max_bond, double truncerr, ttn_ttv* y);

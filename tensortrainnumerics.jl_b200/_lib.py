@@ -73,6 +73,7 @@ def load():
         "ttn_apply": [vp, vp, vpp], "ttn_dot": [vp, vp, dp], "ttn_norm": [vp, dp], "ttn_add": [vp, vp, vpp],
         "ttn_scale": [vp, C.c_double, C.c_double, vpp], "ttn_orthogonalize": [vp, C.c_int, vpp],
         "ttn_compress": [vp, C.c_int64, C.c_double, C.c_int, dp, C.c_int64],
+        "ttn_apply_compress": [vp, vp, C.c_int64, C.c_double, C.c_int, dp, C.c_int64, vpp],
         "ttn_bond_truncate": [vp, C.c_int, C.c_int64, C.c_double, vpp],
         "ttn_swap_sites": [vp, C.c_int, C.c_int, C.c_int64, C.c_double],
         "ttn_merge_sites_diag": [vp, C.c_int],

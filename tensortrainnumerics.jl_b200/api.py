@@ -32,7 +32,7 @@ __all__ = [
     "euclidean_distance_normalized",
     "orthogonalize", "tt_compress_", "tt_bond_truncate_", "als_linsolve", "als_eigsolve", "als_gen_eigsolv", "mals_linsolve",
     "mals_eigsolve", "dmrg_linsolve", "dmrg_eigsolve", "tdvp", "tdvp2", "matvec2", "env_left", "env_right",
-    "shard_range", "shard_batch", "assemble_slices", "ShardedMatvec", "svdtrunc", "heig_top", "set_option", "get_option", "qr_thin", "gemm_host", "launch_count", "reset_launch_count", "synchronize", "library_path", "profile", "profile_read", "stream_handle",
+    "shard_range", "shard_batch", "assemble_slices", "ShardedMatvec", "apply_compress", "svdtrunc", "heig_top", "set_option", "get_option", "qr_thin", "gemm_host", "launch_count", "reset_launch_count", "synchronize", "library_path", "profile", "profile_read", "stream_handle",
     "KERNEL_FAMILIES",
 ]
 
@@ -173,6 +173,39 @@ class DeviceTT:
         check(lib.ttn_ttv_upload(code, d, _i64(x0.ttv_dims), _i64(x0.ttv_rks), _i64(x0.ttv_ot), ptrs, len(xs),
                                  C.byref(out)))
         return cls(out)
+
+    @classmethod
+    def upload_batched(cls, cores, dims, rks, ot=None):
+        """A batch of identically shaped trains given as ONE array per site, `cores[k]` of shape (n_k, r_k, r_{k+1}, batch),
+        Fortran-contiguous (e.g. views of pinned host memory): no host-side repacking, one H2D copy per site."""
+        d = len(cores)
+        dt = np.result_type(*[c.dtype for c in cores])
+        code = _dtype_code(dt)
+        batch = cores[0].shape[3]
+        ptrs = (C.c_void_p * d)()
+        for k, c in enumerate(cores):
+            if c.shape != (dims[k], rks[k], rks[k + 1], batch) or not c.flags["F_CONTIGUOUS"] or c.dtype != dt:
+                raise AssertionError("Incompatible dimensions")
+            ptrs[k] = c.ctypes.data
+        out = C.c_void_p()
+        check(_lib.lib().ttn_ttv_upload(code, d, _i64(dims), _i64(rks), _i64(ot if ot is not None else [0] * d), ptrs, batch,
+                                        C.byref(out)))
+        return cls(out)
+
+    def download_into(self, arrays):
+        """device -> host into caller-provided Fortran-contiguous arrays (one per site, with the trailing batch axis when
+        batch > 1); the counterpart of `upload_batched` for pinned result buffers."""
+        code, d, batch = self._info()
+        dims, rks = self.ttv_dims, self.ttv_rks
+        ptrs = (C.c_void_p * d)()
+        for k in range(d):
+            shp = (dims[k], rks[k], rks[k + 1]) + ((batch,) if batch > 1 else ())
+            a = arrays[k]
+            if tuple(a.shape) != shp or not a.flags["F_CONTIGUOUS"] or a.dtype != _np_dtype(code):
+                raise AssertionError("Incompatible dimensions")
+            ptrs[k] = a.ctypes.data
+        check(_lib.lib().ttn_ttv_download(self._h, ptrs))
+        return arrays
 
     # -- metadata ---------------------------------------------------------------------------------------
     def _info(self):
@@ -424,6 +457,30 @@ def orthogonalize(x, i: int = 1):
     return _ret(DeviceTT(out), host)
 
 
+def apply_compress(A, x, max_bond: int, truncerr: float = 0.0, sweeps: int = 1, return_sigma: bool = False):
+    """`tt_compress!(A * x, max_bond; truncerr, sweeps)` as ONE call (`ttn_apply_compress`): src/tt_operations.jl:101-111 fused
+    into the first pass of src/tt_tools.jl:772-789 — for truncerr == 0 the product cores never reach HBM.  Same result as
+    `tt_compress_(apply(A, x), max_bond, ...)`."""
+    lib = _lib.lib()
+    xd, host = _dev(x)
+    Ad = _devo(A, xd.dtype)
+    if Ad.dtype == np.complex128 and xd.dtype != np.complex128:
+        xd = xd.complex()
+    sig, stride, nsteps = None, 0, 0
+    if return_sigma:
+        stride = int(min(int(max_bond), 4096))      # retained singular values per bond step never exceed max_bond
+        nsteps = 2 * (xd.N - 1) * max(int(sweeps), 0)
+        sig = (C.c_double * max(1, stride * nsteps))()
+    out = C.c_void_p()
+    check(lib.ttn_apply_compress(Ad._h, xd._h, int(max_bond), float(truncerr), int(sweeps), sig, int(stride), C.byref(out)))
+    yd = DeviceTT(out)
+    res = yd.download() if host else yd
+    if return_sigma:
+        s = np.array(sig[:]).reshape(nsteps, stride) if nsteps else np.zeros((0, stride))
+        return res, [row[row > 0] for row in s]
+    return res
+
+
 def tt_compress_(x, max_bond: int, truncerr: float = 0.0, sweeps: int = 1, verbose: bool = False, return_sigma: bool = False):
     """`tt_compress!(ψ, max_bond; truncerr, sweeps, verbose)`, src/tt_tools.jl:772-789: mutates and returns `x`.
     With `return_sigma=True` also returns the retained singular values of every bond step."""
@@ -602,7 +659,7 @@ def mals_eigsolve(A, tt_start, tol=1e-12, sweep_schedule=(2,), rmax_schedule=Non
 
 
 def dmrg_linsolve(A, b, tt_start, sweep_count=2, N=2, tol=1e-12, sweep_schedule=(2,), rmax_schedule=None, it_solver=True,
-                  linsolv_maxiter=200, linsolv_tol=None, itslv_thresh=256, return_info=False, krylovdim=30, symmetrize=False):
+                  linsolv_maxiter=200, linsolv_tol=None, itslv_thresh=256, return_info=False, krylovdim=30, symmetrize=True):
     """src/solvers/dmrg.jl:385-473 (`sweep_count` is accepted and ignored, as in the reference :386)."""
     if rmax_schedule is None:
         rmax_schedule = [_isqrt_prod(tt_start.ttv_dims)]
@@ -617,7 +674,7 @@ def dmrg_linsolve(A, b, tt_start, sweep_count=2, N=2, tol=1e-12, sweep_schedule=
 
 
 def dmrg_eigsolve(A, tt_start, N=2, tol=1e-12, sweep_schedule=(2,), rmax_schedule=None, it_solver=False,
-                  linsolv_maxiter=200, linsolv_tol=None, itslv_thresh=256, krylovdim=30, symmetrize=False):
+                  linsolv_maxiter=200, linsolv_tol=None, itslv_thresh=256, krylovdim=30, symmetrize=True):
     """src/solvers/dmrg.jl:501-578 → (E, tt_opt, r_hist)."""
     if rmax_schedule is None:
         rmax_schedule = [_isqrt_prod(tt_start.ttv_dims)]

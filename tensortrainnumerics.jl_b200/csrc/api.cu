@@ -94,6 +94,9 @@ int ttn_get_option(const char* key, double* value) {
   else if (k == "gram_jacobi_min") *value = c.gram_jacobi_min;
   else if (k == "use_cholqr") *value = c.use_cholqr;
   else if (k == "use_cluster_jacobi") *value = c.use_cluster_jacobi;
+  else if (k == "gram_calls") *value = (double)c.gram_calls;
+  else if (k == "gram_fallbacks") *value = (double)c.gram_fallbacks;
+  else if (k == "gram_last_flags") *value = (double)c.gram_last_flags;
   else throw Error(TTN_EARG, "ttn_get_option: unknown key " + k);
   API_END
 }
@@ -380,6 +383,21 @@ int ttn_compress(ttn_ttv x, int64_t max_bond, double truncerr, int sweeps, doubl
   ttn_assert(x != nullptr, TTN_EARG, "null handle");
   if (x->dtype == TTN_F64) tt_compress(x->r, max_bond, truncerr, sweeps, sigma_out, sigma_stride);
   else tt_compress(x->c, max_bond, truncerr, sweeps, sigma_out, sigma_stride);
+  API_END
+}
+int ttn_apply_compress(ttn_tto A, ttn_ttv x, int64_t max_bond, double truncerr, int sweeps, double* sigma_out, int64_t sigma_stride,
+                       ttn_ttv* y) {
+  API_BEGIN
+  need_init();
+  ttn_assert(A && x && y, TTN_EARG, "null handle");
+  same_dtype(A->dtype, x->dtype);
+  ttn_ttv h = new ttn_ttv_s();
+  h->dtype = x->dtype;
+  try {
+    if (x->dtype == TTN_F64) tt_apply_compress(A->r, x->r, h->r, max_bond, truncerr, sweeps, sigma_out, sigma_stride);
+    else tt_apply_compress(A->c, x->c, h->c, max_bond, truncerr, sweeps, sigma_out, sigma_stride);
+  } catch (...) { delete h; throw; }
+  *y = h;
   API_END
 }
 int ttn_bond_truncate(ttn_ttv x, int k, int64_t max_bond, double truncerr, ttn_ttv* y) {

@@ -211,14 +211,177 @@ __global__ void __launch_bounds__(512) heig_tridiag_kernel(const T* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// K1 (Float64, latency path): the same tridiagonalisation with the whole symmetric matrix in REGISTERS — 4 lanes per row,
+// lane lq holds A(i, lq + 4 m), m < NJ.  A step touches every trailing element once in the matrix-vector product (one
+// broadcast shared-memory load + one DFMA) and once in the rank-2 update (one 16-byte load + two DFMAs): no matrix traffic
+// through shared memory, no address arithmetic, perfectly balanced rows.  Rows k+1 and k+2 are published to shared memory
+// after every update: by symmetry they are the next pivot column x and the next y1 = A(:, k+2).
+// ---------------------------------------------------------------------------------------------------------------------
+template <int NJ>
+__global__ void __launch_bounds__(512) heig_tridiag_reg_kernel(const double* __restrict__ Gp, int n, int64_t ldg, int64_t bG, int nsplit,
+                                                                int64_t sG, double* __restrict__ d_out, double* __restrict__ e_out,
+                                                                double* __restrict__ tau_out, double* __restrict__ V_out, int64_t bV) {
+  constexpr int NP = 4 * NJ;
+  __shared__ __align__(16) double xs[NP];
+  __shared__ __align__(16) double ys[NP];
+  __shared__ __align__(16) double2 vw[NP];
+  __shared__ double red[3 * 32];
+  __shared__ double y0s[2];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ir = lane & 7, lq = lane >> 3;
+  const int i = warp * 8 + ir;
+  const int64_t mb = blockIdx.x;
+  const double* Gb = Gp + mb * bG;
+  d_out += mb * n; e_out += mb * n; tau_out += mb * n; V_out += mb * bV;
+
+  double a[NJ];
+#pragma unroll
+  for (int m = 0; m < NJ; ++m) {
+    const int j = lq + 4 * m;
+    double v = 0.0;
+    if (i < n && j < n)
+      for (int s = 0; s < nsplit; ++s) v += Gb[s * sG + j + (int64_t)i * ldg];
+    a[m] = v;
+  }
+  for (int idx = tid; idx < NP; idx += blockDim.x) { xs[idx] = 0.0; ys[idx] = 0.0; vw[idx] = make_double2(0.0, 0.0); }
+  for (int idx = tid; idx < 96; idx += blockDim.x) red[idx] = 0.0;
+  __syncthreads();
+  if (i == 0 || i == 1) {
+    double* dst = i == 0 ? xs : ys;
+    if (i < n) {
+#pragma unroll
+      for (int m = 0; m < NJ; ++m) dst[lq + 4 * m] = a[m];
+    }
+  }
+  __syncthreads();
+
+  for (int k = 0; k < n - 1; ++k) {
+    const int k1 = k + 1;
+    const bool rowact = (i > k) && (i < n);
+    const int m_lo = (k + 2) >> 2;
+    // ---- A: y2_i = sum_{j >= k+2} A(i,j) x_j ----
+    double y2 = 0.0;
+    if (rowact) {
+      double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+#pragma unroll
+      for (int m = 0; m < NJ; ++m) {
+        if (m >= m_lo) {
+          const int j = lq + 4 * m;
+          const double xv = (m > m_lo || j >= k + 2) ? xs[j] : 0.0;
+          if ((m & 3) == 0) c0 = fma(a[m], xv, c0);
+          else if ((m & 3) == 1) c1 = fma(a[m], xv, c1);
+          else if ((m & 3) == 2) c2 = fma(a[m], xv, c2);
+          else c3 = fma(a[m], xv, c3);
+        }
+      }
+      y2 = (c0 + c1) + (c2 + c3);
+    }
+    y2 += __shfl_xor_sync(0xffffffffu, y2, 8);
+    y2 += __shfl_xor_sync(0xffffffffu, y2, 16);
+    double y1 = 0.0, xi = 0.0, q0 = 0.0, q1 = 0.0, q2 = 0.0;
+    if (rowact && lq == 0) {
+      y1 = ys[i];
+      if (i == k1) { y0s[0] = y1; y0s[1] = y2; }
+      else {
+        xi = xs[i];
+        q0 = xi * xi; q1 = y1 * xi; q2 = y2 * xi;
+      }
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+      q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+      q2 += __shfl_xor_sync(0xffffffffu, q2, o);
+    }
+    if (lane == 0) { red[warp] = q0; red[32 + warp] = q1; red[64 + warp] = q2; }
+    __syncthreads();   // 1
+    // ---- B: scalars, v, w ----
+    q0 = red[lane]; q1 = red[32 + lane]; q2 = red[64 + lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+      q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+      q2 += __shfl_xor_sync(0xffffffffu, q2, o);
+    }
+    const double xn2 = q0;
+    const double ar = xs[k1];
+    const bool have = xn2 != 0.0;
+    double beta = ar, tau = 0.0;
+    if (have) {
+      const double s2 = fma(ar, ar, xn2);
+      const double inv = rsqrt(s2), nrm = s2 * inv;
+      const double sg = ar >= 0.0 ? 1.0 : -1.0;
+      beta = -sg * nrm;
+      tau = fma(fabs(ar), inv, 1.0);
+      const double dr = sg * (fabs(ar) + nrm);          // alpha - beta
+      const double r1 = rsqrt(dr * dr), sc = sg * r1 * r1 * fabs(dr);   // 1 / (alpha - beta)
+      if (rowact && lq == 0) {
+        // p^T v = tau [y1_0 + s y2_0 + s a + s^2 b]
+        const double pv = tau * (y0s[0] + sc * (y0s[1] + q1 + sc * q2));
+        const double a2 = -0.5 * tau * pv;
+        const double vi = (i == k1) ? 1.0 : sc * xi;
+        const double p = tau * fma(sc, y2, y1);
+        vw[i] = make_double2(vi, fma(a2, vi, p));
+        V_out[refl_off(k, n) + (i - k1)] = vi;
+      }
+    } else if (rowact && lq == 0) {
+      V_out[refl_off(k, n) + (i - k1)] = (i == k1) ? 1.0 : 0.0;
+    }
+    if (tid == 0) { d_out[k] = xs[k]; e_out[k] = beta; tau_out[k] = tau; }
+    __syncthreads();   // 2
+    // ---- C: A22 -= v w^T + w v^T (whole rows), hand rows k+1, k+2 over ----
+    if (rowact) {
+      if (have) {
+        const double2 me = vw[i];
+        const int m_c = k1 >> 2;
+#pragma unroll
+        for (int m = 0; m < NJ; ++m) {
+          if (m >= m_c) {
+            const double2 o = vw[lq + 4 * m];      // zero beyond n; columns < k+1 of the m_c group are dead
+            a[m] = fma(-me.x, o.y, fma(-me.y, o.x, a[m]));
+          }
+        }
+      }
+      if (i == k1 || i == k1 + 1) {
+        double* dst = i == k1 ? xs : ys;
+#pragma unroll
+        for (int m = 0; m < NJ; ++m) dst[lq + 4 * m] = a[m];
+      }
+    }
+    __syncthreads();   // 3
+  }
+  if (tid == 0) { d_out[n - 1] = xs[n - 1]; e_out[n - 1] = 0.0; tau_out[n - 1] = 0.0; }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // K2a: eigenvalues n-1-j (ascending index), j < nev, of tridiag(d, e) by multisection on T / |T|: M lanes (aligned
 // segment of a warp) per eigenvalue, grid.x CTAs share the eigenvalues of one matrix.  lam_s: scaled eigenvalues
 // (descending in j), tn_out: |T| bound (Gershgorin); tn = 0 marks a zero / non-finite matrix.
 // ---------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int sturm_count(const double* __restrict__ ds, const double* __restrict__ e2, int n, double x) {
+// number of eigenvalues below x (sign changes of the scaled Sturm sequence).  An exact zero p_i counts correctly by its
+// sign bit alone (p_{i+1} = -e^2 p_{i-1}: one change across the triple) unless the next e is zero too, so the zero test is
+// kept off the dependency chain: it only raises `zero`, and the rare evaluation that saw one is redone by the guarded loop.
+__device__ __forceinline__ int sturm_count_safe(const double* __restrict__ ds, const double* __restrict__ e2, int n, double x) {
   int cnt;
   double pm1 = 1.0, p = ds[0] - x;
   if (p == 0.0) p = -1e-300;
+  cnt = p < 0.0;
+  for (int i = 1; i < n; ++i) {
+    double pn = (ds[i] - x) * p - e2[i - 1] * pm1;
+    if (pn == 0.0) pn = p < 0.0 ? 1e-300 : -1e-300;
+    cnt += (unsigned)(__double2hiint(pn) ^ __double2hiint(p)) >> 31;
+    pm1 = p; p = pn;
+    const double a = fmax(fabs(p), fabs(pm1));
+    if (a < 1e-100) { p *= 1e100; pm1 *= 1e100; }
+    else if (a > 1e100) { p *= 1e-100; pm1 *= 1e-100; }
+  }
+  return cnt;
+}
+
+__device__ __forceinline__ int sturm_count(const double* __restrict__ ds, const double* __restrict__ e2, int n, double x) {
+  int cnt;
+  double pm1 = 1.0, p = ds[0] - x;
+  bool zero = (p == 0.0);
   cnt = p < 0.0;
   int i = 1;
   for (; i + 7 < n; i += 8) {
@@ -227,8 +390,8 @@ __device__ __forceinline__ int sturm_count(const double* __restrict__ ds, const 
     for (int u = 0; u < 8; ++u) { dv[u] = ds[i + u] - x; ev[u] = e2[i + u - 1]; }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      double pn = dv[u] * p - ev[u] * pm1;
-      if (pn == 0.0) pn = p < 0.0 ? 1e-300 : -1e-300;
+      const double pn = fma(dv[u], p, -(ev[u] * pm1));
+      zero |= (pn == 0.0);
       cnt += (unsigned)(__double2hiint(pn) ^ __double2hiint(p)) >> 31;
       pm1 = p; p = pn;
     }
@@ -237,11 +400,12 @@ __device__ __forceinline__ int sturm_count(const double* __restrict__ ds, const 
     else if (a > 1e100) { p *= 1e-100; pm1 *= 1e-100; }
   }
   for (; i < n; ++i) {
-    double pn = (ds[i] - x) * p - e2[i - 1] * pm1;
-    if (pn == 0.0) pn = p < 0.0 ? 1e-300 : -1e-300;
+    const double pn = fma(ds[i] - x, p, -(e2[i - 1] * pm1));
+    zero |= (pn == 0.0);
     cnt += (unsigned)(__double2hiint(pn) ^ __double2hiint(p)) >> 31;
     pm1 = p; p = pn;
   }
+  if (zero) return sturm_count_safe(ds, e2, n, x);
   return cnt;
 }
 
@@ -482,7 +646,11 @@ __global__ void __launch_bounds__(1024) heig_vec_kernel(const double* __restrict
   // modified Gram-Schmidt inside clusters (eigenvalues closer than ctol |T|); block-cooperative, rare
   int cstart = 0;
   for (int j = 1; j <= nev; ++j) {
-    const bool brk = (j == nev) || (lam_s[j - 1] - lam_s[j] >= ctol);
+    // cluster: the gap does not separate the two vectors to the accuracy the reconstruction needs.  The twisted vectors of
+    // eigenvalues gap apart are orthogonal to eps/gap (scaled units) and enter the reconstruction with weight sigma =
+    // sqrt(lambda), so the gap that matters shrinks with sqrt(lambda): small but well separated eigenvalues of a full
+    // spectrum are NOT a cluster.
+    const bool brk = (j == nev) || (lam_s[j - 1] - lam_s[j] >= ctol * sqrt(fmax(lam_s[j - 1], 0.0)) + 1e-14);
     if (!brk) continue;
     const int csize = j - cstart;
     if (csize > 8) {
@@ -648,7 +816,21 @@ bool heig_top(const T* G, int n, int64_t ldg, int64_t bG, int nsplit, int64_t sG
   DevBuf V(sizeof(T) * (size_t)bV * batch), Z(sizeof(double) * (size_t)n * nev * batch);
   DevBuf lam_s(sizeof(double) * (size_t)nev * batch), tn(sizeof(double) * (size_t)batch);
   ProfScope prof_scope_(KF_JACOBI);
-  {
+  bool done_tridiag = false;
+  if (!is_cplx<T>::value && n <= 128 && n >= 2) {
+    // Float64: whole matrix in registers (latency path of the single-train rounding chain; also the fastest batched form)
+    const int nt = ((n + 7) / 8) * 32;
+    const double* Gd = reinterpret_cast<const double*>(G);
+    double* taud = reinterpret_cast<double*>(tau.p);
+    double* Vd = reinterpret_cast<double*>(V.p);
+    if (n <= 32) heig_tridiag_reg_kernel<8><<<batch, nt, 0, ctx().stream>>>(Gd, n, ldg, bG, nsplit, sG, d.as<double>(), e.as<double>(), taud, Vd, bV);
+    else if (n <= 64) heig_tridiag_reg_kernel<16><<<batch, nt, 0, ctx().stream>>>(Gd, n, ldg, bG, nsplit, sG, d.as<double>(), e.as<double>(), taud, Vd, bV);
+    else heig_tridiag_reg_kernel<32><<<batch, nt, 0, ctx().stream>>>(Gd, n, ldg, bG, nsplit, sG, d.as<double>(), e.as<double>(), taud, Vd, bV);
+    TTN_CHECK_LAUNCH();
+    ctx().launches++;
+    done_tridiag = true;
+  }
+  if (!done_tridiag) {
     auto kern = heig_tridiag_kernel<T>;
     const size_t smem = tridiag_smem<T>(n);
     static int attr_dev = -1;

@@ -389,8 +389,46 @@ void tt_bond_truncate(TT<T>& x, int k1, int64_t max_bond, double truncerr, doubl
 // preserved input cores by the QR + one-sided-Jacobi path.  Bonds the eigensolver does not serve (more than 128 / 176
 // rows, tall Theta) take the classic step inside the same sweep.
 // ---------------------------------------------------------------------------------------------------------------------
+// Theta[row, i + n2 (b + Wr mu)] = sum_{a,j} A[i,j,a,b] Z[row, a + Wl j, mu]: the MPO core of site k+1 applied to
+// Z = P x_{k+1} (the apply of src/tt_operations.jl:105-108 folded into the two-site merge of tt_tools.jl:749): the product
+// core y_{k+1} (n2, Wl r, Wr r') is never written to HBM.  One CTA per (mu, train), one thread per row; A in shared memory.
+template <class T>
+__global__ void __launch_bounds__(256) kron_mix_kernel(const T* __restrict__ Z, const T* __restrict__ A, T* __restrict__ Th, int p,
+                                                       int n2, int Wl, int Wr, int rp, int64_t bZ, int64_t bTh) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* As = reinterpret_cast<T*>(smem_raw);   // [ (i,b) ][ (a,j) ]
+  const int KA = Wl * n2, KB = n2 * Wr;
+  for (int t = threadIdx.x; t < KA * KB; t += blockDim.x) {
+    const int aj = t % KA, ib = t / KA;
+    const int a = aj % Wl, j = aj / Wl, i = ib % n2, b = ib / n2;
+    As[t] = A[i + n2 * (j + n2 * (a + Wl * b))];
+  }
+  __syncthreads();
+  const int mu = blockIdx.x;
+  const T* Zb = Z + blockIdx.y * bZ + (int64_t)p * KA * mu;
+  T* Tb = Th + blockIdx.y * bTh + (int64_t)p * KB * mu;
+  for (int row = threadIdx.x; row < p; row += blockDim.x) {
+    for (int ib = 0; ib < KB; ++ib) {
+      T acc = t_zero<T>();
+      const T* ar = As + ib * KA;
+      for (int aj = 0; aj < KA; ++aj) t_fma(acc, ar[aj], Zb[row + (int64_t)p * aj]);
+      Tb[row + (int64_t)p * ib] = acc;
+    }
+  }
+  (void)rp;
+}
+
+// y = A * x not yet materialised beyond its first core: the L->R pass of the Gram sweep consumes (A_{k+1}, x_{k+1}) directly
+template <class T>
+struct LazyProd {
+  const TTO<T>* A = nullptr;
+  const TT<T>* x = nullptr;
+  std::vector<char> virt;     // virt[k] != 0: core k of y is still the un-materialised product A_k (x) x_k
+};
+
 template <class T>
 struct GramSweep {
+  LazyProd<T>* lazy = nullptr;
   TT<T>& x;
   int64_t max_bond;
   DevBuf flags;                       // int per train, sticky
@@ -444,9 +482,49 @@ struct GramSweep {
     g.batch1 = n2; g.batch2 = batch;
     gemm<T>(g);
   }
+  void materialize(int k) {
+    if (!lazy || !lazy->virt[k]) return;
+    const TTO<T>& A = *lazy->A;
+    const TT<T>& v = *lazy->x;
+    x.alloc_core(k);
+    apply_core<T>(A.core(k), v.core(k), x.core(k), (int)A.dims[k], (int)A.dims[k], (int)A.rks[k], (int)A.rks[k + 1], (int)v.rks[k],
+                  (int)v.rks[k + 1], v.batch, v.core_elems(k), x.core_elems(k));
+    lazy->virt[k] = 0;
+  }
+  // Theta (p x q) of bond (k, k+1) when core k+1 is still A_{k+1} (x) x_{k+1}:  Z = P x_{k+1} (GEMMs), then the MPO mix
+  void theta_lazy(int k, DevBuf& Th) {
+    const TTO<T>& A = *lazy->A;
+    const TT<T>& v = *lazy->x;
+    const int batch = x.batch;
+    const int n1 = (int)x.dims[k], n2 = (int)x.dims[k + 1];
+    const int p = n1 * (int)x.rks[k];
+    const int Wl = (int)A.rks[k + 1], Wr = (int)A.rks[k + 2], r = (int)v.rks[k + 1], rp = (int)v.rks[k + 2];
+    const int KA = Wl * n2, KB = n2 * Wr;
+    DevBuf Z(sizeof(T) * (size_t)p * KA * rp * batch);
+    for (int j = 0; j < n2; ++j) {
+      GemmArgs g;   // Z[row, a + Wl j, mu] = sum_nu P[row, a + Wl nu] x[j, nu, mu]
+      g.M = p; g.N = rp; g.K = r;
+      g.A = x.cores[k].p; g.sAm = 1; g.sAk = (int64_t)Wl * p; g.bA1 = p; g.bA2 = x.core_elems(k);
+      g.B = v.core(k + 1) + j; g.sBk = n2; g.sBn = (int64_t)n2 * r; g.bB1 = 0; g.bB2 = v.core_elems(k + 1);
+      g.C = Z.as<T>() + (int64_t)p * Wl * j; g.sCm = 1; g.sCn = (int64_t)p * KA; g.bC1 = p; g.bC2 = (int64_t)p * KA * rp;
+      g.batch1 = Wl; g.batch2 = batch;
+      gemm<T>(g);
+    }
+    const int nt = std::min(256, ((p + 31) / 32) * 32);
+    ProfScope prof_scope_(KF_APPLY);
+    for (int b0 = 0; b0 < batch; b0 += 65535) {
+      const int nb = std::min(65535, batch - b0);
+      kron_mix_kernel<T><<<dim3(rp, nb), nt, sizeof(T) * (size_t)KA * KB, ctx().stream>>>(
+          Z.as<T>() + (int64_t)b0 * p * KA * rp, A.core(k + 1), Th.as<T>() + (int64_t)b0 * p * KB * rp, p, n2, Wl, Wr, rp,
+          (int64_t)p * KA * rp, (int64_t)p * KB * rp);
+      TTN_CHECK_LAUNCH();
+      ctx().launches++;
+    }
+  }
   // one bond step; returns false when the shape is not served (caller takes the classic step)
   bool step(int k, bool left_to_right, int64_t step_idx) {
     const int batch = x.batch;
+    materialize(k);
     const int n1 = (int)x.dims[k], n2 = (int)x.dims[k + 1];
     const int rl = (int)x.rks[k], r = (int)x.rks[k + 1], rr = (int)x.rks[k + 2];
     const int p = n1 * rl, q = n2 * rr, kmin = std::min(p, q);
@@ -455,6 +533,7 @@ struct GramSweep {
     const bool have_w = !left_to_right && colw[k].p != nullptr && colw[k].bytes == sizeof(double) * (size_t)r * batch;
     double* sig0 = sigdev.p ? sigdev.as<double>() + step_idx * sigma_stride : nullptr;
     if (have_w) {
+      materialize(k + 1);
       if (r > heig_max_n<T>() || r > q) return false;
       const int nev = std::min(rn, r);
       if ((int64_t)nev > sigma_stride && sig0) return false;
@@ -494,12 +573,15 @@ struct GramSweep {
       x.rks[k + 1] = rn;
       return true;
     }
-    if (!left_to_right) return false;
-    if (p > q || p > heig_max_n<T>()) return false;
+    const bool virt = lazy && lazy->virt[k + 1];
+    const bool served = left_to_right && p <= q && p <= heig_max_n<T>() && !((int64_t)std::min(rn, r) > sigma_stride && sig0);
+    if (!served) { materialize(k + 1); return false; }
     const int nev = std::min(rn, r);
-    if ((int64_t)nev > sigma_stride && sig0) return false;
     DevBuf Th(sizeof(T) * (size_t)p * q * batch);
-    {
+    if (virt && (size_t)lazy->A->rks[k + 1] * n2 * n2 * lazy->A->rks[k + 2] * sizeof(T) <= 40 * 1024) {
+      theta_lazy(k, Th);           // core k+1 stays virtual until the truncated core replaces it below
+    } else {
+      materialize(k + 1);
       GemmArgs g;  // Theta[(s1,alpha),(s2,beta)] = sum_gamma A[s1,alpha,gamma] B[s2,gamma,beta]     (tt_tools.jl:749)
       g.M = p; g.N = rr; g.K = r;
       g.A = x.cores[k].p; g.sAm = 1; g.sAk = p; g.bA1 = 0; g.bA2 = x.core_elems(k);
@@ -527,6 +609,7 @@ struct GramSweep {
     colw[k] = std::move(w);
     replace(k, std::move(newA));
     replace(k + 1, std::move(newB));
+    if (lazy) lazy->virt[k + 1] = 0;
     x.rks[k + 1] = rn;
     return true;
   }
@@ -534,9 +617,10 @@ struct GramSweep {
 
 // returns false (x restored to its input) when some eigen-decomposition declined; true when the sweep stands
 template <class T>
-bool tt_compress_gram(TT<T>& x, int64_t max_bond, int sweeps, double* sigma_out, int64_t sigma_stride) {
+bool tt_compress_gram(TT<T>& x, int64_t max_bond, int sweeps, double* sigma_out, int64_t sigma_stride, LazyProd<T>* lazy = nullptr) {
   const std::vector<int64_t> rks0 = x.rks;
   GramSweep<T> gs(x, max_bond);
+  gs.lazy = lazy;
   const int64_t nsteps = (int64_t)sweeps * 2 * (x.d - 1);
   gs.sigma_stride = sigma_stride;
   if (sigma_out && sigma_stride > 0) {
@@ -545,11 +629,36 @@ bool tt_compress_gram(TT<T>& x, int64_t max_bond, int sweeps, double* sigma_out,
   }
   int64_t step = 0;
   int ngram = 0;
+  bool threw = false;   // a classic step that is fed the output of a declined Gram step may meet non-finite data
+  static const bool dbg = getenv("TTN_DEBUG_SVD") != nullptr;
+  int dbg_prev = 0;
   auto one = [&](int k1, bool l2r) {
-    if (gs.step(k1 - 1, l2r, step)) { gs.gram_steps.push_back((int)step); ++ngram; }
+    if (threw) return;
+    if (gs.step(k1 - 1, l2r, step)) {
+      gs.gram_steps.push_back((int)step); ++ngram;
+      if (dbg) {   // debugging only: a flag read per step shows which bond declined
+        std::vector<int> f(x.batch);
+        TTN_CUDA(cudaMemcpyAsync(f.data(), gs.flags.p, gs.flags.bytes, cudaMemcpyDeviceToHost, ctx().stream));
+        TTN_CUDA(cudaStreamSynchronize(ctx().stream));
+        int a = 0;
+        for (int v : f) a |= v;
+        if (a != dbg_prev) {
+          fprintf(stderr, "[ttn] gram step %lld bond %d %s ranks (%lld,%lld,%lld): flags 0x%x\n", (long long)step, k1, l2r ? "L->R" : "R->L",
+                  (long long)x.rks[k1 - 1], (long long)x.rks[k1], (long long)x.rks[k1 + 1], a);
+          dbg_prev = a;
+        }
+      }
+    }
     else {
       gs.colw[k1 - 1].release();
-      tt_bond_truncate<T>(x, k1, max_bond, 0.0, sigma_out ? sigma_out + step * sigma_stride : nullptr, sigma_stride, &gs.retired);
+      gs.materialize(k1 - 1);
+      gs.materialize(k1);
+      try {
+        tt_bond_truncate<T>(x, k1, max_bond, 0.0, sigma_out ? sigma_out + step * sigma_stride : nullptr, sigma_stride, &gs.retired);
+      } catch (const Error&) {
+        if (ngram == 0) throw;        // no Gram step before it: the error is the input's
+        threw = true;
+      }
       gs.absorb_retired();
     }
     ++step;
@@ -559,6 +668,7 @@ bool tt_compress_gram(TT<T>& x, int64_t max_bond, int sweeps, double* sigma_out,
     for (int k = x.d - 1; k >= 1; --k) one(k, false);
   }
   if (ngram == 0) return true;    // every bond took the classic step: nothing to verify
+  ctx().gram_calls++;
   std::vector<int> hf(x.batch);
   std::vector<double> hs;
   TTN_CUDA(cudaMemcpyAsync(hf.data(), gs.flags.p, gs.flags.bytes, cudaMemcpyDeviceToHost, ctx().stream));
@@ -567,9 +677,11 @@ bool tt_compress_gram(TT<T>& x, int64_t max_bond, int sweeps, double* sigma_out,
     TTN_CUDA(cudaMemcpyAsync(hs.data(), gs.sigdev.p, gs.sigdev.bytes, cudaMemcpyDeviceToHost, ctx().stream));
   }
   TTN_CUDA(cudaStreamSynchronize(ctx().stream));
-  int any = 0;
+  int any = threw ? 32 : 0;
   for (int f : hf) any |= f;
+  ctx().gram_last_flags = any;
   if (any) {
+    ctx().gram_fallbacks++;
     if (getenv("TTN_DEBUG_SVD")) fprintf(stderr, "[ttn] tt_compress: Gram path declined (flags 0x%x), redoing with the Jacobi path\n", any);
     for (int k = 0; k < x.d; ++k)
       if (gs.have_orig[k]) x.cores[k] = std::move(gs.orig[k]);
@@ -598,7 +710,40 @@ void tt_compress(TT<T>& x, int64_t max_bond, double truncerr, int sweeps, double
   }
 }
 
+// y = tt_compress!(A * x, max_bond; truncerr, sweeps)  (src/tt_operations.jl:101-111 followed by tt_tools.jl:772-789).
+// With truncerr == 0 the product cores are consumed by the L->R pass of the Gram sweep without ever being written to HBM
+// (cfg5: 40.5 MB per vector); otherwise, or when the fast path declines, it is the plain composition of the two calls.
+template <class T>
+void tt_apply_compress(const TTO<T>& A, const TT<T>& x, TT<T>& y, int64_t max_bond, double truncerr, int sweeps, double* sigma_out,
+                       int64_t sigma_stride) {
+  ttn_assert(A.d == x.d && A.dims == x.dims, 1, "Incompatible dimensions");
+  ttn_assert(sweeps >= 1, 2, "sweeps must be >= 1");
+  if (ctx().gram_compress && truncerr == 0.0 && x.d >= 2 && max_bond >= 1) {
+    y.d = x.d; y.batch = x.batch; y.dims = x.dims;
+    y.rks.resize(x.d + 1);
+    for (int k = 0; k <= x.d; ++k) y.rks[k] = A.rks[k] * x.rks[k];
+    y.ot.assign(x.d, 0);
+    y.cores.clear();
+    y.cores.resize(x.d);
+    LazyProd<T> lazy;
+    lazy.A = &A; lazy.x = &x;
+    lazy.virt.assign(x.d, 1);
+    if (tt_compress_gram<T>(y, max_bond, sweeps, sigma_out, sigma_stride, &lazy)) {
+      bool left = false;
+      for (char v : lazy.virt) left |= (v != 0);
+      ttn_assert(!left, 7, "apply_compress: a product core was never materialised");
+      return;
+    }
+  }
+  tt_apply<T>(A, x, y);
+  const bool save = ctx().gram_compress;
+  ctx().gram_compress = false;          // the fast path has just declined this input (or does not apply)
+  try { tt_compress<T>(y, max_bond, truncerr, sweeps, sigma_out, sigma_stride); } catch (...) { ctx().gram_compress = save; throw; }
+  ctx().gram_compress = save;
+}
+
 #define INST(T)                                                                                   \
+  template void tt_apply_compress<T>(const TTO<T>&, const TT<T>&, TT<T>&, int64_t, double, int, double*, int64_t); \
   template void tt_copy<T>(const TT<T>&, TT<T>&);                                                 \
   template void tt_apply<T>(const TTO<T>&, const TT<T>&, TT<T>&);                                 \
   template void tt_dot<T>(const TT<T>&, const TT<T>&, std::vector<T>&);                           \

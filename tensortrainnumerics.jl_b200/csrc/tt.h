@@ -43,6 +43,11 @@ void tt_bond_truncate(TT<T>& x, int k /*1-based*/, int64_t max_bond, double trun
 template <class T>
 void tt_compress(TT<T>& x, int64_t max_bond, double truncerr, int sweeps, double* sigma_out, int64_t sigma_stride);
 
+// y = tt_compress!(A * x, ...) with the product cores folded into the two-site merges (tt.cu)
+template <class T>
+void tt_apply_compress(const TTO<T>& A, const TT<T>& x, TT<T>& y, int64_t max_bond, double truncerr, int sweeps, double* sigma_out,
+                       int64_t sigma_stride);
+
 // site surgery (sites.cu): adjacent-site swap, diagonal merge, site split.  mode 0: relative threshold `tol` on sigma_j/sigma_1
 // (qtt_tools.jl:680-685);  mode 1: `_svdtrunc` tail-norm rule with `max_bond` cap (tt_cross_interpolation.jl:149-166)
 template <class T> void tt_swap_sites(TT<T>& x, int k /*1-based*/, int mode, int64_t max_bond, double tol);

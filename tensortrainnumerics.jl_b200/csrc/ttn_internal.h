@@ -58,6 +58,8 @@ struct Context {
   bool use_cholqr = true;           // CholeskyQR2 fast path for tall-skinny QR (TTN_NO_CHOLQR=1 disables)
   bool jacobi_noise_floor = false;  // see JAC_FLOOR2 in jacobi.cu
   bool use_cluster_jacobi = true;   // single-matrix SVDs on an 8-SM cluster (TTN_NO_CLUSTER_JACOBI=1 disables; A/B timing)
+  long long gram_calls = 0, gram_fallbacks = 0;   // tt_compress! calls that took the Gram path / were redone by the Jacobi path
+  int gram_last_flags = 0;
   bool gram_compress = true;        // Gram path of tt_compress! for truncerr == 0 (heig.cu); TTN_GRAM_COMPRESS=0 disables
   int gram_jacobi_min = 640;        // Gram-block Jacobi (DMMA, two streams) for matrices with min(m, n) >= this (measured crossover);
                                     // TTN_GRAM_JACOBI=1: from 128 columns up, TTN_GRAM_JACOBI=0: never

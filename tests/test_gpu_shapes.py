@@ -150,3 +150,36 @@ def test_gram_vs_jacobi_path_real_well_conditioned():
     for u, v, w in zip(sa, sb, sig_ref):
         assert np.abs(np.asarray(u) - np.asarray(w)).max() / w[0] < 1e-9
         assert np.abs(np.asarray(v) - np.asarray(w)).max() / w[0] < 1e-9
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_apply_compress_fused_equals_two_calls(cplx):
+    """`ttn_apply_compress` (A*x folded into the two-site merges of the first tt_compress! pass) against apply followed by
+    tt_compress!, and against the oracle: same ranks, TT distance at rounding level, same per-bond singular values; batched and
+    single; a truncerr > 0 call (plain composition) as well."""
+    import ttn_b200 as t
+    d, r, W = 12, 16, 3
+    rng = np.random.default_rng(21 + cplx)
+    dt = np.complex128 if cplx else np.float64
+    A = o.rand_tto((2,) * d, W, rng=rng, dtype=dt)
+    xs = [o.rand_tt((2,) * d, r, rng=rng, dtype=dt, normalise=True) for _ in range(5)]
+    Ad = t.DeviceTTO.upload(A)
+    xd = t.DeviceTT.upload(xs)
+    calls0, fb0 = t.get_option("gram_calls"), t.get_option("gram_fallbacks")
+    yf, sf = t.apply_compress(Ad, xd, 10, return_sigma=True)
+    assert t.get_option("gram_calls") == calls0 + 1 and t.get_option("gram_fallbacks") == fb0     # the fused fast path really ran
+    y2, s2 = t.tt_compress_(t.apply(Ad, xd), 10, return_sigma=True)
+    yf, y2 = yf.download(), y2.download()
+    for b in range(5):
+        ref = o.tt_compress(o.apply(A, xs[b]), 10)
+        assert yf[b].ttv_rks == y2[b].ttv_rks == ref.ttv_rks
+        assert o.rel_distance(yf[b], y2[b]) < 1e-10
+        assert o.rel_distance(yf[b], ref) < 1e-9
+    for u, v in zip(sf, s2):
+        assert len(u) == len(v) and np.abs(np.asarray(u) - np.asarray(v)).max() < 1e-10 * max(v[0], 1e-300)
+    # single train through the host API, and a tolerance-driven call (not served by the fast path: plain composition)
+    y1 = t.apply_compress(A, xs[0], 10)
+    assert o.rel_distance(y1, o.tt_compress(o.apply(A, xs[0]), 10)) < 1e-9
+    y3 = t.apply_compress(A, xs[1], 64, truncerr=1e-3)
+    ref3 = o.tt_compress(o.apply(A, xs[1]), 64, truncerr=1e-3)
+    assert y3.ttv_rks == ref3.ttv_rks and o.rel_distance(y3, ref3) < 1e-10

@@ -29,7 +29,7 @@ def run(n, nev, batch, cplx, reps=3):
 
 if __name__ == "__main__":
     out = {}
-    cases = ((128, 64, 1, False), (64, 64, 1, False), (128, 64, 256, True)) if len(sys.argv) > 1 and sys.argv[1] == "short" else ((128, 64, 1, False), (64, 64, 1, False), (128, 64, 1, True), (128, 64, 256, True), (64, 64, 256, True),
+    cases = ((128, 64, 1, False),) if len(sys.argv) > 1 and sys.argv[1] == "one" else ((128, 64, 256, True),) if len(sys.argv) > 1 and sys.argv[1] == "batch" else ((128, 64, 1, False), (64, 64, 1, False), (128, 64, 256, True)) if len(sys.argv) > 1 and sys.argv[1] == "short" else ((128, 64, 1, False), (64, 64, 1, False), (128, 64, 1, True), (128, 64, 256, True), (64, 64, 256, True),
                                 (128, 64, 148, True), (128, 64, 296, False))
     for n, nev, batch, cplx in cases:
         out[f"n{n}_nev{nev}_b{batch}_{'c' if cplx else 'r'}"] = run(n, nev, batch, cplx)
