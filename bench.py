@@ -220,6 +220,101 @@ def pinned_chunks(torch, nvec, chunk, rank):
     return chunks, keep
 
 
+class ChunkWorker(threading.Thread):
+    """One host thread = one library context (compute stream + copy stream + allocation cache, include/ttn_b200.h).  Each worker
+    owns every `nw`-th chunk of this rank's vectors; two workers keep two chunks in flight, so the latency-bound eigensolver
+    kernels of one chunk overlap the DMMA GEMMs of the other."""
+
+    def __init__(self, idx, nw, host_chunks, Ad, rks, torch, keep):
+        super().__init__(daemon=True)
+        import queue
+        self.idx, self.nw, self.Ad, self.rks, self.torch, self.keep = idx, nw, Ad, rks, torch, keep
+        self.host_chunks = host_chunks[idx::nw]
+        self.cmd, self.done = queue.Queue(), queue.Queue()
+        self.error = None
+
+    def run(self):
+        import ttn_b200 as t
+        torch = self.torch
+        try:
+            t.synchronize()                                   # first library call of this thread: creates its context
+            self.stream = torch.cuda.ExternalStream(t.stream_handle())
+            self.dev_chunks = [t.DeviceTT.upload_batched(c, (2,) * D5, self.rks) for c in self.host_chunks]
+            self.res_bufs = {}
+            for c in self.host_chunks:
+                nb = c[0].shape[3]
+                if nb not in self.res_bufs:
+                    self.res_bufs[nb] = [self._result_set(nb), self._result_set(nb)]
+            t.synchronize()
+            self.done.put("ready")
+            while True:
+                cmd = self.cmd.get()
+                if cmd[0] == "stop":
+                    for x in self.dev_chunks:       # handles are released by the thread (context) that created them
+                        x.free()
+                    self.dev_chunks = []
+                    t.synchronize()
+                    from ttn_b200 import _lib
+                    _lib.load().ttn_shutdown()      # this thread's streams and allocation cache
+                    self.done.put("stopped")
+                    break
+                self.done.put(getattr(self, "_" + cmd[0])(t, *cmd[1:]))
+        except Exception as e:   # noqa: BLE001
+            self.error = e
+            self.done.put(e)
+
+    def _result_set(self, nb):
+        res = []
+        for k in range(D5):
+            rl, rr = min(self.rks[k], MAXB5), min(self.rks[k + 1], MAXB5)
+            buf = self.torch.empty(2 * 2 * rl * rr * nb, dtype=self.torch.float64).pin_memory()
+            self.keep.append(buf)
+            res.append(buf.numpy().view(np.complex128).reshape((2, rl, rr, nb), order="F"))
+        return res
+
+    def _device(self, t, nsteps, profile=False):
+        """nsteps passes over this worker's device-resident chunks; returns the end event (on this worker's stream) + counters"""
+        if profile:
+            t.set_option("reset_flops", 1)
+            t.profile(True)
+        t.reset_launch_count()
+        fb0 = t.get_option("gram_fallbacks")
+        last = None
+        for _ in range(nsteps):
+            for xd in self.dev_chunks:
+                last = t.apply_compress(self.Ad, xd, MAXB5)
+        ev = self.torch.cuda.Event(enable_timing=True)
+        ev.record(self.stream)
+        t.synchronize()
+        out = {"end": ev, "launches": t.launch_count(), "fallbacks": int(t.get_option("gram_fallbacks") - fb0),
+               "out_rks": last.ttv_rks if last is not None else None}
+        if profile:
+            out["fam"] = t.profile_read()
+            t.profile(False)
+            out["flops"] = {"gemm": t.get_option("gemm_flops"), "jacobi": t.get_option("heig_flops")}
+        return out
+
+    def _e2e(self, t, nsteps):
+        """software pipeline over this worker's chunks on pinned host memory: H2D of chunk i+1 and D2H of chunk i-1 run on the
+        copy stream while chunk i computes"""
+        hc = self.host_chunks
+        for _ in range(nsteps):
+            if not hc:
+                continue
+            nxt = t.DeviceTT.upload_batched(hc[0], (2,) * D5, self.rks, asynchronous=True)
+            for i, c in enumerate(hc):
+                xd = nxt
+                if i + 1 < len(hc):
+                    nxt = t.DeviceTT.upload_batched(hc[i + 1], (2,) * D5, self.rks, asynchronous=True)
+                y = t.apply_compress(self.Ad, xd, MAXB5)
+                y.download_into(self.res_bufs[c[0].shape[3]][i & 1], asynchronous=True)
+                xd.free(); y.free()
+            t.copy_synchronize()
+        t.synchronize()
+        return {"h2d": int(sum(a.nbytes for c in hc for a in c)),
+                "d2h": int(sum(sum(a.nbytes for a in self.res_bufs[c[0].shape[3]][0]) for c in hc))}
+
+
 def run_ours(args, rank, local_rank, world):
     import torch
     import ttn_b200 as t
@@ -243,11 +338,23 @@ def run_ours(args, rank, local_rank, world):
     rks, Rk = cfg5_ranks()
     first, nvec = t.shard_batch(TOTAL5, rank, world)
     chunk = min(args.chunk, nvec)
-    Ad = t.DeviceTTO.upload(make_mpo(t))
+    Ad = t.DeviceTTO.upload(make_mpo(t))        # read-only, shared by the worker threads
     host_chunks, keep = pinned_chunks(torch, nvec, chunk, rank)
-    dev_chunks = [t.DeviceTT.upload_batched(c, (2,) * D5, rks) for c in host_chunks]
     t.synchronize()
     stream = torch.cuda.ExternalStream(t.stream_handle())
+    nw = max(1, min(args.host_threads, len(host_chunks)))
+    workers = [ChunkWorker(i, nw, host_chunks, Ad, rks, torch, keep) for i in range(nw)]
+    for w in workers:
+        w.start()
+
+    def collect():
+        res = [w.done.get() for w in workers]
+        for r in res:
+            if isinstance(r, Exception):
+                raise r
+        return res
+
+    collect()
 
     def barrier():
         t.synchronize()
@@ -262,101 +369,94 @@ def run_ours(args, rank, local_rank, world):
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         return float(tm.item())
 
-    def step_device():
-        out = None
-        for xd in dev_chunks:
-            out = t.apply_compress(Ad, xd, MAXB5)
-        return out
-
-    def timed(nsteps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    def timed(nsteps, profile=False):
+        """all workers idle -> start event -> nsteps passes on every worker -> latest end event of the workers' streams"""
         barrier()
-        e0.record(stream)
-        out = None
-        for _ in range(nsteps):
-            out = step_device()
-        e1.record(stream)
+        g0 = torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for w in workers:
+            w.cmd.put(("device", nsteps, profile))
+        res = collect()
+        torch.cuda.synchronize()
+        ms = max(g0.elapsed_time(r["end"]) for r in res)
         barrier()
-        return e0.elapsed_time(e1), out
+        return ms, res
 
     # ---- device-resident timing -------------------------------------------------------------------------------
     timed(W)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    t.reset_launch_count()
-    fb0 = t.get_option("gram_fallbacks")
-    ms, last = timed(K)
-    launches = t.launch_count()
-    fallbacks = int(t.get_option("gram_fallbacks") - fb0)
+    ms, res = timed(K)
+    launches = sum(r["launches"] for r in res)
+    fallbacks = sum(r["fallbacks"] for r in res)
     clocks = sampler.stop() if rank == 0 else None
-    out_rks = last.ttv_rks
+    out_rks = res[0]["out_rks"]
     ms_per_step = allmax(ms) / K
     value = TOTAL5 / (ms_per_step * 1e-3)
 
     # ---- end to end through the host API: pinned host buffers, H2D + apply_compress + D2H per chunk ----------------
-    res_bufs = []
-    for c in host_chunks[:1]:
-        nb = c[0].shape[3]
-        res = []
-        for k in range(D5):
-            rl, rr = min(rks[k], MAXB5), min(rks[k + 1], MAXB5)
-            buf = torch.empty(2 * 2 * rl * rr * nb, dtype=torch.float64).pin_memory()
-            keep.append(buf)
-            res.append(buf.numpy().view(np.complex128).reshape((2, rl, rr, nb), order="F"))
-        res_bufs.append(res)
+    def e2e(nsteps):
+        barrier()
+        w0 = time.perf_counter()
+        for w in workers:
+            w.cmd.put(("e2e", nsteps))
+        r = collect()
+        return (time.perf_counter() - w0) / max(1, nsteps), r
 
-    def step_e2e():
-        for c in host_chunks:
-            xd = t.DeviceTT.upload_batched(c, (2,) * D5, rks)
-            y = t.apply_compress(Ad, xd, MAXB5)
-            nb = c[0].shape[3]
-            dst = res_bufs[0] if nb == res_bufs[0][0].shape[3] else [np.empty(a.shape[:3] + (nb,), dtype=a.dtype, order="F") for a in res_bufs[0]]
-            y.download_into(dst)
-            xd.free(); y.free()
-
-    for _ in range(min(W, 1)):
-        step_e2e()
+    e2e(min(W, 1))
     e2e_steps = max(1, min(K, args.e2e_steps))
-    barrier()
-    w0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_e2e()
-    t.synchronize()
-    e2e_s = allmax((time.perf_counter() - w0) / e2e_steps)
-    h2d = int(sum(a.nbytes for c in host_chunks for a in c))
-    d2h = int(sum(a.nbytes for a in res_bufs[0]) * (nvec / res_bufs[0][0].shape[3]))
+    e2e_s, er = e2e(e2e_steps)
+    e2e_s = allmax(e2e_s)
+    h2d, d2h = sum(r["h2d"] for r in er), sum(r["d2h"] for r in er)
     if dist is not None:
         tb = torch.tensor([float(h2d), float(d2h)], device="cuda", dtype=torch.float64)
         dist.all_reduce(tb, op=dist.ReduceOp.SUM)
         h2d, d2h = int(tb[0].item()), int(tb[1].item())
 
-    # ---- roofline pass: per-kernel-family CUDA events over one step -----------------------------------------------
-    t.synchronize()
-    t.profile(True)
-    ms_prof, _ = timed(1)
-    fam = t.profile_read()
-    t.profile(False)
+    # ---- roofline pass: per-kernel-family CUDA events over one step, with the FLOPs the kernels were asked to execute ------
+    ms_prof, pres = timed(1, profile=True)
+    fam_ms, fam_cnt, executed = {}, {}, {"gemm": 0.0, "jacobi": 0.0}
+    for r in pres:
+        for k, v in r["fam"].items():
+            fam_ms[k] = fam_ms.get(k, 0.0) + v[0]
+            fam_cnt[k] = fam_cnt.get(k, 0) + v[1]
+        for k in executed:
+            executed[k] += r["flops"][k]
     model = cfg5_flop_model()
     peak64 = json.load(open(FP64_PEAK_FILE)) if os.path.exists(FP64_PEAK_FILE) else {"fp64_tflops": 35.45, "c128_tflops": 36.8}
     peak = float(peak64.get("fp64_tflops", 35.45))
-    fam_ms = {k: v[0] for k, v in fam.items()}
-    fam_cnt = {k: v[1] for k, v in fam.items()}
     dom = max(fam_ms, key=fam_ms.get)
-    alg_per_vec = {"gemm": model["gemm"], "jacobi": model["svd"]}.get(dom, 0.0)
-    achieved = alg_per_vec * nvec / (fam_ms[dom] * 1e-3) / 1e12 if fam_ms[dom] > 0 else 0.0
+    names = {"gemm": "gemm_kernel<double2,...> (DMMA: Z = P x, Gram, projection GEMMs of the fused apply + rounding)",
+             "jacobi": "heig_* (Gram-path eigensolver: Householder tridiagonalisation, multisection, twisted vectors, back-transformation)"}
+    fams = {}
+    for k in ("gemm", "jacobi"):
+        tfk = executed[k] / (fam_ms[k] * 1e-3) / 1e12 if fam_ms.get(k, 0) > 0 else 0.0
+        fams[k] = {"kernel": names[k], "stream_ms_per_step": round(fam_ms.get(k, 0.0), 3), "launches_per_step": fam_cnt.get(k, 0),
+                   "executed_gflop_per_vector": executed[k] / nvec / 1e9, "achieved_tflops": tfk, "frac": tfk / peak}
     step_tf = model["total"] * TOTAL5 / (ms_per_step * 1e-3) / 1e12 / world
-    roofline = {"bound": "tensor", "kernel": {"gemm": "gemm_kernel<double2,...> (DMMA: Theta, Gram, projection GEMMs)",
-                                              "jacobi": "heig_* (Gram-path eigensolver: tridiagonalisation, multisection, back-transformation)"}.get(dom, dom),
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-                "traffic_note": "batched bond matrices stream through L2; see profiles/ncu_*_r02.txt for dram__bytes of the kernels",
+    exec_tf = (executed["gemm"] + executed["jacobi"]) * (TOTAL5 / nvec) / (ms_per_step * 1e-3) / 1e12 / world
+    roofline = {"bound": "tensor", "kernel": names.get(dom, dom), "achieved": fams.get(dom, {}).get("achieved_tflops", 0.0), "peak": peak,
+                "unit": "TFLOP/s", "frac": fams.get(dom, {}).get("frac", 0.0), "traffic": None,
+                "flop_accounting": "FLOPs the dominant kernel family was asked to execute in the step (GEMM: 8MNK per complex product; "
+                                   "eigensolver: LAPACK counts 4/3 n^3 + 2 n^2 nev, x4 complex), counted inside the library, / the summed "
+                                   "CUDA-event time of that family on its streams (with 2 host threads the families of different chunks "
+                                   "overlap, so the per-family times add up to more than the step)",
+                "traffic_note": "bond matrices stream through L2 / shared memory; dram__bytes of the kernels: profiles/ncu_*_r02.txt",
                 "peak_source": "measured cuBLAS FP64 GEMM 8192^3 burst on this pool's B200 (profiles/fp64_peak_r01.json; builder-"
                                "measured fallback: MEASURED_PEAKS.json carries no FP64 figure)",
-                "algorithmic_flops_per_launch": alg_per_vec * nvec / max(1, fam_cnt[dom]), "launches_per_step": fam_cnt[dom],
-                "ms_per_step_in_kernel": fam_ms[dom], "family_ms_per_step": {k: round(v, 3) for k, v in fam_ms.items()},
-                "whole_step": {"achieved": step_tf, "frac": step_tf / peak, "per_gpu": True,
-                               "model": "13.3 GFLOP per vector (SURVEY.md section 8(d)-5: Theta GEMMs + projections + R-SVD count 6mk^2+20k^3, complex = 4 x real)",
-                               "gflop_per_vector": model["total"] / 1e9}}
+                "families": fams, "family_stream_ms_per_step": {k: round(v, 3) for k, v in fam_ms.items()},
+                "profiled_ms_per_step": ms_prof,
+                "whole_step": {"survey_model": {"achieved": step_tf, "frac": step_tf / peak,
+                                                "gflop_per_vector": model["total"] / 1e9,
+                                                "note": "SURVEY.md section 8(d)-5 per-unit figure (Theta GEMMs + projections + R-SVD count 6mk^2+20k^3, "
+                                                        "complex = 4 x real) x vectors / step time, per GPU; above 1 because the Gram path and the "
+                                                        "fused apply execute fewer FLOPs than that model's algorithm"},
+                               "executed": {"achieved": exec_tf, "frac": exec_tf / peak,
+                                            "gflop_per_vector": (executed["gemm"] + executed["jacobi"]) / nvec / 1e9}}}
+    for w in workers:
+        w.cmd.put(("stop",))
+    collect()
 
     # ---- extras: the other components of BASELINE.json's metric (compact in the line, full detail on disk) ----------
     extras, compact = {}, {}
@@ -381,7 +481,7 @@ def run_ours(args, rank, local_rank, world):
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             import cfg3_bench
             extras["mals_cfg3"] = cfg3_bench.run(bits=20, rmax=128)
-            compact["mals_cfg3_s"] = extras["mals_cfg3"].get("seconds")
+            compact["mals_cfg3_s"] = extras["mals_cfg3"].get("value")
     if dist is not None:
         dist.barrier()
 
@@ -408,11 +508,13 @@ def run_ours(args, rank, local_rank, world):
         line = {"metric": "tt_rounding sweeps/s", "value": value, "unit": "sweeps/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "c128",
                 "data": "synthetic", "config": dict(cfg5_config(world, chunk), out_max_rank=int(max(out_rks)),
-                                                    gram_path_fallbacks_in_timed_region=fallbacks),
+                                                    gram_path_fallbacks_in_timed_region=fallbacks, host_threads_per_rank=nw),
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": TOTAL5 / e2e_s, "unit": "sweeps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-                        "api": "DeviceTT.upload_batched(pinned) -> ttn_b200.apply_compress(A, x, 64) -> download_into(pinned), per chunk"},
+                        "api": "per chunk: DeviceTT.upload_batched(pinned, asynchronous) -> ttn_b200.apply_compress(A, x, 64) -> "
+                               "download_into(pinned, asynchronous); copies on the copy streams overlap the neighbouring chunks' compute; "
+                               f"{nw} host thread(s) = library contexts per rank"},
                 "roofline": roofline, "cpu_baseline": cpu, "extras": compact}
         for dname in ("profiles", "gpurun_out"):
             try:
@@ -569,6 +671,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chunk", type=int, default=296, help="vectors per device batch (cfg5); 296 = two full waves of one matrix per SM")
+    ap.add_argument("--host-threads", type=int, default=2, help="library contexts (host threads) per rank: chunks in flight")
     ap.add_argument("--e2e-steps", type=int, default=5, help="upper bound on the end-to-end steps (each moves 2 x 10 GB over PCIe at N=1)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="skip the cfg2 / cfg4 matvec / DMRG sweep / cfg3 extras")

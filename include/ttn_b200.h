@@ -20,7 +20,10 @@
  *      MPO core A_k[i,j,a,b] of size (n_k, n_k, R_{k-1}, R_k):   ptr[i + n*(j + n*(a + R_{k-1}*b))]  src/tt_tools.jl:48-54
  *  - Host memory stays owned by the caller; the library copies in/out and owns all device memory behind the
  *    opaque handles, so whole sweeps run without host round trips of tensor data.
- *  - One calling thread per process; every call is blocking.  One process drives one GPU.
+ *  - One context per HOST THREAD: every thread that calls the library owns a compute stream, a copy stream, an allocation
+ *    cache and its own counters, and must call ttn_init itself.  Calls are blocking for their thread.  Handles are used and
+ *    released by the thread that created them (an uploaded operator may be READ by several threads).  Two threads working on
+ *    independent trains overlap on the GPU.  One process drives one GPU.
  *  - There is no CPU fallback: without a CUDA device ttn_init fails with TTN_ECUDA.
  */
 #ifndef TTN_B200_H
@@ -49,7 +52,7 @@ typedef struct ttn_ttv_s* ttn_ttv; /* device-resident TTvector  (src/tt_tools.jl
 typedef struct ttn_tto_s* ttn_tto; /* device-resident TToperator (src/tt_tools.jl:48-54) */
 
 /* ---- library lifetime ------------------------------------------------------------------------------ */
-int ttn_init(int device);                 /* selects the device, creates the stream and the memory pool */
+int ttn_init(int device);                 /* selects the device, creates the calling thread's stream and memory cache */
 int ttn_shutdown(void);
 const char* ttn_last_error(void);
 int ttn_version(void);
@@ -74,6 +77,17 @@ int ttn_profile_read(double* ms /* 8 */, long long* counts /* 8 */);
  * `batch` > 1 uploads `batch` TTs of identical dims/ranks; cores[k] then points to (n, r_l, r_r, batch). */
 int ttn_ttv_upload(int dtype, int d, const int64_t* dims, const int64_t* rks, const int64_t* ot,
                    const void* const* cores, int batch, ttn_ttv* out);
+/* Asynchronous variants for pipelines over batches of trains (cfg5): the copies run on the library's copy stream and overlap
+ * the compute stream.  Host buffers must be page-locked and stay valid until the copy has completed.  A handle returned by
+ * ttn_ttv_upload_async may be passed to ttn_apply / ttn_apply_compress / ttn_compress / ttn_ttv_download(_async) / ttn_ttv_free
+ * right away (they make the compute stream wait for the upload); before any other entry point call ttn_ttv_wait.  After
+ * ttn_ttv_download_async the host buffers are valid once ttn_copy_synchronize has returned; ttn_ttv_free may be called at once
+ * (the release is ordered after the copy). */
+int ttn_ttv_upload_async(int dtype, int d, const int64_t* dims, const int64_t* rks, const int64_t* ot,
+                         const void* const* cores, int batch, ttn_ttv* out);
+int ttn_ttv_wait(ttn_ttv x);
+int ttn_ttv_download_async(ttn_ttv x, void* const* cores);
+int ttn_copy_synchronize(void);
 int ttn_ttv_info(ttn_ttv x, int* dtype, int* d, int* batch);
 int ttn_ttv_ranks(ttn_ttv x, int64_t* rks /* d+1 */);
 int ttn_ttv_dims(ttn_ttv x, int64_t* dims /* d */);

@@ -44,9 +44,12 @@ class TdvpParams(C.Structure):
     ]
 
 
+import threading
+
 _lib = None
 _signatures = {}
 _inited_device = None
+_tls = threading.local()       # the library keeps one context (streams, allocation cache) per host thread
 
 
 def load():
@@ -66,6 +69,8 @@ def load():
         "ttn_reset_launch_count": [], "ttn_profile": [C.c_int],
         "ttn_profile_read": [C.POINTER(C.c_double), C.POINTER(C.c_longlong)],
         "ttn_ttv_upload": [C.c_int, C.c_int, i64p, i64p, i64p, vpp, C.c_int, vpp],
+        "ttn_ttv_upload_async": [C.c_int, C.c_int, i64p, i64p, i64p, vpp, C.c_int, vpp], "ttn_ttv_wait": [vp],
+        "ttn_ttv_download_async": [vp, vpp], "ttn_copy_synchronize": [],
         "ttn_ttv_info": [vp, ip, ip, ip], "ttn_ttv_ranks": [vp, i64p], "ttn_ttv_dims": [vp, i64p],
         "ttn_ttv_ot": [vp, i64p], "ttn_ttv_download": [vp, vpp], "ttn_ttv_copy": [vp, vpp],
         "ttn_ttv_complex": [vp, vpp], "ttn_ttv_free": [vp],
@@ -147,4 +152,8 @@ def lib(device: int | None = None):
             device = int(os.environ.get("LOCAL_RANK", "0"))
         check(l.ttn_init(int(device)))
         _inited_device = int(device)
+        _tls.inited = True
+    elif not getattr(_tls, "inited", False):
+        check(l.ttn_init(_inited_device))     # first call from this thread: its own context on the same device
+        _tls.inited = True
     return l

@@ -32,7 +32,7 @@ __all__ = [
     "euclidean_distance_normalized",
     "orthogonalize", "tt_compress_", "tt_bond_truncate_", "als_linsolve", "als_eigsolve", "als_gen_eigsolv", "mals_linsolve",
     "mals_eigsolve", "dmrg_linsolve", "dmrg_eigsolve", "tdvp", "tdvp2", "matvec2", "env_left", "env_right",
-    "shard_range", "shard_batch", "assemble_slices", "ShardedMatvec", "apply_compress", "svdtrunc", "heig_top", "set_option", "get_option", "qr_thin", "gemm_host", "launch_count", "reset_launch_count", "synchronize", "library_path", "profile", "profile_read", "stream_handle",
+    "shard_range", "shard_batch", "assemble_slices", "ShardedMatvec", "apply_compress", "svdtrunc", "heig_top", "set_option", "get_option", "copy_synchronize", "qr_thin", "gemm_host", "launch_count", "reset_launch_count", "synchronize", "library_path", "profile", "profile_read", "stream_handle",
     "KERNEL_FAMILIES",
 ]
 
@@ -66,6 +66,11 @@ def profile_read():
     ms, cnt = (C.c_double * 8)(), (C.c_longlong * 8)()
     check(_lib.lib().ttn_profile_read(ms, cnt))
     return {KERNEL_FAMILIES[i]: (float(ms[i]), int(cnt[i])) for i in range(8)}
+
+
+def copy_synchronize() -> None:
+    """waits for the asynchronous host <-> device copies (`upload_batched(..., asynchronous=True)`, `download_into(..., asynchronous=True)`)"""
+    check(_lib.lib().ttn_copy_synchronize())
 
 
 def set_option(key: str, value) -> None:
@@ -175,9 +180,10 @@ class DeviceTT:
         return cls(out)
 
     @classmethod
-    def upload_batched(cls, cores, dims, rks, ot=None):
+    def upload_batched(cls, cores, dims, rks, ot=None, asynchronous=False):
         """A batch of identically shaped trains given as ONE array per site, `cores[k]` of shape (n_k, r_k, r_{k+1}, batch),
-        Fortran-contiguous (e.g. views of pinned host memory): no host-side repacking, one H2D copy per site."""
+        Fortran-contiguous (e.g. views of pinned host memory): no host-side repacking, one H2D copy per site.
+        `asynchronous=True` (pinned memory only): the copies run on the library's copy stream and overlap the compute stream."""
         d = len(cores)
         dt = np.result_type(*[c.dtype for c in cores])
         code = _dtype_code(dt)
@@ -188,13 +194,14 @@ class DeviceTT:
                 raise AssertionError("Incompatible dimensions")
             ptrs[k] = c.ctypes.data
         out = C.c_void_p()
-        check(_lib.lib().ttn_ttv_upload(code, d, _i64(dims), _i64(rks), _i64(ot if ot is not None else [0] * d), ptrs, batch,
-                                        C.byref(out)))
+        fn = _lib.lib().ttn_ttv_upload_async if asynchronous else _lib.lib().ttn_ttv_upload
+        check(fn(code, d, _i64(dims), _i64(rks), _i64(ot if ot is not None else [0] * d), ptrs, batch, C.byref(out)))
         return cls(out)
 
-    def download_into(self, arrays):
+    def download_into(self, arrays, asynchronous=False):
         """device -> host into caller-provided Fortran-contiguous arrays (one per site, with the trailing batch axis when
-        batch > 1); the counterpart of `upload_batched` for pinned result buffers."""
+        batch > 1); the counterpart of `upload_batched` for pinned result buffers.  `asynchronous=True`: the copies run on the
+        copy stream, the arrays are valid after `copy_synchronize()`."""
         code, d, batch = self._info()
         dims, rks = self.ttv_dims, self.ttv_rks
         ptrs = (C.c_void_p * d)()
@@ -204,7 +211,7 @@ class DeviceTT:
             if tuple(a.shape) != shp or not a.flags["F_CONTIGUOUS"] or a.dtype != _np_dtype(code):
                 raise AssertionError("Incompatible dimensions")
             ptrs[k] = a.ctypes.data
-        check(_lib.lib().ttn_ttv_download(self._h, ptrs))
+        check((_lib.lib().ttn_ttv_download_async if asynchronous else _lib.lib().ttn_ttv_download)(self._h, ptrs))
         return arrays
 
     # -- metadata ---------------------------------------------------------------------------------------

@@ -39,6 +39,7 @@ int ttn_init(int device) {
   Context& c = ctx();
   if (!c.inited || c.device != device) {
     if (c.inited && c.stream) { devbuf_cache_trim(); cudaStreamSynchronize(c.stream); cudaStreamDestroy(c.stream); }
+    if (c.copy_stream) { cudaStreamSynchronize(c.copy_stream); cudaStreamDestroy(c.copy_stream); c.copy_stream = nullptr; }
     c.device = device;
     TTN_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     cudaDeviceProp prop;
@@ -65,6 +66,7 @@ int ttn_shutdown(void) {
     cudaStreamSynchronize(c.stream);
     cudaStreamDestroy(c.stream);
     c.stream = nullptr;
+    if (c.copy_stream) { cudaStreamSynchronize(c.copy_stream); cudaStreamDestroy(c.copy_stream); c.copy_stream = nullptr; }
     c.inited = false;
   }
   API_END
@@ -81,6 +83,7 @@ int ttn_set_option(const char* key, double value) {
   else if (k == "gram_jacobi_min") c.gram_jacobi_min = (int)value;
   else if (k == "use_cholqr") c.use_cholqr = value != 0.0;
   else if (k == "use_cluster_jacobi") c.use_cluster_jacobi = value != 0.0;
+  else if (k == "reset_flops") { c.flops_gemm = 0.0; c.flops_heig = 0.0; }
   else throw Error(TTN_EARG, "ttn_set_option: unknown key " + k);
   API_END
 }
@@ -94,6 +97,8 @@ int ttn_get_option(const char* key, double* value) {
   else if (k == "gram_jacobi_min") *value = c.gram_jacobi_min;
   else if (k == "use_cholqr") *value = c.use_cholqr;
   else if (k == "use_cluster_jacobi") *value = c.use_cluster_jacobi;
+  else if (k == "gemm_flops") *value = c.flops_gemm;
+  else if (k == "heig_flops") *value = c.flops_heig;
   else if (k == "gram_calls") *value = (double)c.gram_calls;
   else if (k == "gram_fallbacks") *value = (double)c.gram_fallbacks;
   else if (k == "gram_last_flags") *value = (double)c.gram_last_flags;
@@ -174,6 +179,91 @@ int ttn_ttv_upload(int dtype, int d, const int64_t* dims, const int64_t* rks, co
 
 #define TTV_FIELD(x, f) ((x)->dtype == TTN_F64 ? (x)->r.f : (x)->c.f)
 
+}  // extern "C"
+static cudaStream_t copy_stream() {
+  Context& c = ctx();
+  if (!c.copy_stream) TTN_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+  return c.copy_stream;
+}
+// the compute stream waits for a pending asynchronous upload of x (no host synchronisation)
+static void await_ready(ttn_ttv x) {
+  if (x && x->ready) {
+    TTN_CUDA(cudaStreamWaitEvent(ctx().stream, x->ready, 0));
+    cudaEventDestroy(x->ready);
+    x->ready = nullptr;
+  }
+}
+extern "C" {
+
+int ttn_ttv_upload_async(int dtype, int d, const int64_t* dims, const int64_t* rks, const int64_t* ot, const void* const* cores,
+                         int batch, ttn_ttv* out) {
+  API_BEGIN
+  need_init();
+  ttn_assert(d >= 1 && batch >= 1 && out, TTN_EARG, "upload: bad arguments");
+  ttn_assert(dtype == TTN_F64 || dtype == TTN_C128, TTN_EARG, "upload: bad dtype");
+  ttn_ttv h = new ttn_ttv_s();
+  h->dtype = dtype;
+  try {
+    auto setup = [&](auto& t) {
+      t.d = d; t.batch = batch;
+      t.dims.assign(dims, dims + d);
+      t.rks.assign(rks, rks + d + 1);
+      if (ot) t.ot.assign(ot, ot + d); else t.ot.assign(d, 0);
+      t.cores.clear();
+      t.cores.resize(d);
+      for (int k = 0; k < d; ++k) {
+        ttn_assert(dims[k] >= 1 && rks[k] >= 1 && rks[k + 1] >= 1, TTN_EDIM, "upload: dims and ranks must be positive");
+        t.alloc_core(k);
+      }
+      // the stream-ordered allocations become usable on the copy stream once the compute stream reaches this point
+      cudaEvent_t ev;
+      TTN_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      TTN_CUDA(cudaEventRecord(ev, ctx().stream));
+      TTN_CUDA(cudaStreamWaitEvent(copy_stream(), ev, 0));
+      cudaEventDestroy(ev);
+      for (int k = 0; k < d; ++k)
+        TTN_CUDA(cudaMemcpyAsync(t.cores[k].p, cores[k], t.cores[k].bytes, cudaMemcpyHostToDevice, copy_stream()));
+    };
+    if (dtype == TTN_F64) setup(h->r); else setup(h->c);
+    TTN_CUDA(cudaEventCreateWithFlags(&h->ready, cudaEventDisableTiming));
+    TTN_CUDA(cudaEventRecord(h->ready, copy_stream()));
+  } catch (...) { delete h; throw; }
+  *out = h;
+  API_END
+}
+int ttn_ttv_wait(ttn_ttv x) {
+  API_BEGIN
+  need_init();
+  await_ready(x);
+  API_END
+}
+int ttn_ttv_download_async(ttn_ttv x, void* const* cores) {
+  API_BEGIN
+  need_init();
+  ttn_assert(x != nullptr, TTN_EARG, "null handle");
+  await_ready(x);
+  cudaEvent_t ev;
+  TTN_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  TTN_CUDA(cudaEventRecord(ev, ctx().stream));            // everything queued on the compute stream so far has produced x
+  TTN_CUDA(cudaStreamWaitEvent(copy_stream(), ev, 0));
+  cudaEventDestroy(ev);
+  const int d = TTV_FIELD(x, d);
+  for (int k = 0; k < d; ++k) {
+    const DevBuf& b = x->dtype == TTN_F64 ? x->r.cores[k] : x->c.cores[k];
+    TTN_CUDA(cudaMemcpyAsync(cores[k], b.p, b.bytes, cudaMemcpyDeviceToHost, copy_stream()));
+  }
+  if (x->busy) cudaEventDestroy(x->busy);
+  TTN_CUDA(cudaEventCreateWithFlags(&x->busy, cudaEventDisableTiming));
+  TTN_CUDA(cudaEventRecord(x->busy, copy_stream()));
+  API_END
+}
+int ttn_copy_synchronize(void) {
+  API_BEGIN
+  need_init();
+  if (ctx().copy_stream) TTN_CUDA(cudaStreamSynchronize(ctx().copy_stream));
+  API_END
+}
+
 int ttn_ttv_info(ttn_ttv x, int* dtype, int* d, int* batch) {
   API_BEGIN
   ttn_assert(x != nullptr, TTN_EARG, "null handle");
@@ -207,6 +297,7 @@ int ttn_ttv_download(ttn_ttv x, void* const* cores) {
   API_BEGIN
   need_init();
   ttn_assert(x != nullptr, TTN_EARG, "null handle");
+  await_ready(x);
   const int d = TTV_FIELD(x, d);
   for (int k = 0; k < d; ++k) {
     const DevBuf& b = x->dtype == TTN_F64 ? x->r.cores[k] : x->c.cores[k];
@@ -300,6 +391,7 @@ int ttn_apply(ttn_tto A, ttn_ttv x, ttn_ttv* y) {
   need_init();
   ttn_assert(A && x && y, TTN_EARG, "null handle");
   same_dtype(A->dtype, x->dtype);
+  await_ready(x);
   ttn_ttv h = new ttn_ttv_s();
   h->dtype = x->dtype;
   try {
@@ -381,6 +473,7 @@ int ttn_compress(ttn_ttv x, int64_t max_bond, double truncerr, int sweeps, doubl
   API_BEGIN
   need_init();
   ttn_assert(x != nullptr, TTN_EARG, "null handle");
+  await_ready(x);
   if (x->dtype == TTN_F64) tt_compress(x->r, max_bond, truncerr, sweeps, sigma_out, sigma_stride);
   else tt_compress(x->c, max_bond, truncerr, sweeps, sigma_out, sigma_stride);
   API_END
@@ -391,6 +484,7 @@ int ttn_apply_compress(ttn_tto A, ttn_ttv x, int64_t max_bond, double truncerr, 
   need_init();
   ttn_assert(A && x && y, TTN_EARG, "null handle");
   same_dtype(A->dtype, x->dtype);
+  await_ready(x);
   ttn_ttv h = new ttn_ttv_s();
   h->dtype = x->dtype;
   try {

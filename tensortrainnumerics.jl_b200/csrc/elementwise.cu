@@ -11,15 +11,19 @@ namespace ttn {
 // ------------------------------------------------------------------------------------------------
 // context + stream-ordered allocator
 // ------------------------------------------------------------------------------------------------
+// One context per HOST THREAD: every thread that calls the library owns a compute stream, a copy stream, an allocation cache
+// and its own counters (ttn_init must be called in each of them).  Two threads working on independent trains therefore
+// overlap on the GPU: the latency-bound eigensolver kernels of one chunk run beside the DMMA GEMMs of another (bench.py).
+// Handles must be used and released by the thread that created them; read-only sharing of uploaded operators is fine.
 Context& ctx() {
-  static Context c;
+  static thread_local Context c;
   return c;
 }
 
 // Exact-size cache in front of the stream-ordered pool.  Sweeps allocate the same buffer sizes over and over (cores,
 // Theta, workspaces); for large blocks the driver pool can answer by mapping fresh physical memory when its free space is
 // fragmented (measured: up to 1 s of idle GPU per cfg5 chunk).  Everything runs on ONE stream, so a block released here
-// may be handed out again at once: its previous users are ahead in the same stream.
+// may be handed out again at once: its previous users are ahead in the same stream.  (One cache per host thread / stream.)
 namespace {
 struct BlockCache {
   std::vector<std::pair<size_t, void*>> free_blocks;   // small, linear search (a few dozen entries)
@@ -49,7 +53,7 @@ struct BlockCache {
   }
 };
 BlockCache& cache() {
-  static BlockCache c;
+  static thread_local BlockCache c;   // per host thread, like the stream it is ordered on
   return c;
 }
 }  // namespace

@@ -215,6 +215,7 @@ template <class T>
 void gemm(const GemmArgs& g) {
   if (g.M <= 0 || g.N <= 0 || g.batch1 <= 0 || g.batch2 <= 0) return;
   ProfScope prof_scope_(KF_GEMM);
+  ctx().flops_gemm += gemm_flops(g, is_cplx<T>::value);
   const int64_t ctas_big = (int64_t)((g.M + Tiles<T>::BIGM - 1) / Tiles<T>::BIGM) *
                            ((g.N + Tiles<T>::BIGN - 1) / Tiles<T>::BIGN) * g.batch1 * g.batch2;
   const bool big = g.M >= (Tiles<T>::BIGM * 3) / 4 && g.N >= (Tiles<T>::BIGN * 3) / 4 &&

@@ -12,6 +12,7 @@
 //   K3  back-transformation U = H_0 ... H_{n-2} Z, columns spread over lane groups, reflectors staged in shared memory.
 // LAPACK conventions (zhetd2 'L', zlarfg); tools/heig_proto.py is the NumPy twin the kernels were checked against.
 #include "ttn_internal.h"
+#include "tma.h"
 
 namespace ttn {
 namespace {
@@ -694,10 +695,11 @@ __global__ void __launch_bounds__(1024) heig_vec_kernel(const double* __restrict
 // ---------------------------------------------------------------------------------------------------------------------
 // K3: U = H_0 H_1 ... H_{n-2} Z.  8 lanes per column, rows l + 8 m in registers, reflectors in shared memory.
 // ---------------------------------------------------------------------------------------------------------------------
-template <class T, int NR>
+template <class T, int NR, int CPG>
 __global__ void __launch_bounds__(256) heig_back_kernel(const T* __restrict__ Vp, int64_t bV, const T* __restrict__ tau_in,
                                                         const double* __restrict__ Z, int n, int nev, T* __restrict__ U,
                                                         int64_t ldu, int64_t bU) {
+  // CPG columns per 8-lane group: every reflector element fetched from shared memory serves CPG dot products / updates
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* Vs = reinterpret_cast<T*>(smem_raw);
   const int nv = (n * (n - 1)) >> 1;
@@ -705,50 +707,76 @@ __global__ void __launch_bounds__(256) heig_back_kernel(const T* __restrict__ Vp
   const int tid = threadIdx.x;
   const int64_t mb = blockIdx.y;
   Vp += mb * bV; tau_in += mb * n; Z += mb * (int64_t)n * nev; U += mb * bU;
-  for (int idx = tid; idx < nv; idx += blockDim.x) Vs[idx] = Vp[idx];
-  for (int idx = tid; idx < n; idx += blockDim.x) taus[idx] = tau_in[idx];
-  __syncthreads();
-  const int cpb = blockDim.x >> 3;
-  const int l = tid & 7;
-  for (int col = blockIdx.x * cpb + (tid >> 3); col < ((nev + cpb - 1) / cpb) * cpb; col += gridDim.x * cpb) {
-    const bool act = col < nev;
-    T z[NR];
-#pragma unroll
-    for (int m = 0; m < NR; ++m) {
-      const int i = l + 8 * m;
-      z[m] = (act && i < n) ? t_from<T>(Z[(int64_t)col * n + i], 0.0) : t_zero<T>();
+  // stage the reflectors (one contiguous run of up to 130 KB): a single bulk copy of the copy engine (TMA, 1-D) completing
+  // on an mbarrier when the run is 16-byte aligned, a cooperative loop otherwise
+  __shared__ __align__(8) uint64_t bar;
+  const size_t vbytes = sizeof(T) * (size_t)nv;
+  const bool bulk = nv > 0 && (vbytes & 15) == 0 && ((reinterpret_cast<uintptr_t>(Vp) & 15) == 0);
+  if (bulk) {
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    __syncthreads();
+    if (tid == 0) {
+      mbar_arrive_expect_tx(&bar, (uint32_t)vbytes);
+      bulk_copy_g2s(Vs, Vp, (uint32_t)vbytes, &bar);
     }
+  } else {
+    for (int idx = tid; idx < nv; idx += blockDim.x) Vs[idx] = Vp[idx];
+  }
+  for (int idx = tid; idx < n; idx += blockDim.x) taus[idx] = tau_in[idx];
+  if (bulk) mbar_wait(&bar, 0);
+  __syncthreads();
+  const int cpb = (blockDim.x >> 3) * CPG;      // columns per CTA pass
+  const int l = tid & 7;
+  for (int c0 = blockIdx.x * cpb + (tid >> 3) * CPG; c0 < ((nev + cpb - 1) / cpb) * cpb; c0 += gridDim.x * cpb) {
+    T z[CPG][NR];
+#pragma unroll
+    for (int c = 0; c < CPG; ++c)
+#pragma unroll
+      for (int m = 0; m < NR; ++m) {
+        const int i = l + 8 * m;
+        z[c][m] = (c0 + c < nev && i < n) ? t_from<T>(Z[(int64_t)(c0 + c) * n + i], 0.0) : t_zero<T>();
+      }
     for (int k = n - 2; k >= 0; --k) {
       const T tk = taus[k];
       if (t_abs2(tk) == 0.0) continue;
       const T* vk = Vs + refl_off(k, n) - (k + 1);   // vk[i], i >= k+1
       T v[NR];
-      T a0 = t_zero<T>(), a1 = t_zero<T>();
 #pragma unroll
       for (int m = 0; m < NR; ++m) {
         const int i = l + 8 * m;
         v[m] = (i > k && i < n) ? vk[i] : t_zero<T>();
       }
+      T acc[CPG];
 #pragma unroll
-      for (int m = 0; m < NR; m += 2) {
-        t_fma(a0, t_conj(v[m]), z[m]);
-        if (m + 1 < NR) t_fma(a1, t_conj(v[m + 1]), z[m + 1]);
+      for (int c = 0; c < CPG; ++c) {
+        T a0 = t_zero<T>(), a1 = t_zero<T>();
+#pragma unroll
+        for (int m = 0; m < NR; m += 2) {
+          t_fma(a0, t_conj(v[m]), z[c][m]);
+          if (m + 1 < NR) t_fma(a1, t_conj(v[m + 1]), z[c][m + 1]);
+        }
+        acc[c] = t_add(a0, a1);
       }
-      T acc = t_add(a0, a1);
-      acc = t_add(acc, shfl_xor_t(acc, 4));
-      acc = t_add(acc, shfl_xor_t(acc, 2));
-      acc = t_add(acc, shfl_xor_t(acc, 1));
-      const T w = t_mul(tk, acc);
 #pragma unroll
-      for (int m = 0; m < NR; ++m) z[m] = t_sub(z[m], t_mul(w, v[m]));
-    }
-    if (act) {
+      for (int o = 4; o > 0; o >>= 1)
 #pragma unroll
-      for (int m = 0; m < NR; ++m) {
-        const int i = l + 8 * m;
-        if (i < n) U[(int64_t)col * ldu + i] = z[m];
+        for (int c = 0; c < CPG; ++c) acc[c] = t_add(acc[c], shfl_xor_t(acc[c], o));
+#pragma unroll
+      for (int c = 0; c < CPG; ++c) {
+        const T w = t_mul(tk, acc[c]);
+#pragma unroll
+        for (int m = 0; m < NR; ++m) z[c][m] = t_sub(z[c][m], t_mul(w, v[m]));
       }
     }
+#pragma unroll
+    for (int c = 0; c < CPG; ++c)
+      if (c0 + c < nev) {
+#pragma unroll
+        for (int m = 0; m < NR; ++m) {
+          const int i = l + 8 * m;
+          if (i < n) U[(int64_t)(c0 + c) * ldu + i] = z[c][m];
+        }
+      }
   }
 }
 
@@ -816,6 +844,8 @@ bool heig_top(const T* G, int n, int64_t ldg, int64_t bG, int nsplit, int64_t sG
   DevBuf V(sizeof(T) * (size_t)bV * batch), Z(sizeof(double) * (size_t)n * nev * batch);
   DevBuf lam_s(sizeof(double) * (size_t)nev * batch), tn(sizeof(double) * (size_t)batch);
   ProfScope prof_scope_(KF_JACOBI);
+  // LAPACK counts: tridiagonalisation 4/3 n^3, back-transformation of nev vectors 2 n^2 nev (complex: x4); the O(n^2) stages are not counted
+  ctx().flops_heig += (double)batch * (is_cplx<T>::value ? 4.0 : 1.0) * (4.0 / 3.0 * n * (double)n * n + 2.0 * n * (double)n * nev);
   bool done_tridiag = false;
   if (!is_cplx<T>::value && n <= 128 && n >= 2) {
     // Float64: whole matrix in registers (latency path of the single-train rounding chain; also the fastest batched form)
@@ -882,17 +912,20 @@ bool heig_top(const T* G, int n, int64_t ldg, int64_t bG, int nsplit, int64_t sG
     ctx().launches++;
   }
   {
+    // few matrices: one column per lane group and many CTAs (latency); batches: two columns per group, one CTA per matrix
     const bool few = batch * 8 <= ctx().sm_count;
-    int cpb = few ? 8 : 32;                        // columns per CTA
-    cpb = std::min(cpb, ((nev + 3) / 4) * 4);
-    const int nt = cpb * 8;
+    const int cpg = few ? 1 : 2;
+    int groups = few ? 8 : 32;                     // 8-lane groups per CTA
+    groups = std::min(groups, ((((nev + cpg - 1) / cpg) + 3) / 4) * 4);
+    const int nt = groups * 8;
+    const int cpb = groups * cpg;
     const int nv = n * (n - 1) / 2;
     const size_t smem = sizeof(T) * ((size_t)nv + (nv & 1) + n);
     dim3 grid(few ? (nev + cpb - 1) / cpb : 1, batch);
     const int nr = (n + 7) / 8;
-#define TTN_BACK(NR)                                                                                              \
+#define TTN_BACK2(NR, CPG)                                                                                        \
     {                                                                                                             \
-      auto kern = heig_back_kernel<T, NR>;                                                                        \
+      auto kern = heig_back_kernel<T, NR, CPG>;                                                                   \
       static int attr_dev = -1;                                                                                   \
       if (attr_dev != ctx().device) {                                                                             \
         TTN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));            \
@@ -900,10 +933,12 @@ bool heig_top(const T* G, int n, int64_t ldg, int64_t bG, int nsplit, int64_t sG
       }                                                                                                           \
       kern<<<grid, nt, smem, ctx().stream>>>(V.as<T>(), bV, tau.as<T>(), Z.as<double>(), n, nev, U, n, (int64_t)n * nev); \
     }
+#define TTN_BACK(NR) { if (cpg == 1) TTN_BACK2(NR, 1) else TTN_BACK2(NR, 2) }
     if (nr <= 4) TTN_BACK(4)
     else if (nr <= 8) TTN_BACK(8)
     else if (nr <= 16) TTN_BACK(16)
     else TTN_BACK(22)
+#undef TTN_BACK2
 #undef TTN_BACK
     TTN_CHECK_LAUNCH();
     ctx().launches++;

@@ -502,12 +502,14 @@ struct GramSweep {
     const int KA = Wl * n2, KB = n2 * Wr;
     DevBuf Z(sizeof(T) * (size_t)p * KA * rp * batch);
     for (int j = 0; j < n2; ++j) {
-      GemmArgs g;   // Z[row, a + Wl j, mu] = sum_nu P[row, a + Wl nu] x[j, nu, mu]
-      g.M = p; g.N = rp; g.K = r;
-      g.A = x.cores[k].p; g.sAm = 1; g.sAk = (int64_t)Wl * p; g.bA1 = p; g.bA2 = x.core_elems(k);
-      g.B = v.core(k + 1) + j; g.sBk = n2; g.sBn = (int64_t)n2 * r; g.bB1 = 0; g.bB2 = v.core_elems(k + 1);
-      g.C = Z.as<T>() + (int64_t)p * Wl * j; g.sCm = 1; g.sCn = (int64_t)p * KA; g.bC1 = p; g.bC2 = (int64_t)p * KA * rp;
-      g.batch1 = Wl; g.batch2 = batch;
+      // Z[(row,a), j, mu] = sum_nu P[(row,a), nu] x[j, nu, mu]: the fused left bond (a + Wl nu) of P makes (row, a) one
+      // contiguous M index of length p*Wl, so the Wl products of a site are ONE GEMM (larger tiles than Wl small ones)
+      GemmArgs g;
+      g.M = p * Wl; g.N = rp; g.K = r;
+      g.A = x.cores[k].p; g.sAm = 1; g.sAk = (int64_t)Wl * p; g.bA2 = x.core_elems(k);
+      g.B = v.core(k + 1) + j; g.sBk = n2; g.sBn = (int64_t)n2 * r; g.bB2 = v.core_elems(k + 1);
+      g.C = Z.as<T>() + (int64_t)p * Wl * j; g.sCm = 1; g.sCn = (int64_t)p * KA; g.bC2 = (int64_t)p * KA * rp;
+      g.batch1 = 1; g.batch2 = batch;
       gemm<T>(g);
     }
     const int nt = std::min(256, ((p + 31) / 32) * 32);

@@ -90,6 +90,13 @@ struct ttn_ttv_s {
   int dtype = 0;
   ttn::TT<double> r;
   ttn::TT<ttn::zc> c;
+  // asynchronous host <-> device traffic on the library's copy stream (ttn_ttv_upload_async / ttn_ttv_download_async):
+  cudaEvent_t ready = nullptr;   // recorded after the H2D copies: the compute stream must wait for it before the first use
+  cudaEvent_t busy = nullptr;    // recorded after the D2H copies: the cores must not be released before it
+  ~ttn_ttv_s() {
+    if (ready) { cudaStreamWaitEvent(ttn::ctx().stream, ready, 0); cudaEventDestroy(ready); }
+    if (busy) { cudaStreamWaitEvent(ttn::ctx().stream, busy, 0); cudaEventDestroy(busy); }
+  }
 };
 struct ttn_tto_s {
   int dtype = 0;

@@ -49,6 +49,7 @@ struct ProfRec { int fam; cudaEvent_t a, b; };
 struct Context {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // host <-> device copies that overlap the compute stream (created on first use)
   int sm_count = 148;
   long long launches = 0;  // kernels launched by this library since the last reset
   bool inited = false;
@@ -58,6 +59,7 @@ struct Context {
   bool use_cholqr = true;           // CholeskyQR2 fast path for tall-skinny QR (TTN_NO_CHOLQR=1 disables)
   bool jacobi_noise_floor = false;  // see JAC_FLOOR2 in jacobi.cu
   bool use_cluster_jacobi = true;   // single-matrix SVDs on an 8-SM cluster (TTN_NO_CLUSTER_JACOBI=1 disables; A/B timing)
+  double flops_gemm = 0.0, flops_heig = 0.0;   // real FLOPs the DMMA GEMMs / the Gram-path eigensolver were asked to execute (roofline accounting)
   long long gram_calls = 0, gram_fallbacks = 0;   // tt_compress! calls that took the Gram path / were redone by the Jacobi path
   int gram_last_flags = 0;
   bool gram_compress = true;        // Gram path of tt_compress! for truncerr == 0 (heig.cu); TTN_GRAM_COMPRESS=0 disables

@@ -183,3 +183,84 @@ def test_apply_compress_fused_equals_two_calls(cplx):
     y3 = t.apply_compress(A, xs[1], 64, truncerr=1e-3)
     ref3 = o.tt_compress(o.apply(A, xs[1]), 64, truncerr=1e-3)
     assert y3.ttv_rks == ref3.ttv_rks and o.rel_distance(y3, ref3) < 1e-10
+
+
+def test_async_upload_download_pipeline_matches_sync():
+    """`upload_batched(..., asynchronous=True)` / `download_into(..., asynchronous=True)` (copy stream overlapping the compute stream,
+    the e2e pipeline of bench.py): three chunks through apply_compress, results identical to the synchronous calls."""
+    import torch
+    import ttn_b200 as t
+    d, r, W, nb = 10, 8, 2, 6
+    rng = np.random.default_rng(33)
+    A = o.rand_tto((2,) * d, W, rng=rng, dtype=np.complex128)
+    Ad = t.DeviceTTO.upload(A)
+    rks = [min(2 ** k, 2 ** (d - k), r) for k in range(d + 1)]
+    keep, chunks = [], []
+    for c in range(3):
+        cores = []
+        for k in range(d):
+            buf = torch.empty(2 * 2 * rks[k] * rks[k + 1] * nb, dtype=torch.float64).pin_memory()
+            buf.normal_()
+            keep.append(buf)
+            cores.append(buf.numpy().view(np.complex128).reshape((2, rks[k], rks[k + 1], nb), order="F"))
+        chunks.append(cores)
+    ref = []
+    for cores in chunks:
+        y = t.apply_compress(Ad, t.DeviceTT.upload_batched(cores, (2,) * d, rks), 4)
+        ref.append([np.array(a) for a in y.download_into([np.empty((2, min(rks[k], 4), min(rks[k + 1], 4), nb), dtype=np.complex128, order="F")
+                                                          for k in range(d)])])
+    outs = []
+    nxt = t.DeviceTT.upload_batched(chunks[0], (2,) * d, rks, asynchronous=True)
+    for i, cores in enumerate(chunks):
+        xd = nxt
+        if i + 1 < len(chunks):
+            nxt = t.DeviceTT.upload_batched(chunks[i + 1], (2,) * d, rks, asynchronous=True)
+        y = t.apply_compress(Ad, xd, 4)
+        dst = []
+        for k in range(d):
+            buf = torch.empty(2 * 2 * min(rks[k], 4) * min(rks[k + 1], 4) * nb, dtype=torch.float64).pin_memory()
+            keep.append(buf)
+            dst.append(buf.numpy().view(np.complex128).reshape((2, min(rks[k], 4), min(rks[k + 1], 4), nb), order="F"))
+        y.download_into(dst, asynchronous=True)
+        xd.free(); y.free()
+        outs.append(dst)
+    t.copy_synchronize()
+    for a, b in zip(outs, ref):
+        for u, v in zip(a, b):
+            assert np.array_equal(u, v)
+
+
+def test_two_host_threads_two_contexts_match_serial():
+    """One library context per host thread (include/ttn_b200.h): two threads compress different batches concurrently (their
+    kernels overlap on the GPU); every result equals the single-threaded one bit for bit."""
+    import threading
+    import ttn_b200 as t
+    d, r, W = 12, 16, 3
+    rng = np.random.default_rng(77)
+    A = o.rand_tto((2,) * d, W, rng=rng, dtype=np.complex128)
+    Ad = t.DeviceTTO.upload(A)
+    batches = [[o.rand_tt((2,) * d, r, rng=rng, dtype=np.complex128, normalise=True) for _ in range(4)] for _ in range(6)]
+    serial = [[y.ttv_vec for y in t.apply_compress(Ad, t.DeviceTT.upload(b), 8).download()] for b in batches]
+    t.synchronize()
+    out, errs = [None] * len(batches), []
+
+    def work(idx):
+        try:
+            for k in range(idx, len(batches), 2):
+                for _ in range(3):
+                    y = t.apply_compress(Ad, t.DeviceTT.upload(batches[k]), 8)
+                out[k] = [v.ttv_vec for v in y.download()]
+            t.synchronize()
+        except Exception as e:   # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    assert not errs, errs
+    for a, b in zip(out, serial):
+        for va, vb in zip(a, b):
+            for ca, cb in zip(va, vb):
+                assert np.array_equal(ca, cb)
