@@ -9,4 +9,4 @@ from .krylov_tt import krylov_linsolve  # noqa: F401,E402
 from .steppers import (euler_method, implicit_euler_method, crank_nicholson_method, rk4_method,  # noqa: F401,E402
                        id_tto, tto_add, tto_scale)
 from .sites import (hadamard, ttv_to_diag_tto, hadamard_ttm, swap_adjacent_sites_, bubble_sort_swaps,  # noqa: F401,E402
-                    reorder, to_qtt, QTTvector)
+                    reorder, to_qtt, QTTvector, dmrg_cross_superblock_split)

@@ -52,6 +52,7 @@ int ttn_init(int device) {
     c.use_cluster_jacobi = getenv("TTN_NO_CLUSTER_JACOBI") == nullptr;
     c.use_cholqr = getenv("TTN_NO_CHOLQR") == nullptr;
     c.gram_compress = !(getenv("TTN_GRAM_COMPRESS") && atoi(getenv("TTN_GRAM_COMPRESS")) == 0);
+    c.gemm_bulk = !(getenv("TTN_GEMM_BULK") && atoi(getenv("TTN_GEMM_BULK")) == 0);
     if (const char* e = getenv("TTN_GRAM_JACOBI")) c.gram_jacobi_min = (atoi(e) != 0) ? 128 : (1 << 30);
     c.inited = true;
   }
@@ -80,6 +81,7 @@ int ttn_set_option(const char* key, double value) {
   const std::string k(key);
   Context& c = ctx();
   if (k == "gram_compress") c.gram_compress = value != 0.0;
+  else if (k == "gemm_bulk") c.gemm_bulk = value != 0.0;
   else if (k == "gram_jacobi_min") c.gram_jacobi_min = (int)value;
   else if (k == "use_cholqr") c.use_cholqr = value != 0.0;
   else if (k == "use_cluster_jacobi") c.use_cluster_jacobi = value != 0.0;
@@ -94,6 +96,7 @@ int ttn_get_option(const char* key, double* value) {
   const std::string k(key);
   const Context& c = ctx();
   if (k == "gram_compress") *value = c.gram_compress;
+  else if (k == "gemm_bulk") *value = c.gemm_bulk;
   else if (k == "gram_jacobi_min") *value = c.gram_jacobi_min;
   else if (k == "use_cholqr") *value = c.use_cholqr;
   else if (k == "use_cluster_jacobi") *value = c.use_cluster_jacobi;

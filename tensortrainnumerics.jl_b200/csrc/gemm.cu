@@ -15,6 +15,7 @@
 // mma.sync is the FP64 tensor path on this chip (larger f64 shapes decompose to 8x8x4 in SASS).
 #include "ttn_internal.h"
 #include "dmma.h"
+#include "tma.h"
 
 namespace ttn {
 
@@ -155,6 +156,165 @@ __global__ void __launch_bounds__(NT) gemm_kernel(const GemmArgs g) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// TMA-staged variant of the big tile (north star: "DMMA tiles staged through TMA and shared memory").  Operands whose tile
+// rows are contiguous in global memory (A: m fastest; B: n fastest or k fastest) are moved by the copy engine: warp 0 issues
+// one bulk asynchronous copy per tile row (cp.async.bulk, SASS UBLKCP) into the same padded shared-memory rows the DMMA
+// fragment loads expect, all copies of a k-slab complete on that stage's mbarrier (expect_tx = bytes of the slab), and the
+// other seven warps never touch an address computation for them.  B with k fastest has tile rows of only 128 bytes: issuing
+// 128 bulk copies per slab measured 2x SLOWER than LDGSTS (12.5 vs 24.9 TFLOP/s on the cfg4 matvec), so that operand keeps the
+// per-element LDGSTS staging of gemm_kernel while A still comes through the copy engine.
+// Requirements (checked by the host dispatcher): unit stride along the tile rows, full tiles, 16-byte aligned rows.
+// ---------------------------------------------------------------------------------------------------------------------
+template <class T, int BM, int BN, int WM, int WN, bool BMAJ>
+__global__ void __launch_bounds__(NT) gemm_bulk_kernel(const GemmArgs g) {
+  constexpr int PAD = Pad<T>::v;
+  constexpr int PA = BM + PAD, PB = BN + PAD;
+  constexpr int EB = BN * BK / NT;
+  constexpr int MT = WM / 8, NTL = WN / 8;
+  constexpr int WARPS_M = BM / WM;
+  constexpr int STAGE = BK * (PA + PB);
+  // bytes the copy engine delivers per k-slab: the A rows, and the B rows when B is n-fastest (k-fastest B has 128-byte tile
+  // rows — measured 2x slower as 128 bulk copies per slab — and is staged by LDGSTS like in gemm_kernel)
+  constexpr uint32_t STAGE_BYTES = (uint32_t)(sizeof(T) * (BM * BK + (BMAJ ? BN * BK : 0)));
+  static_assert((BM / WM) * (BN / WN) == NT / 32, "warp layout must cover the CTA tile");
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* Sm = reinterpret_cast<T*>(smem_raw);
+  __shared__ __align__(8) uint64_t full[NSTAGE];
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g8 = lane >> 2, t4 = lane & 3;
+  const int wm0 = (warp % WARPS_M) * WM, wn0 = (warp / WARPS_M) * WN;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int b = blockIdx.z, b1 = b % g.batch1, b2 = b / g.batch1;
+  const T* __restrict__ A = reinterpret_cast<const T*>(g.A) + b1 * g.bA1 + b2 * g.bA2;
+  const T* __restrict__ B = reinterpret_cast<const T*>(g.B) + b1 * g.bB1 + b2 * g.bB2;
+  T* __restrict__ C = reinterpret_cast<T*>(g.C) + b1 * g.bC1 + b2 * g.bC2;
+
+  Acc<T> acc[MT][NTL];
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < NTL; ++j) acc[i][j].zero();
+  const int nkt = g.K / BK;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  // k-fastest B: per-thread element coordinates of the LDGSTS staging (as in gemm_kernel, !BMAJ)
+  int bn[EB], bk[EB];
+  int64_t boff[EB];
+#pragma unroll
+  for (int r = 0; r < EB; ++r) {
+    const int idx = tid + r * NT;
+    bn[r] = idx / BK;
+    bk[r] = idx % BK;
+    boff[r] = (int64_t)bk[r] * g.sBk + (int64_t)(n0 + bn[r]) * g.sBn;
+  }
+  auto issue = [&](int kt) {
+    if (kt < nkt) {
+      const int s = kt % NSTAGE;
+      T* as = Sm + (size_t)s * STAGE;
+      T* bs = as + BK * PA;
+      const int k0 = kt * BK;
+      if (warp == 0) {
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy reads of the slot before the async writes
+        if (lane == 0) mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+        __syncwarp();
+        for (int r = lane; r < BK; r += 32)
+          bulk_copy_g2s(as + r * PA, A + m0 + (int64_t)(k0 + r) * g.sAk, (uint32_t)(sizeof(T) * BM), &full[s]);
+        if (BMAJ)
+          for (int r = lane; r < BK; r += 32)
+            bulk_copy_g2s(bs + r * PB, B + (int64_t)(k0 + r) * g.sBk + n0, (uint32_t)(sizeof(T) * BN), &full[s]);
+      }
+      if (!BMAJ) {
+#pragma unroll
+        for (int r = 0; r < EB; ++r) cp_async_elem<T>(bs + bk[r] * PB + bn[r], B + boff[r] + (int64_t)k0 * g.sBk, true);
+      }
+    }
+    if (!BMAJ) cp_async_commit();   // one group per slab (empty past the end): wait_group counts stay uniform
+  };
+#pragma unroll
+  for (int s = 0; s < NSTAGE - 1; ++s) issue(s);
+
+  for (int kt = 0; kt < nkt; ++kt) {
+    if (!BMAJ) cp_async_wait<NSTAGE - 2>();                         // this thread's LDGSTS of slab kt
+    mbar_wait(&full[kt % NSTAGE], (uint32_t)((kt / NSTAGE) & 1));   // the copy engine's rows of slab kt
+    __syncthreads();                                                // slab kt-1 is no longer being read by anyone
+    issue(kt + NSTAGE - 1);
+    const T* as = Sm + (size_t)(kt % NSTAGE) * STAGE;
+    const T* bs = as + BK * PA;
+#pragma unroll
+    for (int kk = 0; kk < BK; kk += 4) {
+      T af[MT], bf[NTL];
+#pragma unroll
+      for (int i = 0; i < MT; ++i) af[i] = as[(kk + t4) * PA + wm0 + i * 8 + g8];
+#pragma unroll
+      for (int j = 0; j < NTL; ++j)
+        bf[j] = bs[(kk + t4) * PB + wn0 + j * 8 + g8];
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NTL; ++j) acc[i][j].mma(af[i], bf[j]);
+    }
+  }
+
+  if (!BMAJ) cp_async_wait<0>();
+  const bool has_beta = (g.beta != 0.0);
+#pragma unroll
+  for (int i = 0; i < MT; ++i) {
+    const int row = m0 + wm0 + i * 8 + g8;
+#pragma unroll
+    for (int j = 0; j < NTL; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int col = n0 + wn0 + j * 8 + 2 * t4 + e;
+        T* p = C + (int64_t)row * g.sCm + (int64_t)col * g.sCn;
+        T v = t_scale(acc[i][j].get(e), g.alpha);
+        if (has_beta) v = t_add(v, t_scale(*p, g.beta));
+        *p = v;
+      }
+    }
+  }
+}
+
+template <class T, int BM, int BN, int WM, int WN, bool BMAJ>
+void launch_bulk(const GemmArgs& g) {
+  constexpr int PAD = Pad<T>::v;
+  const size_t smem = sizeof(T) * NSTAGE * BK * ((BM + PAD) + (BN + PAD));
+  auto kern = gemm_bulk_kernel<T, BM, BN, WM, WN, BMAJ>;
+  static int attr_dev = -1;
+  if (attr_dev != ctx().device) {
+    TTN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_dev = ctx().device;
+  }
+  dim3 grid(g.M / BM, g.N / BN, (unsigned)(g.batch1 * g.batch2));
+  kern<<<grid, NT, smem, ctx().stream>>>(g);
+  TTN_CHECK_LAUNCH();
+  ctx().launches++;
+}
+
+// true when the TMA-staged big-tile kernel can serve g (and then launches it)
+template <class T, int BM, int BN, int WM, int WN>
+bool try_bulk(const GemmArgs& g) {
+  if (!ctx().gemm_bulk || g.npeer != 0 || g.conjA || g.conjB) return false;
+  if (g.M % BM || g.N % BN || g.K % BK || g.K < BK) return false;
+  if ((int64_t)g.batch1 * g.batch2 > 65535 || g.N / BN > 65535) return false;
+  const int64_t ev = 16 / (int64_t)sizeof(T);                 // elements per 16 bytes
+  auto al = [&](int64_t v) { return v % ev == 0; };
+  if (g.sAm != 1 || !al(g.sAk) || !al(g.bA1) || !al(g.bA2) || (reinterpret_cast<uintptr_t>(g.A) & 15)) return false;
+  if (!al(g.bB1) || !al(g.bB2) || (reinterpret_cast<uintptr_t>(g.B) & 15)) return false;
+  if (g.sBn == 1 && al(g.sBk)) { launch_bulk<T, BM, BN, WM, WN, true>(g); return true; }
+  if (g.sBk == 1 && al(g.sBn)) { launch_bulk<T, BM, BN, WM, WN, false>(g); return true; }
+  return false;
+}
+
 template <class T, int BM, int BN, int WM, int WN, bool AMAJ, bool BMAJ>
 void launch_cfg(const GemmArgs& g) {
   constexpr int PAD = Pad<T>::v;
@@ -220,8 +380,12 @@ void gemm(const GemmArgs& g) {
                            ((g.N + Tiles<T>::BIGN - 1) / Tiles<T>::BIGN) * g.batch1 * g.batch2;
   const bool big = g.M >= (Tiles<T>::BIGM * 3) / 4 && g.N >= (Tiles<T>::BIGN * 3) / 4 &&
                    ctas_big >= (int64_t)(ctx().sm_count * 3) / 4;
-  if (big) Tiles<T>::big(g);
-  else Tiles<T>::small(g);
+  if (big) {
+    if (!is_cplx<T>::value && try_bulk<double, 128, 128, 64, 32>(g)) return;
+    Tiles<T>::big(g);
+  } else {
+    Tiles<T>::small(g);
+  }
 }
 
 template void gemm<double>(const GemmArgs&);

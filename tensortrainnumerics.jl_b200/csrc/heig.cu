@@ -740,20 +740,23 @@ __global__ void __launch_bounds__(256) heig_back_kernel(const T* __restrict__ Vp
       const T tk = taus[k];
       if (t_abs2(tk) == 0.0) continue;
       const T* vk = Vs + refl_off(k, n) - (k + 1);   // vk[i], i >= k+1
+      // rows <= k are untouched by reflector k: whole register rows (8 m + 7 <= k, uniform over the lanes) are skipped
       T v[NR];
 #pragma unroll
       for (int m = 0; m < NR; ++m) {
         const int i = l + 8 * m;
-        v[m] = (i > k && i < n) ? vk[i] : t_zero<T>();
+        v[m] = (8 * m + 7 > k && i > k && i < n) ? vk[i] : t_zero<T>();
       }
       T acc[CPG];
 #pragma unroll
       for (int c = 0; c < CPG; ++c) {
         T a0 = t_zero<T>(), a1 = t_zero<T>();
 #pragma unroll
-        for (int m = 0; m < NR; m += 2) {
-          t_fma(a0, t_conj(v[m]), z[c][m]);
-          if (m + 1 < NR) t_fma(a1, t_conj(v[m + 1]), z[c][m + 1]);
+        for (int m = 0; m < NR; ++m) {
+          if (8 * m + 7 > k) {
+            if (m & 1) t_fma(a1, t_conj(v[m]), z[c][m]);
+            else t_fma(a0, t_conj(v[m]), z[c][m]);
+          }
         }
         acc[c] = t_add(a0, a1);
       }
@@ -765,7 +768,8 @@ __global__ void __launch_bounds__(256) heig_back_kernel(const T* __restrict__ Vp
       for (int c = 0; c < CPG; ++c) {
         const T w = t_mul(tk, acc[c]);
 #pragma unroll
-        for (int m = 0; m < NR; ++m) z[c][m] = t_sub(z[c][m], t_mul(w, v[m]));
+        for (int m = 0; m < NR; ++m)
+          if (8 * m + 7 > k) z[c][m] = t_sub(z[c][m], t_mul(w, v[m]));
       }
     }
 #pragma unroll
@@ -914,7 +918,7 @@ bool heig_top(const T* G, int n, int64_t ldg, int64_t bG, int nsplit, int64_t sG
   {
     // few matrices: one column per lane group and many CTAs (latency); batches: two columns per group, one CTA per matrix
     const bool few = batch * 8 <= ctx().sm_count;
-    const int cpg = few ? 1 : 2;
+    const int cpg = 1;   // two columns per group (CPG = 2) measured no faster: the kernel is FP64-issue bound, not load bound
     int groups = few ? 8 : 32;                     // 8-lane groups per CTA
     groups = std::min(groups, ((((nev + cpg - 1) / cpg) + 3) / 4) * 4);
     const int nt = groups * 8;

@@ -62,6 +62,7 @@ struct Context {
   double flops_gemm = 0.0, flops_heig = 0.0;   // real FLOPs the DMMA GEMMs / the Gram-path eigensolver were asked to execute (roofline accounting)
   long long gram_calls = 0, gram_fallbacks = 0;   // tt_compress! calls that took the Gram path / were redone by the Jacobi path
   int gram_last_flags = 0;
+  bool gemm_bulk = true;            // TMA-staged (cp.async.bulk + mbarrier) big-tile GEMM when the operands allow it; TTN_GEMM_BULK=0 disables
   bool gram_compress = true;        // Gram path of tt_compress! for truncerr == 0 (heig.cu); TTN_GRAM_COMPRESS=0 disables
   int gram_jacobi_min = 640;        // Gram-block Jacobi (DMMA, two streams) for matrices with min(m, n) >= this (measured crossover);
                                     // TTN_GRAM_JACOBI=1: from 128 columns up, TTN_GRAM_JACOBI=0: never

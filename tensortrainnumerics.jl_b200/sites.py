@@ -156,3 +156,25 @@ def to_qtt(tt, split_dims, threshold: float = 0.0):
             site += 1
         site += 1
     return out.download() if host else out
+
+
+def dmrg_cross_superblock_split(superblock, max_bond: int, truncerr: float = 0.0, direction: str = "right"):
+    """The truncated superblock split of the DMRG-cross sweeps, tt_cross_interpolation.jl:609-622 (L→R) and :636-647 (R→L):
+    `U, S, Vt = _svdtrunc(reshape(superblock, r_l*s1, s2*r_g); max_bond = rmax, truncerr = tol)` on the device
+    (`ttn_svdtrunc_host`, the tail-norm rule of :149-166), followed by the two core forms the reference writes at the ends of a
+    sweep.  `superblock` has shape (r_l, s1, s2, r_g).  Returns (core_k, core_k1, s, U, Vt): for direction "right"
+    core_k = U as (s1, r_l, r), core_k1 = S·Vt as (s2, r, r_g) (lines 618-620); for "left" core_k = U·S, core_k1 = Vt
+    (lines 644-646).  The index selection (`maxvol!`) of the interior bonds stays with the caller: TT-cross sampling is host
+    work and out of scope (SURVEY.md §8, rows marked out of scope)."""
+    sb = np.asarray(superblock)
+    r_l, s1, s2, r_g = sb.shape
+    A = np.asfortranarray(sb.reshape(r_l * s1, s2 * r_g, order="F"))
+    U, s, Vt = _a.svdtrunc(A, max_bond=max_bond, truncerr=truncerr)
+    r = len(s)
+    if direction == "right":
+        core_k = np.transpose(U.reshape(r_l, s1, r, order="F"), (1, 0, 2))
+        core_k1 = np.transpose((s[:, None] * Vt).reshape(r, s2, r_g, order="F"), (1, 0, 2))
+    else:
+        core_k = np.transpose((U * s[None, :]).reshape(r_l, s1, r, order="F"), (1, 0, 2))
+        core_k1 = np.transpose(Vt.reshape(r, s2, r_g, order="F"), (1, 0, 2))
+    return np.asfortranarray(core_k), np.asfortranarray(core_k1), s, U, Vt

@@ -297,3 +297,28 @@ def test_qr_tall_single_matrix_smem_panels(shape, cplx):
     assert np.abs(np.tril(R, -1)).max() == 0.0
     assert relerr(Q @ R, A) < 1e-13
     assert np.abs(Q.conj().T @ Q - np.eye(k)).max() < 1e-12
+
+
+@pytest.mark.parametrize("transB", [False, True])
+@pytest.mark.parametrize("shape", [(1536, 1280, 16), (1536, 1280, 96), (2048, 1152, 1040), (1280, 1536, 48)])
+def test_gemm_tma_staged_big_tile(shape, transB):
+    """The TMA-staged big-tile kernel (cp.async.bulk + mbarrier, csrc/gemm.cu::gemm_bulk_kernel) is taken for Float64 full-tile
+    problems with unit-stride tile rows (both B layouts: k-fastest and n-fastest); same result as the LDGSTS kernel and NumPy,
+    with alpha / beta."""
+    import ttn_b200 as t
+    M, N, K = shape
+    rng = np.random.default_rng(M + N + K + transB)
+    A = rnd(rng, (M, K), False)
+    B = rnd(rng, (N, K) if transB else (K, N), False)
+    C0 = rnd(rng, (M, N), False)
+    ref = 0.75 * (A @ (B.T if transB else B)) - 0.5 * C0
+    assert t.get_option("gemm_bulk") == 1.0
+    got = t.gemm_host(A, B, transB=transB, alpha=0.75, beta=-0.5, C0=C0)
+    assert relerr(got, ref) < 1e-13
+    t.set_option("gemm_bulk", 0)
+    try:
+        plain = t.gemm_host(A, B, transB=transB, alpha=0.75, beta=-0.5, C0=C0)
+    finally:
+        t.set_option("gemm_bulk", 1)
+    assert relerr(plain, ref) < 1e-13
+    assert relerr(got, plain) < 1e-14

@@ -174,3 +174,36 @@ def test_qttvector_wrapper_reorder_and_compress():
     assert out is qi and qi.ttv_vec is vec_list and max(qi.ttv_rks) <= 3       # same object, same lists mutated
     with pytest.raises(AssertionError):
         t.QTTvector(x, 2, 3, "zigzag")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cplx", [False, True])
+def test_dmrg_cross_superblock_split_vs_oracle(cplx):
+    """SURVEY.md §8(f)-4, last item: the truncated superblock split of `tt_cross` with the DMRG strategy
+    (tt_cross_interpolation.jl:609-622, 636-647) — `_svdtrunc` of the (r_l s1) x (s2 r_g) superblock with the tail-norm rule
+    and the rmax cap, then the two end-of-sweep core forms.  Against the oracle's `svdtrunc` (gesdd): same rank, singular
+    values to 1e-10, and the two cores multiply back to the rank-r truncation of the superblock (gauge-free check)."""
+    import ttn_b200 as t
+    rng = np.random.default_rng(44 + cplx)
+    r_l, s1, s2, r_g = 12, 4, 3, 15
+    # a superblock sampled from a function of numerical rank ~9 plus a tail decaying below the tolerance
+    m, n = r_l * s1, s2 * r_g
+    U0, _ = np.linalg.qr(rng.standard_normal((m, m)) + (1j * rng.standard_normal((m, m)) if cplx else 0))
+    V0, _ = np.linalg.qr(rng.standard_normal((n, n)) + (1j * rng.standard_normal((n, n)) if cplx else 0))
+    sv = np.r_[np.logspace(0, -3, 9), np.logspace(-7, -12, min(m, n) - 9)]
+    A = (U0[:, :min(m, n)] * sv) @ V0[:, :min(m, n)].conj().T
+    sb = A.reshape(r_l, s1, s2, r_g, order="F")
+    for max_bond, tol in ((20, 1e-6), (6, 0.0), (64, 1e-10)):
+        Ur, Sr, Vtr = o.svdtrunc(A, max_bond=max_bond, truncerr=tol)
+        sr = np.diag(Sr) if np.ndim(Sr) == 2 else np.asarray(Sr)
+        for direction in ("right", "left"):
+            ck, ck1, s, U, Vt = t.dmrg_cross_superblock_split(sb, max_bond, tol, direction=direction)
+            r = len(s)
+            assert r == len(sr) and np.abs(s - sr).max() < 1e-10 * sr[0]
+            assert ck.shape == (s1, r_l, r) and ck1.shape == (s2, r, r_g)
+            left = np.transpose(ck, (1, 0, 2)).reshape(m, r, order="F")
+            right = np.transpose(ck1, (1, 0, 2)).reshape(r, n, order="F")
+            ref = (Ur * sr) @ Vtr
+            assert np.linalg.norm(left @ right - ref) < 1e-10 * np.linalg.norm(ref)
+            if direction == "right":
+                assert np.linalg.norm(left.conj().T @ left - np.eye(r)) < 1e-10       # U is the new left-orthogonal core
