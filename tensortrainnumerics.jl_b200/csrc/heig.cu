@@ -212,144 +212,197 @@ __global__ void __launch_bounds__(512) heig_tridiag_kernel(const T* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// K1 (Float64, latency path): the same tridiagonalisation with the whole symmetric matrix in REGISTERS — 4 lanes per row,
-// lane lq holds A(i, lq + 4 m), m < NJ.  A step touches every trailing element once in the matrix-vector product (one
-// broadcast shared-memory load + one DFMA) and once in the rank-2 update (one 16-byte load + two DFMAs): no matrix traffic
-// through shared memory, no address arithmetic, perfectly balanced rows.  Rows k+1 and k+2 are published to shared memory
-// after every update: by symmetry they are the next pivot column x and the next y1 = A(:, k+2).
+// K1 (Float64, latency path): the same tridiagonalisation with the whole symmetric matrix in REGISTERS.
+// Warp w owns the rows w, w + NW, w + 2 NW, ... (8 of them: cyclic, so the shrinking trailing block stays balanced over the
+// warps); lane l owns the columns l + 32 c, c < NC.  A step touches every trailing element once in the matrix-vector product
+// and once in the rank-2 update, both from registers; per step a lane loads only ITS NC entries of x and of (v, w) from shared
+// memory (conflict-free, one wavefront per 16 lanes) plus one (v_i, w_i) pair per row, and the 8 row sums of the product are
+// reduced over the 32 lanes by a transposed butterfly (9 exchanges instead of 40).  The shared-memory pipe, not the FP64
+// pipe, bounds this kernel (measured on the first version: 4 lanes per row and broadcast loads: 2.4 us per step), hence the layout.
+// Rows k+1 and k+2 are published to shared memory after every update: by symmetry they are the next pivot column x and the
+// next y1 = A(:, k+2).  The reflector scalars are computed by warp 0 alone and broadcast through shared memory.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int NJ>
-__global__ void __launch_bounds__(512) heig_tridiag_reg_kernel(const double* __restrict__ Gp, int n, int64_t ldg, int64_t bG, int nsplit,
-                                                                int64_t sG, double* __restrict__ d_out, double* __restrict__ e_out,
-                                                                double* __restrict__ tau_out, double* __restrict__ V_out, int64_t bV) {
-  constexpr int NP = 4 * NJ;
+template <int NW, int NC>
+__global__ void __launch_bounds__(NW * 32) heig_tridiag_reg_kernel(const double* __restrict__ Gp, int n, int64_t ldg, int64_t bG,
+                                                                   int nsplit, int64_t sG, double* __restrict__ d_out,
+                                                                   double* __restrict__ e_out, double* __restrict__ tau_out,
+                                                                   double* __restrict__ V_out, int64_t bV) {
+  constexpr int NP = 32 * NC;     // padded order (columns); rows: 8 * NW >= n
+  constexpr int NRW = 8;
   __shared__ __align__(16) double xs[NP];
   __shared__ __align__(16) double ys[NP];
-  __shared__ __align__(16) double2 vw[NP];
+  __shared__ __align__(16) double2 vw[NP > 8 * NW ? NP : 8 * NW];
   __shared__ double red[3 * 32];
   __shared__ double y0s[2];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int ir = lane & 7, lq = lane >> 3;
-  const int i = warp * 8 + ir;
+  __shared__ double scal[4];      // sc, tau, a2-prefactor pieces, have
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
   const int64_t mb = blockIdx.x;
   const double* Gb = Gp + mb * bG;
   d_out += mb * n; e_out += mb * n; tau_out += mb * n; V_out += mb * bV;
 
-  double a[NJ];
+  double a[NRW][NC];
 #pragma unroll
-  for (int m = 0; m < NJ; ++m) {
-    const int j = lq + 4 * m;
-    double v = 0.0;
-    if (i < n && j < n)
-      for (int s = 0; s < nsplit; ++s) v += Gb[s * sG + j + (int64_t)i * ldg];
-    a[m] = v;
+  for (int rr = 0; rr < NRW; ++rr) {
+    const int i = w + NW * rr;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int j = lane + 32 * c;
+      double v = 0.0;
+      if (i < n && j < n) {
+        // the upper triangle of G is read (G is symmetric up to the rounding of the split-K sums)
+        const int64_t off = j <= i ? j + (int64_t)i * ldg : i + (int64_t)j * ldg;
+        for (int s = 0; s < nsplit; ++s) v += Gb[s * sG + off];
+      }
+      a[rr][c] = v;
+    }
   }
-  for (int idx = tid; idx < NP; idx += blockDim.x) { xs[idx] = 0.0; ys[idx] = 0.0; vw[idx] = make_double2(0.0, 0.0); }
+  for (int idx = tid; idx < NP; idx += blockDim.x) { xs[idx] = 0.0; ys[idx] = 0.0; }
+  for (int idx = tid; idx < (NP > 8 * NW ? NP : 8 * NW); idx += blockDim.x) vw[idx] = make_double2(0.0, 0.0);
   for (int idx = tid; idx < 96; idx += blockDim.x) red[idx] = 0.0;
   __syncthreads();
-  if (i == 0 || i == 1) {
-    double* dst = i == 0 ? xs : ys;
-    if (i < n) {
+  // rows 0 and 1 -> xs, ys  (row i lives in warp i % NW, register row i / NW)
 #pragma unroll
-      for (int m = 0; m < NJ; ++m) dst[lq + 4 * m] = a[m];
+  for (int rr = 0; rr < NRW; ++rr) {
+    const int i = w + NW * rr;
+    if (i == 0 || i == 1) {
+      double* dst = i == 0 ? xs : ys;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) dst[lane + 32 * c] = a[rr][c];
     }
   }
   __syncthreads();
 
+  const int myrr = (lane >> 2) & 7;          // the row whose sum this lane ends up with
+  const int myrow = w + NW * myrr;
+  const bool owner = (lane & 3) == 0;
+
   for (int k = 0; k < n - 1; ++k) {
     const int k1 = k + 1;
-    const bool rowact = (i > k) && (i < n);
-    const int m_lo = (k + 2) >> 2;
-    // ---- A: y2_i = sum_{j >= k+2} A(i,j) x_j ----
-    double y2 = 0.0;
-    if (rowact) {
-      double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+    // ---- A: y2_i = sum_{j >= k+2} A(i,j) x_j for the warp's rows ----
+    double xr[NC];
 #pragma unroll
-      for (int m = 0; m < NJ; ++m) {
-        if (m >= m_lo) {
-          const int j = lq + 4 * m;
-          const double xv = (m > m_lo || j >= k + 2) ? xs[j] : 0.0;
-          if ((m & 3) == 0) c0 = fma(a[m], xv, c0);
-          else if ((m & 3) == 1) c1 = fma(a[m], xv, c1);
-          else if ((m & 3) == 2) c2 = fma(a[m], xv, c2);
-          else c3 = fma(a[m], xv, c3);
-        }
-      }
-      y2 = (c0 + c1) + (c2 + c3);
+    for (int c = 0; c < NC; ++c) {
+      const int j = lane + 32 * c;
+      xr[c] = (j >= k + 2) ? xs[j] : 0.0;
     }
-    y2 += __shfl_xor_sync(0xffffffffu, y2, 8);
-    y2 += __shfl_xor_sync(0xffffffffu, y2, 16);
+    double p[NRW];
+#pragma unroll
+    for (int rr = 0; rr < NRW; ++rr) {
+      double acc = 0.0;
+      if (w + NW * rr > k) {                 // warp-uniform
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc = fma(a[rr][c], xr[c], acc);
+      }
+      p[rr] = acc;
+    }
+    // transposed butterfly: 8 sums over 32 lanes; lane l ends with the total of row (l >> 2) & 7
+    double y2;
+    {
+      const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+      double p4[4], p2[2];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const double send = h16 ? p[q] : p[q + 4], keep = h16 ? p[q + 4] : p[q];
+        p4[q] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const double send = h8 ? p4[q] : p4[q + 2], keep = h8 ? p4[q + 2] : p4[q];
+        p2[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+      {
+        const double send = h4 ? p2[0] : p2[1], keep = h4 ? p2[1] : p2[0];
+        y2 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+      y2 += __shfl_xor_sync(0xffffffffu, y2, 2);
+      y2 += __shfl_xor_sync(0xffffffffu, y2, 1);
+    }
+    const bool rowact = owner && myrow > k && myrow < n;
     double y1 = 0.0, xi = 0.0, q0 = 0.0, q1 = 0.0, q2 = 0.0;
-    if (rowact && lq == 0) {
-      y1 = ys[i];
-      if (i == k1) { y0s[0] = y1; y0s[1] = y2; }
+    if (rowact) {
+      y1 = ys[myrow];
+      if (myrow == k1) { y0s[0] = y1; y0s[1] = y2; }
       else {
-        xi = xs[i];
+        xi = xs[myrow];
         q0 = xi * xi; q1 = y1 * xi; q2 = y2 * xi;
       }
     }
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {
+    for (int o = 4; o < 32; o <<= 1) {
       q0 += __shfl_xor_sync(0xffffffffu, q0, o);
       q1 += __shfl_xor_sync(0xffffffffu, q1, o);
       q2 += __shfl_xor_sync(0xffffffffu, q2, o);
     }
-    if (lane == 0) { red[warp] = q0; red[32 + warp] = q1; red[64 + warp] = q2; }
+    if (lane == 0) { red[w] = q0; red[32 + w] = q1; red[64 + w] = q2; }
     __syncthreads();   // 1
-    // ---- B: scalars, v, w ----
-    q0 = red[lane]; q1 = red[32 + lane]; q2 = red[64 + lane];
+    // ---- B: scalars (warp 0), broadcast ----
+    if (w == 0) {
+      double s0 = red[lane], s1 = red[32 + lane], s2 = red[64 + lane];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      q0 += __shfl_xor_sync(0xffffffffu, q0, o);
-      q1 += __shfl_xor_sync(0xffffffffu, q1, o);
-      q2 += __shfl_xor_sync(0xffffffffu, q2, o);
-    }
-    const double xn2 = q0;
-    const double ar = xs[k1];
-    const bool have = xn2 != 0.0;
-    double beta = ar, tau = 0.0;
-    if (have) {
-      const double s2 = fma(ar, ar, xn2);
-      const double inv = rsqrt(s2), nrm = s2 * inv;
-      const double sg = ar >= 0.0 ? 1.0 : -1.0;
-      beta = -sg * nrm;
-      tau = fma(fabs(ar), inv, 1.0);
-      const double dr = sg * (fabs(ar) + nrm);          // alpha - beta
-      const double r1 = rsqrt(dr * dr), sc = sg * r1 * r1 * fabs(dr);   // 1 / (alpha - beta)
-      if (rowact && lq == 0) {
-        // p^T v = tau [y1_0 + s y2_0 + s a + s^2 b]
-        const double pv = tau * (y0s[0] + sc * (y0s[1] + q1 + sc * q2));
-        const double a2 = -0.5 * tau * pv;
-        const double vi = (i == k1) ? 1.0 : sc * xi;
-        const double p = tau * fma(sc, y2, y1);
-        vw[i] = make_double2(vi, fma(a2, vi, p));
-        V_out[refl_off(k, n) + (i - k1)] = vi;
+      for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
       }
-    } else if (rowact && lq == 0) {
-      V_out[refl_off(k, n) + (i - k1)] = (i == k1) ? 1.0 : 0.0;
-    }
-    if (tid == 0) { d_out[k] = xs[k]; e_out[k] = beta; tau_out[k] = tau; }
-    __syncthreads();   // 2
-    // ---- C: A22 -= v w^T + w v^T (whole rows), hand rows k+1, k+2 over ----
-    if (rowact) {
-      if (have) {
-        const double2 me = vw[i];
-        const int m_c = k1 >> 2;
-#pragma unroll
-        for (int m = 0; m < NJ; ++m) {
-          if (m >= m_c) {
-            const double2 o = vw[lq + 4 * m];      // zero beyond n; columns < k+1 of the m_c group are dead
-            a[m] = fma(-me.x, o.y, fma(-me.y, o.x, a[m]));
-          }
+      if (lane == 0) {
+        const double ar = xs[k1];
+        const bool have = s0 != 0.0;
+        double beta = ar, tau = 0.0, sc = 0.0, a2 = 0.0;
+        if (have) {
+          const double sq = fma(ar, ar, s0);
+          const double inv = rsqrt(sq), nrm = sq * inv;
+          const double sg = ar >= 0.0 ? 1.0 : -1.0;
+          beta = -sg * nrm;
+          tau = fma(fabs(ar), inv, 1.0);
+          const double dr = fabs(ar) + nrm;               // |alpha - beta|
+          const double r1 = rsqrt(dr * dr);
+          sc = sg * r1 * r1 * dr;                         // 1 / (alpha - beta)
+          // p^T v = tau [y1_0 + s y2_0 + s a + s^2 b],  a2 = -tau/2 (p^T v)
+          const double pv = tau * (y0s[0] + sc * (y0s[1] + s1 + sc * s2));
+          a2 = -0.5 * tau * pv;
         }
+        scal[0] = sc; scal[1] = tau; scal[2] = a2; scal[3] = have ? 1.0 : 0.0;
+        d_out[k] = xs[k]; e_out[k] = beta; tau_out[k] = tau;
       }
-      if (i == k1 || i == k1 + 1) {
-        double* dst = i == k1 ? xs : ys;
-#pragma unroll
-        for (int m = 0; m < NJ; ++m) dst[lq + 4 * m] = a[m];
+    }
+    __syncthreads();   // 2
+    const bool have = scal[3] != 0.0;
+    if (rowact) {
+      double vi = (myrow == k1) ? 1.0 : 0.0;
+      if (have) {
+        const double sc = scal[0], tau = scal[1], a2 = scal[2];
+        if (myrow != k1) vi = sc * xi;
+        const double pp = tau * fma(sc, y2, y1);
+        vw[myrow] = make_double2(vi, fma(a2, vi, pp));
       }
+      V_out[refl_off(k, n) + (myrow - k1)] = vi;
     }
     __syncthreads();   // 3
+    // ---- C: A22 -= v w^T + w v^T (whole rows, registers), hand rows k+1, k+2 over ----
+    if (have) {
+      double2 cj[NC];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) cj[c] = vw[lane + 32 * c];     // zero beyond n; columns <= k are dead
+#pragma unroll
+      for (int rr = 0; rr < NRW; ++rr) {
+        const int i = w + NW * rr;
+        if (i > k && i < n) {                  // warp-uniform
+          const double2 me = vw[i];
+#pragma unroll
+          for (int c = 0; c < NC; ++c) a[rr][c] = fma(-me.x, cj[c].y, fma(-me.y, cj[c].x, a[rr][c]));
+        }
+      }
+    }
+#pragma unroll
+    for (int rr = 0; rr < NRW; ++rr) {
+      const int i = w + NW * rr;
+      if (i == k1 || i == k1 + 1) {            // warp-uniform
+        double* dst = i == k1 ? xs : ys;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) dst[lane + 32 * c] = a[rr][c];
+      }
+    }
+    __syncthreads();   // 4
   }
   if (tid == 0) { d_out[n - 1] = xs[n - 1]; e_out[n - 1] = 0.0; tau_out[n - 1] = 0.0; }
 }
@@ -853,13 +906,12 @@ bool heig_top(const T* G, int n, int64_t ldg, int64_t bG, int nsplit, int64_t sG
   bool done_tridiag = false;
   if (!is_cplx<T>::value && n <= 128 && n >= 2) {
     // Float64: whole matrix in registers (latency path of the single-train rounding chain; also the fastest batched form)
-    const int nt = ((n + 7) / 8) * 32;
     const double* Gd = reinterpret_cast<const double*>(G);
     double* taud = reinterpret_cast<double*>(tau.p);
     double* Vd = reinterpret_cast<double*>(V.p);
-    if (n <= 32) heig_tridiag_reg_kernel<8><<<batch, nt, 0, ctx().stream>>>(Gd, n, ldg, bG, nsplit, sG, d.as<double>(), e.as<double>(), taud, Vd, bV);
-    else if (n <= 64) heig_tridiag_reg_kernel<16><<<batch, nt, 0, ctx().stream>>>(Gd, n, ldg, bG, nsplit, sG, d.as<double>(), e.as<double>(), taud, Vd, bV);
-    else heig_tridiag_reg_kernel<32><<<batch, nt, 0, ctx().stream>>>(Gd, n, ldg, bG, nsplit, sG, d.as<double>(), e.as<double>(), taud, Vd, bV);
+    if (n <= 32) heig_tridiag_reg_kernel<4, 1><<<batch, 128, 0, ctx().stream>>>(Gd, n, ldg, bG, nsplit, sG, d.as<double>(), e.as<double>(), taud, Vd, bV);
+    else if (n <= 64) heig_tridiag_reg_kernel<8, 2><<<batch, 256, 0, ctx().stream>>>(Gd, n, ldg, bG, nsplit, sG, d.as<double>(), e.as<double>(), taud, Vd, bV);
+    else heig_tridiag_reg_kernel<16, 4><<<batch, 512, 0, ctx().stream>>>(Gd, n, ldg, bG, nsplit, sG, d.as<double>(), e.as<double>(), taud, Vd, bV);
     TTN_CHECK_LAUNCH();
     ctx().launches++;
     done_tridiag = true;

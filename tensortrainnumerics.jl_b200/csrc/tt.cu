@@ -523,6 +523,83 @@ struct GramSweep {
       ctx().launches++;
     }
   }
+  // Theta (p x q) of bond (k, k+1), materialised or folded product
+  void theta(int k, bool virt, DevBuf& Th) {
+    const int batch = x.batch;
+    const int n1 = (int)x.dims[k], n2 = (int)x.dims[k + 1];
+    const int rl = (int)x.rks[k], r = (int)x.rks[k + 1], rr = (int)x.rks[k + 2];
+    const int p = n1 * rl, q = n2 * rr;
+    if (virt && (size_t)lazy->A->rks[k + 1] * n2 * n2 * lazy->A->rks[k + 2] * sizeof(T) <= 40 * 1024) {
+      theta_lazy(k, Th);           // core k+1 stays virtual until the truncated core replaces it
+    } else {
+      materialize(k + 1);
+      GemmArgs g;  // Theta[(s1,alpha),(s2,beta)] = sum_gamma A[s1,alpha,gamma] B[s2,gamma,beta]     (tt_tools.jl:749)
+      g.M = p; g.N = rr; g.K = r;
+      g.A = x.cores[k].p; g.sAm = 1; g.sAk = p; g.bA1 = 0; g.bA2 = x.core_elems(k);
+      g.B = x.cores[k + 1].p; g.sBk = n2; g.sBn = (int64_t)n2 * r; g.bB1 = 1; g.bB2 = x.core_elems(k + 1);
+      g.C = Th.p; g.sCm = 1; g.sCn = (int64_t)p * n2; g.bC1 = p; g.bC2 = (int64_t)p * q;
+      g.batch1 = n2; g.batch2 = batch;
+      gemm<T>(g);
+    }
+  }
+  // L->R step of a TALL bond (p > q: the last sites of a train): G = Theta^H Theta = V S^2 V^H (q x q),
+  // core k+1 <- sqrt(S) V^H, core k <- Theta V S^{-1/2} = U sqrt(S)
+  bool step_tall(int k, bool virt, int nev, int rn, double* sig0) {
+    const int batch = x.batch;
+    const int n1 = (int)x.dims[k], n2 = (int)x.dims[k + 1];
+    const int rl = (int)x.rks[k], rr = (int)x.rks[k + 2];
+    const int p = n1 * rl, q = n2 * rr;
+    DevBuf Th(sizeof(T) * (size_t)p * q * batch);
+    theta(k, virt, Th);
+    DevBuf Gp(sizeof(T) * (size_t)q * q * batch);
+    {
+      GemmArgs g;   // G[c, c'] = sum_row conj(Theta[row, c]) Theta[row, c']
+      g.M = q; g.N = q; g.K = p;
+      g.A = Th.p; g.sAm = p; g.sAk = 1; g.conjA = true; g.bA1 = (int64_t)p * q;
+      g.B = Th.p; g.sBk = 1; g.sBn = p; g.bB1 = (int64_t)p * q;
+      g.C = Gp.p; g.sCm = 1; g.sCn = q; g.bC1 = (int64_t)q * q;
+      g.batch1 = batch;
+      gemm<T>(g);
+    }
+    DevBuf lam(sizeof(double) * (size_t)nev * batch), V(sizeof(T) * (size_t)q * nev * batch);
+    if (!heig_top<T>(Gp.as<T>(), q, q, (int64_t)q * q, 1, 0, nev, batch, lam.as<double>(), V.as<T>(), flags.as<int>())) {
+      materialize(k + 1);
+      return false;
+    }
+    DevBuf Vs(sizeof(T) * (size_t)q * nev * batch), Vi(sizeof(T) * (size_t)q * nev * batch), w(sizeof(double) * (size_t)rn * batch);
+    DevBuf newA(sizeof(T) * (size_t)p * rn * batch), newB(sizeof(T) * (size_t)n2 * rn * rr * batch);
+    if (nev < rn) {
+      fill<T>(newA.as<T>(), (int64_t)p * rn * batch, t_zero<T>());
+      fill<T>(newB.as<T>(), (int64_t)n2 * rn * rr * batch, t_zero<T>());
+      TTN_CUDA(cudaMemsetAsync(w.p, 0, w.bytes, ctx().stream));
+    }
+    heig_finalize<T>(V.as<T>(), q, nev, batch, lam.as<double>(), nullptr, Vs.as<T>(), q, (int64_t)q * nev, Vi.as<T>(), q,
+                     (int64_t)q * nev, w.as<double>(), rn, sig0, flags.as<int>());
+    {
+      Copy4 c;   // newB[s2, kappa, beta] = conj(Vs[(s2, beta), kappa])
+      c.n0 = n2; c.s0 = 1; c.d0 = 1;
+      c.n1 = nev; c.s1 = q; c.d1 = n2;
+      c.n2 = rr; c.s2 = n2; c.d2 = (int64_t)n2 * rn;
+      c.n3 = batch; c.s3 = (int64_t)q * nev; c.d3 = (int64_t)n2 * rn * rr;
+      c.conj = true;
+      copy4<T>(Vs.as<T>(), newB.as<T>(), c);
+    }
+    {
+      GemmArgs g;   // core k <- Theta (V S^{-1/2})
+      g.M = p; g.N = nev; g.K = q;
+      g.A = Th.p; g.sAm = 1; g.sAk = p; g.bA1 = (int64_t)p * q;
+      g.B = Vi.p; g.sBk = 1; g.sBn = q; g.bB1 = (int64_t)q * nev;
+      g.C = newA.p; g.sCm = 1; g.sCn = p; g.bC1 = (int64_t)p * rn;
+      g.batch1 = batch;
+      gemm<T>(g);
+    }
+    colw[k] = std::move(w);
+    replace(k, std::move(newA));
+    replace(k + 1, std::move(newB));
+    if (lazy) lazy->virt[k + 1] = 0;
+    x.rks[k + 1] = rn;
+    return true;
+  }
   // one bond step; returns false when the shape is not served (caller takes the classic step)
   bool step(int k, bool left_to_right, int64_t step_idx) {
     const int batch = x.batch;
@@ -576,22 +653,13 @@ struct GramSweep {
       return true;
     }
     const bool virt = lazy && lazy->virt[k + 1];
-    const bool served = left_to_right && p <= q && p <= heig_max_n<T>() && !((int64_t)std::min(rn, r) > sigma_stride && sig0);
+    const int ng = std::min(p, q);                       // order of the Gram matrix: Theta Theta^H (wide) or Theta^H Theta (tall)
+    const bool served = left_to_right && ng <= heig_max_n<T>() && !((int64_t)std::min(rn, r) > sigma_stride && sig0);
     if (!served) { materialize(k + 1); return false; }
     const int nev = std::min(rn, r);
+    if (p > q) return step_tall(k, virt, nev, rn, sig0);
     DevBuf Th(sizeof(T) * (size_t)p * q * batch);
-    if (virt && (size_t)lazy->A->rks[k + 1] * n2 * n2 * lazy->A->rks[k + 2] * sizeof(T) <= 40 * 1024) {
-      theta_lazy(k, Th);           // core k+1 stays virtual until the truncated core replaces it below
-    } else {
-      materialize(k + 1);
-      GemmArgs g;  // Theta[(s1,alpha),(s2,beta)] = sum_gamma A[s1,alpha,gamma] B[s2,gamma,beta]     (tt_tools.jl:749)
-      g.M = p; g.N = rr; g.K = r;
-      g.A = x.cores[k].p; g.sAm = 1; g.sAk = p; g.bA1 = 0; g.bA2 = x.core_elems(k);
-      g.B = x.cores[k + 1].p; g.sBk = n2; g.sBn = (int64_t)n2 * r; g.bB1 = 1; g.bB2 = x.core_elems(k + 1);
-      g.C = Th.p; g.sCm = 1; g.sCn = (int64_t)p * n2; g.bC1 = p; g.bC2 = (int64_t)p * q;
-      g.batch1 = n2; g.batch2 = batch;
-      gemm<T>(g);
-    }
+    theta(k, virt, Th);
     DevBuf Gp;
     const int nsplit = gram(Th.as<T>(), p, q, Gp);
     DevBuf lam(sizeof(double) * (size_t)nev * batch), U(sizeof(T) * (size_t)p * nev * batch);
