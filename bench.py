@@ -468,6 +468,21 @@ def run_ours(args, rank, local_rank, world):
             extras["matvec_cfg4_sharded"] = sm
             compact["matvec_cfg4_sharded_fused_ms"] = sm.get("fused_ms")
             compact["matvec_cfg4_sharded_tflops"] = sm.get("fused_tflops")
+            # cfg4 DMRG sweep over all ranks: replicated sweep, Lanczos matvec of every bond step sharded (csrc/shard.cu)
+            def exchange(bts):
+                out = [None] * world
+                dist.all_gather_object(out, bts)
+                return out
+            sc = t.ShardContext(np.float64, args.dmrg_chi * args.dmrg_chi * 4, rank, world, exchange)
+            ds = bench_dmrg(t, args.dmrg_chi, shard=sc)
+            tm = torch.tensor([ds["value"]], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            ds["value"] = float(tm.item())
+            ds["n_gpus"] = world
+            ds["note"] += "; sweep replicated on every rank, Lanczos matvecs sharded over the ranks with the fused all-gather epilogue"
+            sc.free()
+            extras["dmrg_sweep_sharded"] = ds
+            compact["dmrg_sweep_sharded_s"] = ds["value"]
         if rank == 0:
             extras["cfg2"] = bench_cfg2(t, torch, stream)
             compact["cfg2_sweeps_per_s"] = extras["cfg2"]["value"]
@@ -614,7 +629,7 @@ def bench_matvec(t, torch, stream, peak64, chi=1024, w=5, nn=4, reps=10):
             "note": "one application of K (dmrg.jl:239-244 applies the symmetrised pair: twice this work); working set 0.5 GB > L2"}
 
 
-def bench_dmrg(t, chi, L=64, kd=8):
+def bench_dmrg(t, chi, L=64, kd=8, shard=None):
     """cfg4-style DMRG sweep: Heisenberg XYZ chain L=64 (MPO rank 5), one full two-site sweep from a random TT capped at
     bond `chi`, fixed Lanczos budget (krylovdim 8 x 1 restart) as in SURVEY.md §8(d)-4; symmetrize=True as dmrg.jl:241."""
     sys.path.insert(0, os.path.join(ROOT, "tools"))
@@ -625,7 +640,7 @@ def bench_dmrg(t, chi, L=64, kd=8):
     t.reset_launch_count()
     t0 = time.perf_counter()
     E, x, rh = t.dmrg_eigsolve(H, x0, N=2, tol=1e-12, sweep_schedule=[2], rmax_schedule=[chi], linsolv_maxiter=1,
-                               linsolv_tol=1e-10, krylovdim=kd, symmetrize=True)
+                               linsolv_tol=1e-10, krylovdim=kd, symmetrize=True, shard=shard)
     t.synchronize()
     el = time.perf_counter() - t0
     return {"metric": "DMRG sweep s", "value": el, "unit": "s", "L": L, "chi": chi, "krylovdim": kd, "bond_steps": len(E),

@@ -230,6 +230,19 @@ int ttn_shard_eigsolve(ttn_shard_matvec mv, void* x_dev, int krylovdim, int maxi
 int ttn_shard_matvec_slice(ttn_shard_matvec mv, int* c0, int* cp);
 int ttn_shard_matvec_error(ttn_shard_matvec mv, int* err);    /* 1 if an epoch wait timed out (a peer died) */
 int ttn_shard_matvec_free(ttn_shard_matvec mv);
+
+/* ---- DMRG over several GPUs of one node (one process per GPU): the sweep of src/solvers/dmrg.jl:501-578 runs replicated
+ * on every rank (identical data, environment updates and two-site SVDs replicated), the Lanczos matvec of every bond step
+ * (dmrg.jl:239-245) is sharded on the bra index of the right environment and exchanged through the fused all-gather
+ * epilogue over NVLink peer memory.  The exchange buffers live in a context created ONCE (max_elems >= chi_max^2 n^N
+ * elements), exported as 2 x 192 bytes of CUDA IPC handles and bound to the handles of all ranks (rank-major). */
+typedef struct ttn_shard_ctx_s* ttn_shard_ctx;
+int ttn_shard_ctx_create(int dtype, int64_t max_elems, int rank, int nranks, ttn_shard_ctx* out);
+int ttn_shard_ctx_handles(ttn_shard_ctx c, void* handles384);
+int ttn_shard_ctx_bind(ttn_shard_ctx c, const void* all_handles);
+int ttn_shard_ctx_free(ttn_shard_ctx c);
+int ttn_dmrg_eigsolve_sharded(ttn_tto A, ttn_ttv x0, const ttn_solver_params* p, ttn_shard_ctx sc, ttn_ttv* x, double* E,
+                              int64_t* r_hist, int cap_E, int* n_E);
 /* environment updates on HOST arrays, reference layouts (src/solvers/dmrg.jl:27-35) */
 int ttn_env_left_host(int dtype, int n, int w_l, int w_r, int r_l, int r_r, const void* G, const void* x, const void* A,
                       void* Gout);

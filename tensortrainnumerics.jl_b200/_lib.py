@@ -91,6 +91,9 @@ def load():
         "ttn_mals_eigsolve": [vp, vp, C.POINTER(SolverParams), vpp, dp, i64p, C.c_int, ip],
         "ttn_dmrg_linsolve": [vp, vp, vp, C.POINTER(SolverParams), vpp, dp],
         "ttn_dmrg_eigsolve": [vp, vp, C.POINTER(SolverParams), vpp, dp, i64p, C.c_int, ip],
+        "ttn_dmrg_eigsolve_sharded": [vp, vp, C.POINTER(SolverParams), vp, vpp, dp, i64p, C.c_int, ip],
+        "ttn_shard_ctx_create": [C.c_int, C.c_int64, C.c_int, C.c_int, vpp], "ttn_shard_ctx_handles": [vp, vp],
+        "ttn_shard_ctx_bind": [vp, vp], "ttn_shard_ctx_free": [vp],
         "ttn_tdvp": [vp, vp, C.POINTER(TdvpParams), vpp],
         "ttn_gemm": [C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int64, C.c_int64, C.c_int, vp, C.c_int64, C.c_int64,
                      C.c_int, vp, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_int, C.c_int64, C.c_int64, C.c_int64],

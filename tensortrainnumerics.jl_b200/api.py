@@ -32,7 +32,7 @@ __all__ = [
     "euclidean_distance_normalized",
     "orthogonalize", "tt_compress_", "tt_bond_truncate_", "als_linsolve", "als_eigsolve", "als_gen_eigsolv", "mals_linsolve",
     "mals_eigsolve", "dmrg_linsolve", "dmrg_eigsolve", "tdvp", "tdvp2", "matvec2", "env_left", "env_right",
-    "shard_range", "shard_batch", "assemble_slices", "ShardedMatvec", "apply_compress", "svdtrunc", "heig_top", "set_option", "get_option", "copy_synchronize", "qr_thin", "gemm_host", "launch_count", "reset_launch_count", "synchronize", "library_path", "profile", "profile_read", "stream_handle",
+    "shard_range", "shard_batch", "assemble_slices", "ShardedMatvec", "ShardContext", "apply_compress", "svdtrunc", "heig_top", "set_option", "get_option", "copy_synchronize", "qr_thin", "gemm_host", "launch_count", "reset_launch_count", "synchronize", "library_path", "profile", "profile_read", "stream_handle",
     "KERNEL_FAMILIES",
 ]
 
@@ -640,14 +640,41 @@ def mals_linsolve(A, b, tt_start, tol=1e-12, rmax=None, return_info=False, linso
     return (x, {"residual": res}) if return_info else x
 
 
-def _eig_with_hist(fn, A, tt_start, p, cap):
+def _eig_with_hist(fn, A, tt_start, p, cap, shard_ctx=None):
     xd, host = _dev(tt_start)
     Ad = _devo(A, xd.dtype)
     if Ad.dtype == np.complex128 and xd.dtype != np.complex128:
         xd = xd.complex()
     E, rh, nE, out = (C.c_double * cap)(), (C.c_int64 * cap)(), C.c_int(), C.c_void_p()
-    check(fn(Ad._h, xd._h, C.byref(p), C.byref(out), E, rh, cap, C.byref(nE)))
+    if shard_ctx is None:
+        check(fn(Ad._h, xd._h, C.byref(p), C.byref(out), E, rh, cap, C.byref(nE)))
+    else:
+        check(fn(Ad._h, xd._h, C.byref(p), shard_ctx.h, C.byref(out), E, rh, cap, C.byref(nE)))
     return np.array(E[:nE.value]), _ret(DeviceTT(out), host), [int(v) for v in rh[:nE.value]]
+
+
+class ShardContext:
+    """Exchange buffers of the sharded Lanczos matvec inside a multi-GPU DMRG sweep (`ttn_shard_ctx_*`): one per rank, created once
+    per solve with `max_elems >= chi_max^2 * n^N`; `exchange` all-gathers a bytes object over the ranks
+    (e.g. torch.distributed.all_gather_object) so that every rank can map its peers' buffers (CUDA IPC over NVLink)."""
+
+    def __init__(self, dtype, max_elems, rank, nranks, exchange):
+        lib = _lib.lib()
+        self.h = C.c_void_p()
+        self.rank, self.nranks = int(rank), int(nranks)
+        check(lib.ttn_shard_ctx_create(_dtype_code(dtype), int(max_elems), self.rank, self.nranks, C.byref(self.h)))
+        if self.nranks > 1:
+            buf = (C.c_char * 384)()
+            check(lib.ttn_shard_ctx_handles(self.h, buf))
+            allb = exchange(bytes(buf))
+            assert len(allb) == self.nranks and all(len(b) == 384 for b in allb)
+            joined = (C.c_char * (384 * self.nranks)).from_buffer_copy(b"".join(allb))
+            check(lib.ttn_shard_ctx_bind(self.h, joined))
+
+    def free(self):
+        if self.h:
+            check(_lib.lib().ttn_shard_ctx_free(self.h))
+            self.h = C.c_void_p()
 
 
 def mals_eigsolve(A, tt_start, tol=1e-12, sweep_schedule=(2,), rmax_schedule=None, it_solver=False, linsolv_maxiter=200,
@@ -681,8 +708,9 @@ def dmrg_linsolve(A, b, tt_start, sweep_count=2, N=2, tol=1e-12, sweep_schedule=
 
 
 def dmrg_eigsolve(A, tt_start, N=2, tol=1e-12, sweep_schedule=(2,), rmax_schedule=None, it_solver=False,
-                  linsolv_maxiter=200, linsolv_tol=None, itslv_thresh=256, krylovdim=30, symmetrize=True):
-    """src/solvers/dmrg.jl:501-578 → (E, tt_opt, r_hist)."""
+                  linsolv_maxiter=200, linsolv_tol=None, itslv_thresh=256, krylovdim=30, symmetrize=True, shard=None):
+    """src/solvers/dmrg.jl:501-578 → (E, tt_opt, r_hist).  `shard`: a bound `ShardContext` — every rank of a one-node job calls this
+    with identical arguments; the sweep runs replicated and the Lanczos matvec of every bond step is sharded over the ranks."""
     if rmax_schedule is None:
         rmax_schedule = [_isqrt_prod(tt_start.ttv_dims)]
     if len(rmax_schedule) != len(sweep_schedule):
@@ -693,6 +721,8 @@ def dmrg_eigsolve(A, tt_start, N=2, tol=1e-12, sweep_schedule=(2,), rmax_schedul
                       linsolv_maxiter=int(linsolv_maxiter), linsolv_tol=float(linsolv_tol), krylovdim=int(krylovdim),
                       symmetrize=int(bool(symmetrize)))
     cap = 2 * tt_start.N * (int(sweep_schedule[-1]) + 1) + 8
+    if shard is not None and shard.nranks > 1:
+        return _eig_with_hist(_lib.lib().ttn_dmrg_eigsolve_sharded, A, tt_start, p, cap, shard_ctx=shard)
     return _eig_with_hist(_lib.lib().ttn_dmrg_eigsolve, A, tt_start, p, cap)
 
 

@@ -666,6 +666,54 @@ int ttn_dmrg_eigsolve(ttn_tto A, ttn_ttv x0, const ttn_solver_params* p, ttn_ttv
   *x = h;
   API_END
 }
+// ---- multi-GPU DMRG: replicated sweep, sharded Lanczos matvec (shard.cu) -----------------------------------------
+int ttn_shard_ctx_create(int dtype, int64_t max_elems, int rank, int nranks, ttn_shard_ctx* out) {
+  API_BEGIN
+  need_init();
+  ttn_assert(out != nullptr && (dtype == TTN_F64 || dtype == TTN_C128), TTN_EARG, "shard ctx: bad arguments");
+  *out = shard_ctx_create(dtype, max_elems, rank, nranks);
+  API_END
+}
+int ttn_shard_ctx_handles(ttn_shard_ctx c, void* handles384) {
+  API_BEGIN
+  need_init();
+  shard_ctx_handles(c, handles384);
+  API_END
+}
+int ttn_shard_ctx_bind(ttn_shard_ctx c, const void* all_handles) {
+  API_BEGIN
+  need_init();
+  shard_ctx_bind(c, all_handles);
+  API_END
+}
+int ttn_shard_ctx_free(ttn_shard_ctx c) {
+  API_BEGIN
+  if (c) shard_ctx_free(c);
+  API_END
+}
+int ttn_dmrg_eigsolve_sharded(ttn_tto A, ttn_ttv x0, const ttn_solver_params* p, ttn_shard_ctx sc, ttn_ttv* x, double* E,
+                              int64_t* r_hist, int cap_E, int* n_E) {
+  API_BEGIN
+  SOLVER_PROLOGUE(A, x0)
+  ttn_assert(sc != nullptr, TTN_EARG, "null shard context");
+  active_shard_ctx() = sc;
+  try {
+    std::vector<double> Ev;
+    std::vector<int64_t> rh;
+    if (x0->dtype == TTN_F64) dmrg_eigsolve(A->r, x0->r, *p, h->r, Ev, rh);
+    else dmrg_eigsolve(A->c, x0->c, *p, h->c, Ev, rh);
+    active_shard_ctx() = nullptr;
+    ttn_assert(shard_ctx_error(sc) == 0, TTN_ECUDA,
+               "sharded DMRG: a peer did not publish its slice within the epoch timeout (TTN_SHARD_TIMEOUT_S); the result is invalid");
+    if (n_E) *n_E = (int)Ev.size();
+    for (int i = 0; i < (int)Ev.size() && i < cap_E; ++i) {
+      if (E) E[i] = Ev[i];
+      if (r_hist) r_hist[i] = rh[i];
+    }
+  } catch (...) { active_shard_ctx() = nullptr; delete h; throw; }
+  *x = h;
+  API_END
+}
 int ttn_tdvp(ttn_tto H, ttn_ttv u0, const ttn_tdvp_params* p, ttn_ttv* u) {
   API_BEGIN
   need_init();

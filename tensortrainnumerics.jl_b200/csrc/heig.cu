@@ -240,20 +240,33 @@ __global__ void __launch_bounds__(NW * 32) heig_tridiag_reg_kernel(const double*
   const double* Gb = Gp + mb * bG;
   d_out += mb * n; e_out += mb * n; tau_out += mb * n; V_out += mb * bV;
 
+  // the upper triangle of G is read (G is symmetric up to the rounding of the split-K sums); split loop outermost so that the
+  // 8 * NC loads of a partial matrix are independent and in flight together (the profile of the first version showed 10 % of
+  // the kernel in this prologue, latency bound)
   double a[NRW][NC];
 #pragma unroll
-  for (int rr = 0; rr < NRW; ++rr) {
-    const int i = w + NW * rr;
+  for (int rr = 0; rr < NRW; ++rr)
 #pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      const int j = lane + 32 * c;
-      double v = 0.0;
-      if (i < n && j < n) {
-        // the upper triangle of G is read (G is symmetric up to the rounding of the split-K sums)
-        const int64_t off = j <= i ? j + (int64_t)i * ldg : i + (int64_t)j * ldg;
-        for (int s = 0; s < nsplit; ++s) v += Gb[s * sG + off];
+    for (int c = 0; c < NC; ++c) a[rr][c] = 0.0;
+  for (int s = 0; s < nsplit; ++s) {
+    const double* Gs = Gb + s * sG;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {          // two batches of 4 rows: 4 NC loads in flight without spilling the 8 NC accumulators
+      double v[NRW / 2][NC];
+#pragma unroll
+      for (int r2 = 0; r2 < NRW / 2; ++r2) {
+        const int i = w + NW * (r2 + h * (NRW / 2));
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const int j = lane + 32 * c;
+          const int lo = j <= i ? j : i, hi = j <= i ? i : j;
+          v[r2][c] = (i < n && j < n) ? __ldg(Gs + lo + (int64_t)hi * ldg) : 0.0;
+        }
       }
-      a[rr][c] = v;
+#pragma unroll
+      for (int r2 = 0; r2 < NRW / 2; ++r2)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) a[r2 + h * (NRW / 2)][c] += v[r2][c];
     }
   }
   for (int idx = tid; idx < NP; idx += blockDim.x) { xs[idx] = 0.0; ys[idx] = 0.0; }
@@ -354,9 +367,12 @@ __global__ void __launch_bounds__(NW * 32) heig_tridiag_reg_kernel(const double*
           const double sg = ar >= 0.0 ? 1.0 : -1.0;
           beta = -sg * nrm;
           tau = fma(fabs(ar), inv, 1.0);
-          const double dr = fabs(ar) + nrm;               // |alpha - beta|
-          const double r1 = rsqrt(dr * dr);
-          sc = sg * r1 * r1 * dr;                         // 1 / (alpha - beta)
+          // 1 / (alpha - beta) = sg / (|ar| + nrm) = sg inv / tau with tau in [1, 2]: reciprocal by Newton from a float seed
+          // (two steps: 2^-23 -> 2^-46 -> below 2^-53), shorter than a second rsqrt on the serial path of the step
+          double rt = (double)__frcp_rn((float)tau);
+          rt = rt * fma(-tau, rt, 2.0);
+          rt = rt * fma(-tau, rt, 2.0);
+          sc = sg * inv * rt;
           // p^T v = tau [y1_0 + s y2_0 + s a + s^2 b],  a2 = -tau/2 (p^T v)
           const double pv = tau * (y0s[0] + sc * (y0s[1] + s1 + sc * s2));
           a2 = -0.5 * tau * pv;

@@ -92,6 +92,7 @@ template <class T>
 struct ShardOp {
   int chi_l = 1, chi_r = 1, w_l = 1, w_r = 1, nn = 1, rank = 0, nranks = 1, c0 = 0, cp = 1;
   DevBuf L, Rs, Wq, T1, T2, err;
+  const void* Lp = nullptr;                // L2[a,(y,d)] used by the last GEMM: L.p, or the sweep's environment itself (no copy)
   void* Ybuf[2] = {nullptr, nullptr};      // cudaMalloc (IPC-exportable), full (chi_l, nn, chi_r) vectors
   unsigned* flags = nullptr;               // cudaMalloc, [2][nranks] epoch counters (one row per buffer parity is not needed)
   void* Ypeer[2][8] = {};
@@ -138,6 +139,7 @@ static void shard_setup(ShardOp<T>& op, int w_l, int w_r, int chi_l, int chi_r, 
     c.n2 = chi_l; c.s2 = (int64_t)w_l * chi_l; c.d2 = (int64_t)chi_l * w_l;
     copy4<T>(Gd.as<T>(), op.L.template as<T>(), c);
   }
+  op.Lp = op.L.p;
   // Rs[f, z, c_loc] = H[z, c0 + c_loc, f]   (reference layout [mpo, bra, ket], dmrg.jl:27-30)
   op.Rs.alloc(sizeof(T) * (size_t)chi_r * w_r * op.cp);
   {
@@ -197,7 +199,7 @@ static T* shard_apply(ShardOp<T>& op, const T* V) {
   {
     GemmArgs g;  // Y[a,(b,c)] = L[a,(y,d)] T2[(y,d),(b,c)]   (+ fused all-gather: peers get the same tiles)
     g.M = cl; g.N = nn * cp; g.K = wl * cl;
-    g.A = op.L.p; g.sAm = 1; g.sAk = cl;
+    g.A = op.Lp; g.sAm = 1; g.sAk = cl;
     g.B = op.T2.p; g.sBk = 1; g.sBn = (int64_t)wl * cl;
     g.C = Y + (int64_t)cl * nn * op.c0; g.sCm = 1; g.sCn = cl;
     if (op.bound) {
@@ -219,7 +221,7 @@ static T* shard_apply(ShardOp<T>& op, const T* V) {
 struct ShardHandles { cudaIpcMemHandle_t y[2]; cudaIpcMemHandle_t flags; };
 
 template <class T>
-static void shard_bind(ShardOp<T>& op, const ShardHandles* all) {
+static void shard_bind(ShardOp<T>& op, const ShardHandles* all, int stride = 1) {
   std::vector<unsigned*> fp(8, nullptr);
   for (int q = 0; q < op.nranks; ++q) {
     if (q == op.rank) {
@@ -228,12 +230,12 @@ static void shard_bind(ShardOp<T>& op, const ShardHandles* all) {
     }
     for (int i = 0; i < 2; ++i) {
       void* p = nullptr;
-      TTN_CUDA(cudaIpcOpenMemHandle(&p, all[q].y[i], cudaIpcMemLazyEnablePeerAccess));
+      TTN_CUDA(cudaIpcOpenMemHandle(&p, all[q * stride].y[i], cudaIpcMemLazyEnablePeerAccess));
       op.opened.push_back(p);
       op.Ypeer[i][q] = p;
     }
     void* f = nullptr;
-    TTN_CUDA(cudaIpcOpenMemHandle(&f, all[q].flags, cudaIpcMemLazyEnablePeerAccess));
+    TTN_CUDA(cudaIpcOpenMemHandle(&f, all[q * stride].flags, cudaIpcMemLazyEnablePeerAccess));
     op.opened.push_back(f);
     fp[q] = reinterpret_cast<unsigned*>(f);
   }
@@ -241,6 +243,89 @@ static void shard_bind(ShardOp<T>& op, const ShardHandles* all) {
   TTN_CUDA(cudaMemcpyAsync(op.flag_peer_d.p, fp.data(), sizeof(unsigned*) * 8, cudaMemcpyHostToDevice, ctx().stream));
   TTN_CUDA(cudaStreamSynchronize(ctx().stream));
   op.bound = true;
+}
+
+}  // namespace ttn
+
+namespace ttn {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The sharded operator INSIDE a DMRG sweep: every rank runs the same sweep on identical data
+// (environment updates and the two-site SVD are replicated); the Lanczos matvec of every bond step is sharded on the bra
+// index of the right environment and exchanged through the fused all-gather epilogue.  The exchange buffers are allocated
+// ONCE per solve at the largest window size and exported as CUDA IPC handles; per bond step the operator is re-bound to the
+// sweep's device-resident environments (canonical layout E[bra, mpo, ket]): the left environment is used in place, the owned
+// slice of the right environment and the fused MPO are re-laid out by two strided copies.  op[1] is the transposed operator
+// of the symmetrised pair 0.5 (K + K^T) of dmrg.jl:241.
+// ---------------------------------------------------------------------------------------------------------------------
+template <class T>
+struct ShardCtxT {
+  ShardOp<T> op[2];
+  int rank = 0, nranks = 1;
+  int64_t max_elems = 0;
+};
+
+template <class T>
+static void shard_ctx_alloc(ShardCtxT<T>& c, int64_t max_elems, int rank, int nranks) {
+  ttn_assert(nranks >= 1 && nranks <= 8 && rank >= 0 && rank < nranks && max_elems >= 1, 2, "shard ctx: bad arguments");
+  c.rank = rank; c.nranks = nranks; c.max_elems = max_elems;
+  for (int t = 0; t < 2; ++t) {
+    ShardOp<T>& op = c.op[t];
+    op.rank = rank; op.nranks = nranks;
+    op.err.alloc(sizeof(int));
+    TTN_CUDA(cudaMemsetAsync(op.err.p, 0, sizeof(int), ctx().stream));
+    for (int i = 0; i < 2; ++i) {
+      TTN_CUDA(cudaMalloc(&op.Ybuf[i], sizeof(T) * (size_t)max_elems));
+      TTN_CUDA(cudaMemsetAsync(op.Ybuf[i], 0, sizeof(T) * (size_t)max_elems, ctx().stream));
+    }
+    TTN_CUDA(cudaMalloc((void**)&op.flags, sizeof(unsigned) * 8));
+    TTN_CUDA(cudaMemsetAsync(op.flags, 0, sizeof(unsigned) * 8, ctx().stream));
+  }
+  TTN_CUDA(cudaStreamSynchronize(ctx().stream));
+}
+
+// Re-binds op to the window (Lc: chi_l x w_l x chi_l, Rc: chi_r x w_r x chi_r, canonical layout; Wf: fused MPO in the
+// reference Amid layout [y, b, e, z]).  transposed: the pieces of K^T.  false when the window cannot be sharded.
+template <class T>
+static bool shard_rebind(ShardOp<T>& op, int64_t max_elems, const T* Lc, int chi_l, int w_l, const T* Rc, int chi_r, int w_r,
+                         const T* Wf, int nn, bool transposed) {
+  if (chi_r < op.nranks || nn * w_r > 32 || (int64_t)chi_l * nn * chi_r > max_elems) return false;
+  op.chi_l = chi_l; op.chi_r = chi_r; op.w_l = w_l; op.w_r = w_r; op.nn = nn;
+  shard_range(chi_r, op.rank, op.nranks, &op.c0, &op.cp);
+  if (!transposed) {
+    op.Lp = Lc;                                   // L2[a,(y,d)] is the canonical layout itself
+  } else {
+    op.L.alloc(sizeof(T) * (size_t)chi_l * w_l * chi_l);
+    Copy4 c;   // Lt[a,y,d] = L[d,y,a]
+    c.n0 = chi_l; c.s0 = (int64_t)chi_l * w_l; c.d0 = 1;
+    c.n1 = w_l; c.s1 = chi_l; c.d1 = chi_l;
+    c.n2 = chi_l; c.s2 = 1; c.d2 = (int64_t)chi_l * w_l;
+    copy4<T>(Lc, op.L.template as<T>(), c);
+    op.Lp = op.L.p;
+  }
+  // Rs[f, z, c_loc] = R[c0 + c_loc, z, f]   (transposed: R[f, z, c0 + c_loc])
+  op.Rs.alloc(sizeof(T) * (size_t)chi_r * w_r * op.cp);
+  {
+    Copy4 c;
+    c.n0 = chi_r; c.d0 = 1;
+    c.n1 = w_r; c.s1 = chi_r; c.d1 = chi_r;
+    c.n2 = op.cp; c.d2 = (int64_t)chi_r * w_r;
+    if (!transposed) { c.s0 = (int64_t)chi_r * w_r; c.s2 = 1; copy4<T>(Rc + op.c0, op.Rs.template as<T>(), c); }
+    else { c.s0 = 1; c.s2 = (int64_t)chi_r * w_r; copy4<T>(Rc + (int64_t)op.c0 * chi_r * w_r, op.Rs.template as<T>(), c); }
+  }
+  // Wq[(e,z),(y,b)] = Amid[y,b,e,z]   (transposed: Amid[y,e,b,z])
+  op.Wq.alloc(sizeof(T) * (size_t)w_l * nn * nn * w_r);
+  {
+    Copy4 c;
+    c.n0 = w_l; c.s0 = 1; c.d0 = (int64_t)nn * w_r;                                   // y
+    c.n1 = nn; c.s1 = transposed ? (int64_t)w_l * nn : w_l; c.d1 = (int64_t)nn * w_r * w_l;   // b
+    c.n2 = nn; c.s2 = transposed ? w_l : (int64_t)w_l * nn; c.d2 = 1;                          // e
+    c.n3 = w_r; c.s3 = (int64_t)w_l * nn * nn; c.d3 = nn;                                     // z
+    copy4<T>(Wf, op.Wq.template as<T>(), c);
+  }
+  op.T1.alloc(sizeof(T) * (size_t)chi_l * nn * w_r * op.cp);
+  op.T2.alloc(sizeof(T) * (size_t)w_l * chi_l * nn * op.cp);
+  return true;
 }
 
 }  // namespace ttn
@@ -331,5 +416,83 @@ void shard_slice(ttn_shard_matvec mv, int* c0, int* cp) {
 }
 
 void shard_free(ttn_shard_matvec mv) { delete mv; }
+
+}  // namespace ttn
+
+struct ttn_shard_ctx_s {
+  int dtype = 0;
+  ttn::ShardCtxT<double> r;
+  ttn::ShardCtxT<ttn::zc> c;
+};
+
+namespace ttn {
+
+ttn_shard_ctx shard_ctx_create(int dtype, int64_t max_elems, int rank, int nranks) {
+  ttn_shard_ctx c = new ttn_shard_ctx_s();
+  c->dtype = dtype;
+  try {
+    if (dtype == TTN_F64) shard_ctx_alloc<double>(c->r, max_elems, rank, nranks);
+    else shard_ctx_alloc<zc>(c->c, max_elems, rank, nranks);
+  } catch (...) { delete c; throw; }
+  return c;
+}
+// 2 x 192 bytes: the IPC handles of the two operators' exchange buffers
+void shard_ctx_handles(ttn_shard_ctx c, void* out384) {
+  ttn_assert(c != nullptr && out384 != nullptr, 2, "null argument");
+  for (int t = 0; t < 2; ++t) {
+    ShardHandles h;
+    void* const* yb = c->dtype == TTN_F64 ? c->r.op[t].Ybuf : c->c.op[t].Ybuf;
+    unsigned* fl = c->dtype == TTN_F64 ? c->r.op[t].flags : c->c.op[t].flags;
+    TTN_CUDA(cudaIpcGetMemHandle(&h.y[0], yb[0]));
+    TTN_CUDA(cudaIpcGetMemHandle(&h.y[1], yb[1]));
+    TTN_CUDA(cudaIpcGetMemHandle(&h.flags, fl));
+    memcpy(reinterpret_cast<char*>(out384) + t * sizeof(ShardHandles), &h, sizeof(h));
+  }
+}
+void shard_ctx_bind(ttn_shard_ctx c, const void* all) {
+  ttn_assert(c != nullptr && all != nullptr, 2, "null argument");
+  const ShardHandles* hs = reinterpret_cast<const ShardHandles*>(all);
+  for (int t = 0; t < 2; ++t) {
+    if (c->dtype == TTN_F64) shard_bind<double>(c->r.op[t], hs + t, 2);
+    else shard_bind<zc>(c->c.op[t], hs + t, 2);
+  }
+}
+void shard_ctx_free(ttn_shard_ctx c) { delete c; }
+int shard_ctx_error(ttn_shard_ctx c) {
+  int e = 0, tot = 0;
+  for (int t = 0; t < 2; ++t) {
+    void* p = c->dtype == TTN_F64 ? c->r.op[t].err.p : c->c.op[t].err.p;
+    TTN_CUDA(cudaMemcpyAsync(&e, p, sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
+    TTN_CUDA(cudaStreamSynchronize(ctx().stream));
+    tot |= e;
+  }
+  return tot;
+}
+
+// installs the sharded matvec on `lop` for the current window; false: the window is not sharded (too small), lop unchanged
+template <class T>
+bool shard_install(ttn_shard_ctx c, LocalOp<T>& lop, const T* Lc, const T* Rc, const T* Wf) {
+  if (c == nullptr) return false;
+  ShardCtxT<T>* sc = nullptr;
+  if (std::is_same<T, double>::value) { if (c->dtype != TTN_F64) return false; sc = reinterpret_cast<ShardCtxT<T>*>(&c->r); }
+  else { if (c->dtype != TTN_C128) return false; sc = reinterpret_cast<ShardCtxT<T>*>(&c->c); }
+  if (sc->nranks <= 1 || !sc->op[0].bound || lop.zero_site) return false;
+  if (!shard_rebind<T>(sc->op[0], sc->max_elems, Lc, lop.chi_l, lop.w_l, Rc, lop.chi_r, lop.w_r, Wf, lop.nn, false)) return false;
+  const bool sym = lop.symmetrize;
+  if (sym && !shard_rebind<T>(sc->op[1], sc->max_elems, Lc, lop.chi_l, lop.w_l, Rc, lop.chi_r, lop.w_r, Wf, lop.nn, true)) return false;
+  const int64_t nel = lop.size();
+  lop.ext_apply = [sc, sym, nel](const T* V, T* Y) {
+    const T* Y1 = shard_apply<T>(sc->op[0], V);
+    TTN_CUDA(cudaMemcpyAsync(Y, Y1, sizeof(T) * (size_t)nel, cudaMemcpyDeviceToDevice, ctx().stream));
+    if (sym) {
+      const T* Y2 = shard_apply<T>(sc->op[1], V);
+      axpy<T>(nel, t_one<T>(), Y2, Y);
+      scal<T>(nel, t_from<T>(0.5, 0.0), Y);
+    }
+  };
+  return true;
+}
+template bool shard_install<double>(ttn_shard_ctx, LocalOp<double>&, const double*, const double*, const double*);
+template bool shard_install<zc>(ttn_shard_ctx, LocalOp<zc>&, const zc*, const zc*, const zc*);
 
 }  // namespace ttn

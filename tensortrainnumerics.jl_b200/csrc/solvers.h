@@ -113,7 +113,16 @@ struct ttn_matvec_s {
   ttn::DevBuf L, R;
 };
 typedef struct ttn_shard_matvec_s* ttn_shard_matvec;
+typedef struct ttn_shard_ctx_s* ttn_shard_ctx;
 namespace ttn {
+// sharded matvec inside a sweep (shard.cu): persistent exchange buffers + per-window re-binding
+ttn_shard_ctx shard_ctx_create(int dtype, int64_t max_elems, int rank, int nranks);
+void shard_ctx_handles(ttn_shard_ctx c, void* out384);
+void shard_ctx_bind(ttn_shard_ctx c, const void* all);
+void shard_ctx_free(ttn_shard_ctx c);
+int shard_ctx_error(ttn_shard_ctx c);
+template <class T> bool shard_install(ttn_shard_ctx c, LocalOp<T>& lop, const T* Lc, const T* Rc, const T* Wf);
+ttn_shard_ctx& active_shard_ctx();   // per host thread; set by ttn_dmrg_eigsolve_sharded around the sweep
 // sharded effective operator (shard.cu)
 void shard_range(int chi, int rank, int nranks, int* c0, int* cp);
 ttn_shard_matvec shard_create(int dtype, int w_l, int w_r, int chi_l, int chi_r, int nn, const void* G, const void* Amid,

@@ -623,6 +623,11 @@ void mals_eigsolve(const TTO<T>& A, const TT<T>& x0, const ttn_solver_params& p,
   }
 }
 
+ttn_shard_ctx& active_shard_ctx() {
+  static thread_local ttn_shard_ctx c = nullptr;
+  return c;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // DMRG (src/solvers/dmrg.jl:385-473, :501-578), N in {1, 2}
 // ---------------------------------------------------------------------------------------------------------
@@ -635,6 +640,9 @@ struct DmrgLocal {
   double solve(Sweeper<T>& S, int k, int N, DevBuf& V) {
     LocalOp<T> op; DevBuf W;
     S.setup_op(op, W, k, N, p.symmetrize != 0);
+    // multi-GPU: the matvec of this window sharded over the ranks (shard.cu); windows too small to shard stay local
+    if (!lin && active_shard_ctx() != nullptr)
+      shard_install<T>(active_shard_ctx(), op, S.L[k].template as<T>(), S.R[k + N].template as<T>(), W.as<T>());
     const int kd = std::max(p.krylovdim, 2), maxit = std::max(p.linsolv_maxiter, 1);
     if (lin) {
       DevBuf Pb;

@@ -52,7 +52,7 @@ def test_product_does_not_import_oracle():
 
 def _c_kind(decl):
     """scalar class of one C parameter declaration of the header"""
-    if "*" in decl or re.match(r"\s*(const\s+)?ttn_(ttv|tto|matvec|shard_matvec)\b", decl):
+    if "*" in decl or re.match(r"\s*(const\s+)?ttn_(ttv|tto|matvec|shard_matvec|shard_ctx)\b", decl):
         return "ptr"
     words = re.findall(r"[A-Za-z_][A-Za-z0-9_]*", decl)
     for w, k in (("int64_t", "i64"), ("size_t", "size"), ("double", "f64"), ("int", "i32")):
