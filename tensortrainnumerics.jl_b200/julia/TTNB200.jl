@@ -135,6 +135,26 @@ function tt_compress!(ψ::TTvector, max_bond::Int; truncerr::Real = 0.0, sweeps:
     return ψ
 end
 
+# `tt_compress!(A * x, max_bond; ...)` as ONE device call: the product cores of `A * x` are consumed by the first rounding pass
+# without ever being written to memory (ttn_apply_compress; csrc/tt.cu).  A maintainer who wants the fusion behind the
+# reference's own syntax makes `A * x` return a lazy `TTProduct(A, x)` and adds the method `tt_compress!(p::TTProduct, max_bond; ...)`
+# that calls this function (every other consumer of a TTProduct materialises it with `apply`).
+function apply_compress(A::TToperator{T}, x::TTvector{T}, max_bond::Int; truncerr::Real = 0.0, sweeps::Int = 1) where {T}
+    Ad, xd = upload(A), upload(x)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ttn_apply_compress, LIB[]), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Float64, Cint, Ptr{Float64}, Int64, Ptr{Ptr{Cvoid}}),
+                Ad.h, xd.h, max_bond, truncerr, sweeps, C_NULL, 0, out))
+    return download(DevTT(out[]))
+end
+
+# run-time switches of the library ("gram_compress", "gemm_bulk", "gram_jacobi_min", "use_cholqr", "use_cluster_jacobi")
+set_option!(key::AbstractString, value::Real) = check(ccall((:ttn_set_option, LIB[]), Cint, (Cstring, Float64), key, value))
+function get_option(key::AbstractString)
+    v = Ref{Float64}(0.0)
+    check(ccall((:ttn_get_option, LIB[]), Cint, (Cstring, Ptr{Float64}), key, v))
+    return v[]
+end
+
 # ---- site surgery (the other two-site-SVD users) -----------------------------------------------------------------------
 const NO_CAP = Int64(1) << 62
 

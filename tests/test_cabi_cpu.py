@@ -114,7 +114,7 @@ def test_julia_shim_ccall_arities_match_header():
         jt = [x.strip() for x in types.split(",") if x.strip()]
         assert len(jt) == decls[name], (name, len(jt), decls[name])
         for pos, (carg, jtype) in enumerate(zip(cargs[name], jt)):
-            kind = "ptr" if jtype.startswith(("Ptr{", "Ref{")) else {"Cint": "i32", "Int64": "i64", "Float64": "f64",
+            kind = "ptr" if jtype.startswith(("Ptr{", "Ref{")) or jtype == "Cstring" else {"Cint": "i32", "Int64": "i64", "Float64": "f64",
                                                                       "Cdouble": "f64", "Csize_t": "size"}[jtype]
             assert _c_kind(carg) == kind, (name, pos, carg, jtype)
         seen.add(name)
