@@ -636,34 +636,35 @@ __global__ void __launch_bounds__(1024) heig_vec_kernel(const double* __restrict
       }
     }
     __syncthreads();
-    // (2) pivots, gamma, chain factors: thread (vector c, segment sg) owns rows [i0, i1)
+    // (2) pivots, gamma, chain factors: thread (vector c, segment sg) owns rows [i0, i1).  In place: a thread overwrites row i
+    // only after it has read rows i and i+1; the one row it reads from its neighbour's segment (i1) is taken before the
+    // barrier.  Two reciprocals per row (1/phi_{i+1}, 1/psi_{i+1}, each reused by the next row) instead of four divisions.
     {
       const int c = tid % C, sg = tid / C;
       const bool act = sg < NSEG && c < nc;
       const int i0 = sg * seglen, i1 = min(n, i0 + seglen);
-      double fl[24], fr[24];           // seglen <= 22 (n <= 176)
+      double ph_end = 1.0, ps_end = 1.0;
+      if (act && i0 < i1) { ph_end = PH[(size_t)i1 * pitch + c]; ps_end = PS[(size_t)i1 * pitch + c]; }
+      __syncthreads();
       double gbest = 1e300;
       int rbest = 0;
-      if (act) {
+      if (act && i0 < i1) {
         const double lam = lam_s[c0 + c];
         double ph = PH[(size_t)i0 * pitch + c], ps = PS[(size_t)i0 * pitch + c];
-#pragma unroll 4
+        double rph = 1.0 / ph, rps = 1.0 / ps;
         for (int i = i0; i < i1; ++i) {
-          const double ph1 = PH[(size_t)(i + 1) * pitch + c], ps1 = PS[(size_t)(i + 1) * pitch + c];
-          const double si = ph1 / ph, pi = ps / ps1;                 // s_i, p_i
-          const double gam = fabs(si + pi - (ds[i] - lam));
+          const bool last = i + 1 == i1;
+          const double ph1 = last ? ph_end : PH[(size_t)(i + 1) * pitch + c];
+          const double ps1 = last ? ps_end : PS[(size_t)(i + 1) * pitch + c];
+          const double rph1 = 1.0 / ph1, rps1 = 1.0 / ps1;
+          const double gam = fabs(ph1 * rph + ps * rps1 - (ds[i] - lam));      // s_i + p_i - (d_i - lambda)
           if (gam < gbest) { gbest = gam; rbest = i; }
-          fl[i - i0] = -es[i] * (ph / ph1);                           // z_i = fl_i z_{i+1}
-          fr[i - i0] = i > 0 ? -es[i - 1] * (ps1 / ps) : 0.0;         // z_i = fr_i z_{i-1}   ( -(e_{i-1} / p_i) )
-          ph = ph1; ps = ps1;
+          PH[(size_t)i * pitch + c] = -es[i] * (ph * rph1);                    // z_i = fl_i z_{i+1}:  -(e_i / s_i)
+          PS[(size_t)i * pitch + c] = i > 0 ? -es[i - 1] * (ps1 * rps) : 0.0;  // z_i = fr_i z_{i-1}:  -(e_{i-1} / p_i)
+          ph = ph1; ps = ps1; rph = rph1; rps = rps1;
         }
       }
-      __syncthreads();
       if (act) {
-        for (int i = i0; i < i1; ++i) {
-          PH[(size_t)i * pitch + c] = fl[i - i0];
-          PS[(size_t)i * pitch + c] = fr[i - i0];
-        }
         gm[sg * C + c] = gbest;
         gr[sg * C + c] = rbest;
       }
@@ -701,14 +702,17 @@ __global__ void __launch_bounds__(1024) heig_vec_kernel(const double* __restrict
       zn[dir * C + c] = nrm2;
     }
     __syncthreads();
-    // (4) normalise and store (coalesced along i)
+    // (4) normalise and store (coalesced along i); one rsqrt per vector
+    if (tid < nc) {
+      const double nrm2 = zn[tid] + zn[C + tid];
+      const double inv = rsqrt(nrm2);
+      zn[tid] = inv;
+      if (!(gm[tid] * inv <= 1e-9) || !isfinite(nrm2)) atomicOr(&s_flag, 4);
+    }
+    __syncthreads();
     for (int idx = tid; idx < nc * n; idx += blockDim.x) {
       const int c = idx / n, i = idx - c * n;
-      const double nrm2 = zn[c] + zn[C + c];
-      const double inv = rsqrt(nrm2);
-      const double v = (i <= rtw[c] ? PH[(size_t)i * pitch + c] : PS[(size_t)i * pitch + c]) * inv;
-      Z[(int64_t)(c0 + c) * n + i] = v;
-      if (i == 0 && (!(gm[c] * inv <= 1e-9) || !isfinite(nrm2))) atomicOr(&s_flag, 4);
+      Z[(int64_t)(c0 + c) * n + i] = (i <= rtw[c] ? PH[(size_t)i * pitch + c] : PS[(size_t)i * pitch + c]) * zn[c];
     }
     __syncthreads();
   }

@@ -301,3 +301,31 @@ def test_als_gen_eigsolv_complex_follows_reference_transpose():
     E, x = t.als_gen_eigsolv(A, S, x0, sweep_schedule=[3], rmax_schedule=[2])
     Eo, xo = o.als_gen_eigsolv(A, S, x0, sweep_schedule=[3], rmax_schedule=[2])
     assert len(E) == len(Eo) and np.max(np.abs(E - Eo)) < 1e-9
+
+
+def test_mals_linsolve_matrix_free_gmres_saturated_ranks_vs_oracle():
+    """`mals_linsolve` (mals.jl:240-309) in the regime where the dense local matrix of mals.jl:148-169 is replaced by the
+    matrix-free GMRES solve (windows above 2048 unknowns: n^2 r_l r_r = 4 * 32 * 32 = 4096): d = 12, a right-hand side of rank 40
+    and a start of rank 32 so that the two-site solves hit the cap rmax = 32 at the centre bonds.  The operator is a well
+    conditioned SPD operator (Laplace + 3 I), so the comparison with the oracle (dense local solves, the reference algorithm)
+    and with the dense solution is meaningful at 1e-8; for the Laplace operator of cfg3 itself (kappa ~ 1e12) parity is stated on
+    residuals (test_cfg3_laplace2d_interleaved_mals_linsolve)."""
+    import ttn_b200 as t
+    d = 12
+    rng = np.random.default_rng(91)
+    A = spd_op(d, 3.0)
+    b = o.rand_tt((2,) * d, 40, rng=rng, normalise=True)
+    x0 = o.rand_tt((2,) * d, 32, rng=rng, normalise=True)
+    t.reset_launch_count()
+    x, info = t.mals_linsolve(A, b, x0, tol=1e-13, rmax=32, return_info=True, linsolv_maxiter=40, krylovdim=40)
+    assert max(x.ttv_rks) == 32                                     # the cap is reached
+    xo = o.mals_linsolve(A, b, x0, tol=1e-13, rmax=32)
+    assert x.ttv_rks == xo.ttv_rks
+    assert relerr(dv(x), dv(xo)) < 1e-8
+    Ad = o.tto_to_matrix(A)
+    res = np.linalg.norm(Ad @ dv(x) - dv(b)) / np.linalg.norm(dv(b))
+    res_o = np.linalg.norm(Ad @ dv(xo) - dv(b)) / np.linalg.norm(dv(b))
+    assert abs(res - res_o) < 1e-8 and abs(info["residual"] - res) < 1e-6
+    # energy-norm distance to the oracle's result
+    e = dv(x) - dv(xo)
+    assert np.sqrt(e @ (Ad @ e)) < 1e-8 * np.sqrt(dv(xo) @ (Ad @ dv(xo)))
