@@ -1009,7 +1009,7 @@ bool heig_top(const T* G, int n, int64_t ldg, int64_t bG, int nsplit, int64_t sG
       }                                                                                                           \
       kern<<<grid, nt, smem, ctx().stream>>>(V.as<T>(), bV, tau.as<T>(), Z.as<double>(), n, nev, U, n, (int64_t)n * nev); \
     }
-#define TTN_BACK(NR) { if (cpg == 1) TTN_BACK2(NR, 1) else TTN_BACK2(NR, 2) }
+#define TTN_BACK(NR) TTN_BACK2(NR, 1)
     if (nr <= 4) TTN_BACK(4)
     else if (nr <= 8) TTN_BACK(8)
     else if (nr <= 16) TTN_BACK(16)
