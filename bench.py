@@ -497,6 +497,13 @@ def run_ours(args, rank, local_rank, world):
             import cfg3_bench
             extras["mals_cfg3"] = cfg3_bench.run(bits=20, rmax=128)
             compact["mals_cfg3_s"] = extras["mals_cfg3"].get("value")
+            # cfg3 with ranks at the cap: implicit-Euler heat operator, known rank-128 solution (full size), and the same problem at
+            # 2 x 10 bits / rmax 32 where the reference's dense-K algorithm is feasible on the CPU (timed below)
+            extras["mals_cfg3_heat"] = cfg3_bench.run_heat(bits=20, rmax=128)
+            extras["mals_cfg3_heat_small"] = cfg3_bench.run_heat(bits=10, rmax=32, start_rank=16)
+            compact["mals_cfg3_heat_s"] = extras["mals_cfg3_heat"]["value"]
+            compact["mals_cfg3_heat_max_rank"] = extras["mals_cfg3_heat"]["calls"][0]["max_rank"]
+            compact["mals_cfg3_heat_err"] = extras["mals_cfg3_heat"]["calls"][-1]["relative_error"]
     if dist is not None:
         dist.barrier()
 
@@ -520,6 +527,11 @@ def run_ours(args, rank, local_rank, world):
             if "dmrg_sweep" in extras:
                 extras["dmrg_sweep"]["cpu_baseline"] = cpu_dmrg(o, args.dmrg_chi)
                 extras["matvec_cfg4"]["cpu_baseline"] = extras["dmrg_sweep"]["cpu_baseline"].get("matvec")
+            if "mals_cfg3_heat_small" in extras:
+                cb = cpu_cfg3_heat(o, cfg3_bench, 10, 32, 16)
+                cb["gpu_first_call_speedup"] = cb["value"] / extras["mals_cfg3_heat_small"]["value"]
+                extras["mals_cfg3_heat_small"]["cpu_baseline"] = cb
+                compact["mals_cfg3_heat_small_cpu_over_gpu"] = cb["gpu_first_call_speedup"]
         line = {"metric": "tt_rounding sweeps/s", "value": value, "unit": "sweeps/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "c128",
                 "data": "synthetic", "config": dict(cfg5_config(world, chunk), out_max_rank=int(max(out_rks)),
@@ -677,6 +689,24 @@ def cpu_dmrg(o, chi, w=5, nn=4):
                        "sample": "one full-size application (chi=1024) through three BLAS GEMMs"},
             "sample": "three bulk bond steps measured at full size (8 symmetrised Lanczos matvecs + gesdd 2048^2), mean x the ~105 "
                       "full-rank bond steps of the L=64 sweep (environment updates not counted); NumPy restatement, not Julia"}
+
+
+def cpu_cfg3_heat(o, cfg3_bench, bits, rmax, start_rank, tol=1e-10):
+    """CPU leg of the cfg3 (implicit-Euler heat step) extra: one `mals_linsolve` call of the restated algorithm (dense local K,
+    mals.jl:148-169, NumPy/LAPACK) on the inputs tools/cfg3_bench.heat_problem builds for the GPU leg at the same (bits, rmax)."""
+    A, _, xt, x0 = cfg3_bench.heat_problem(bits, rmax, start_rank)
+    d = 2 * bits
+    oA = o.TToperator(d, [np.array(c) for c in A.tto_vec], tuple(A.tto_dims), list(A.tto_rks))
+    mk = lambda v: o.TTvector(d, [np.array(c) for c in v.ttv_vec], tuple(v.ttv_dims), list(v.ttv_rks), [0] * d)  # noqa: E731
+    oxt, ox = mk(xt), mk(x0)
+    ob = o.apply(oA, oxt)
+    t0 = time.perf_counter()
+    ox = o.mals_linsolve(oA, ob, ox, tol=tol, rmax=rmax)
+    el = time.perf_counter() - t0
+    r = o.add(o.apply(oA, ox), o.scale(-1.0, ob))
+    return {"value": el, "unit": "s per call", "kind": "port", "cores": host_threads(), "bits": bits, "rmax": rmax,
+            "relative_residual": float(o.norm(r) / o.norm(ob)), "max_rank": int(max(ox.ttv_rks)),
+            "sample": "one call on the same inputs as the GPU leg of the same (bits, rmax); dense local K through NumPy/LAPACK, not Julia"}
 
 
 def main():

@@ -138,6 +138,73 @@ def run(bits=20, rmax=128, tol=1e-12, maxiter=200, krylovdim=30, x0rank=8, profi
                     "(mals.jl:240-309); the residual is that of the reference algorithm after one call, not of a converged solve"}
 
 
+def heat_operator(bits, dt_scale=100.0):
+    """I + dt * L with L the interleaved 2-D Laplace operator above and dt = dt_scale / ||L||: the operator of one implicit Euler
+    step of the heat equation on the 2^bits x 2^bits grid (what `implicit_euler_method`, src/solvers/euler.jl:99-135, hands to
+    `mals_linsolve`); condition number ~ dt_scale, so the matrix-free local solves converge and the residual is meaningful"""
+    lap = toeplitz_cores(2.0, -1.0, -1.0, bits)
+    lcores = add_ops(interleave(lap, True), interleave(lap, False))
+    h = 1.0 / (2 ** bits - 1)
+    dt = dt_scale / (8.0 / h ** 2)
+    lcores[0] = lcores[0] * (dt / h ** 2)
+    d = 2 * bits
+    ident = [np.eye(2).reshape(2, 2, 1, 1).copy() for _ in range(d)]
+    cores = add_ops(ident, lcores)
+    return t.TToperator(d, [np.asfortranarray(c) for c in cores], (2,) * d, [1] + [c.shape[3] for c in cores]), dt
+
+
+def heat_problem(bits, rmax, start_rank, dt_scale=100.0):
+    """operator, a known solution of rank `rmax`, and a random start of rank `start_rank` (host objects of the package's mirror types)"""
+    d = 2 * bits
+    A, dt = heat_operator(bits, dt_scale)
+    rng = np.random.default_rng(5)
+
+    def rand_tt(rank):
+        rks = [min(2 ** k, 2 ** (d - k), rank) for k in range(d + 1)]
+        return t.TTvector(d, [np.asfortranarray(rng.standard_normal((2, rks[k], rks[k + 1])) / np.sqrt(2 * rks[k + 1])) for k in range(d)],
+                          (2,) * d, rks)
+
+    return A, dt, rand_tt(rmax), rand_tt(start_rank)
+
+
+def run_heat(bits=20, rmax=128, tol=1e-10, maxiter=20, krylovdim=40, start_rank=64, dt_scale=100.0, calls=3):
+    """cfg3 at its stated size with ranks that actually reach the cap: `mals_linsolve(I + dt L, b, x0; tol, rmax)` on the interleaved
+    2 x `bits`-bit grid with b = (I + dt L) x_true, x_true a random train of rank `rmax`, x0 a random train of rank `start_rank`;
+    the call is repeated on its own result (each call = one forward + one backward two-site sweep, mals.jl:240-309) and the error
+    against x_true is reported per call.  Windows of n^2 r^2 = 65 536 unknowns are solved matrix-free (GMRES on the three-GEMM
+    matvec); the dense local matrix of mals.jl:148-169 would be 34 GB.  bench.py times the NumPy port of the
+    reference algorithm (dense local K, so only at small `rmax`) on the inputs `heat_problem` returns."""
+    d = 2 * bits
+    A, dt, xt, x0 = heat_problem(bits, rmax, start_rank, dt_scale)
+    Ad, xtd, xd = t.DeviceTTO.upload(A), t.DeviceTT.upload(xt), t.DeviceTT.upload(x0)
+    bd = t.apply(Ad, xtd)
+    nb, nxt = t.norm(bd), t.norm(xtd)
+    t.synchronize()
+    per_call = []
+    for c in range(calls):
+        t.reset_launch_count()
+        t.set_option("reset_flops", 1)
+        t.synchronize()
+        t0 = time.perf_counter()
+        xd = t.mals_linsolve(Ad, bd, xd, tol=tol, rmax=rmax, linsolv_maxiter=maxiter, krylovdim=krylovdim)
+        t.synchronize()
+        el = time.perf_counter() - t0
+        gflop = t.get_option("gemm_flops") / 1e9
+        res = t.norm(t.sub(t.apply(Ad, xd), bd)) / nb
+        err = t.norm(t.sub(xd, xtd)) / nxt
+        per_call.append({"s": el, "relative_residual": float(res), "relative_error": float(err), "max_rank": int(max(xd.ttv_rks)),
+                         "ranks_at_cap": int(sum(1 for v in xd.ttv_rks if v == rmax)), "gpu_launches": int(t.launch_count()),
+                         "gemm_gflop": gflop, "gemm_tflops": gflop / 1e3 / el})
+        if res < 10 * tol:
+            break
+    out = {"metric": "cfg3 (implicit-Euler heat step) mals_linsolve s per call", "value": per_call[0]["s"], "unit": "s", "bits": bits, "d": d,
+           "rmax": rmax, "tol": tol, "dt": dt, "condition_number_about": dt_scale, "mpo_rank": int(max(A.tto_rks)),
+           "rhs_rank": int(max(bd.ttv_rks)), "start_rank": start_rank, "calls": per_call,
+           "note": "b = (I + dt L) x_true with a random rank-rmax x_true; every call is one forward + one backward two-site sweep; local "
+                   "systems of up to n^2 rmax^2 unknowns solved matrix-free by GMRES"}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--bits", type=int, default=20)
@@ -146,7 +213,12 @@ def main():
     ap.add_argument("--maxiter", type=int, default=200)
     ap.add_argument("--krylovdim", type=int, default=30)
     ap.add_argument("--x0rank", type=int, default=8)
+    ap.add_argument("--heat", action="store_true", help="the well-conditioned implicit-Euler variant whose ranks reach the cap")
+    ap.add_argument("--start-rank", type=int, default=64)
     args = ap.parse_args()
+    if args.heat:
+        print(json.dumps(run_heat(args.bits, args.rmax, start_rank=args.start_rank)), flush=True)
+        return
     print(json.dumps(run(args.bits, args.rmax, args.tol, args.maxiter, args.krylovdim, args.x0rank, profile=True)), flush=True)
 
 
