@@ -295,20 +295,33 @@ class ChunkWorker(threading.Thread):
         return out
 
     def _e2e(self, t, nsteps):
-        """software pipeline over this worker's chunks on pinned host memory: H2D of chunk i+1 and D2H of chunk i-1 run on the
-        copy stream while chunk i computes"""
+        """software pipeline over this worker's chunks on pinned host memory, running across the step boundaries: H2D of the next
+        chunk and D2H of the previous one run on the copy stream while the current chunk computes; every step moves all of its
+        inputs host -> device and all of its results device -> host, and the timed region ends when the last result has landed"""
         hc = self.host_chunks
-        for _ in range(nsteps):
-            if not hc:
-                continue
-            nxt = t.DeviceTT.upload_batched(hc[0], (2,) * D5, self.rks, asynchronous=True)
-            for i, c in enumerate(hc):
+        seq = [c for _ in range(nsteps) for c in hc]
+        if seq:
+            mode = os.environ.get("TTN_BENCH_E2E_MODE", "full")      # diagnosis only: "nodown" drops the result copies
+            trace = os.environ.get("TTN_BENCH_E2E_TRACE") == "1"
+            acc = {"up": 0.0, "compute": 0.0, "down": 0.0, "free": 0.0}
+            up = lambda c: t.DeviceTT.upload_batched(c, (2,) * D5, self.rks, asynchronous=True)  # noqa: E731
+            nxt = up(seq[0])
+            for j, c in enumerate(seq):
                 xd = nxt
-                if i + 1 < len(hc):
-                    nxt = t.DeviceTT.upload_batched(hc[i + 1], (2,) * D5, self.rks, asynchronous=True)
+                t0 = time.perf_counter()
+                if j + 1 < len(seq):
+                    nxt = up(seq[j + 1])
+                t1 = time.perf_counter()
                 y = t.apply_compress(self.Ad, xd, MAXB5)
-                y.download_into(self.res_bufs[c[0].shape[3]][i & 1], asynchronous=True)
+                t2 = time.perf_counter()
+                if mode != "nodown":
+                    y.download_into(self.res_bufs[c[0].shape[3]][j & 1], asynchronous=True)
+                t3 = time.perf_counter()
                 xd.free(); y.free()
+                t4 = time.perf_counter()
+                acc["up"] += t1 - t0; acc["compute"] += t2 - t1; acc["down"] += t3 - t2; acc["free"] += t4 - t3
+            if trace:
+                print(f"[e2e trace] worker {self.idx}: chunks {len(seq)} host seconds {acc}", file=sys.stderr, flush=True)
             t.copy_synchronize()
         t.synchronize()
         return {"h2d": int(sum(a.nbytes for c in hc for a in c)),
@@ -538,7 +551,7 @@ def run_ours(args, rank, local_rank, world):
                                                     gram_path_fallbacks_in_timed_region=fallbacks, host_threads_per_rank=nw),
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": TOTAL5 / e2e_s, "unit": "sweeps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+                        "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "mode": os.environ.get("TTN_BENCH_E2E_MODE", "full"),
                         "api": "per chunk: DeviceTT.upload_batched(pinned, asynchronous) -> ttn_b200.apply_compress(A, x, 64) -> "
                                "download_into(pinned, asynchronous); copies on the copy streams overlap the neighbouring chunks' compute; "
                                f"{nw} host thread(s) = library contexts per rank"},

@@ -38,8 +38,9 @@ int ttn_init(int device) {
   TTN_CUDA(cudaSetDevice(device));
   Context& c = ctx();
   if (!c.inited || c.device != device) {
-    if (c.inited && c.stream) { devbuf_cache_trim(); cudaStreamSynchronize(c.stream); cudaStreamDestroy(c.stream); }
+    if (c.inited && c.stream) { drain_deferred_releases(true); devbuf_cache_trim(); cudaStreamSynchronize(c.stream); cudaStreamDestroy(c.stream); }
     if (c.copy_stream) { cudaStreamSynchronize(c.copy_stream); cudaStreamDestroy(c.copy_stream); c.copy_stream = nullptr; }
+    if (c.host_stage) { cudaFreeHost(c.host_stage); c.host_stage = nullptr; c.host_stage_bytes = 0; }
     c.device = device;
     TTN_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     cudaDeviceProp prop;
@@ -63,11 +64,13 @@ int ttn_shutdown(void) {
   API_BEGIN
   Context& c = ctx();
   if (c.inited) {
+    drain_deferred_releases(true);
     devbuf_cache_trim();
     cudaStreamSynchronize(c.stream);
     cudaStreamDestroy(c.stream);
     c.stream = nullptr;
     if (c.copy_stream) { cudaStreamSynchronize(c.copy_stream); cudaStreamDestroy(c.copy_stream); c.copy_stream = nullptr; }
+    if (c.host_stage) { cudaFreeHost(c.host_stage); c.host_stage = nullptr; c.host_stage_bytes = 0; }
     c.inited = false;
   }
   API_END
@@ -189,6 +192,54 @@ static cudaStream_t copy_stream() {
   return c.copy_stream;
 }
 // the compute stream waits for a pending asynchronous upload of x (no host synchronisation)
+namespace {
+struct DeferredRelease {
+  cudaEvent_t ev;
+  std::vector<ttn::DevBuf> bufs;
+};
+struct DeferredList {
+  std::vector<DeferredRelease> v;
+  ~DeferredList() {                                   // thread exit: the context may already be gone, just wait and let go
+    for (auto& d : v) { cudaEventSynchronize(d.ev); cudaEventDestroy(d.ev); }
+  }
+};
+DeferredList& deferred() {
+  static thread_local DeferredList l;
+  return l;
+}
+}  // namespace
+void ttn::drain_deferred_releases(bool block) {
+  auto& v = deferred().v;
+  size_t keep = 0;
+  for (size_t i = 0; i < v.size(); ++i) {
+    bool done = block ? (cudaEventSynchronize(v[i].ev), true) : cudaEventQuery(v[i].ev) == cudaSuccess;
+    if (done) {
+      cudaEventDestroy(v[i].ev);
+      v[i].bufs.clear();                              // DevBuf destructors: back to the block cache of this thread
+    } else {
+      if (keep != i) v[keep] = std::move(v[i]);
+      ++keep;
+    }
+  }
+  if (!block) cudaGetLastError();                     // cudaErrorNotReady of the queries is not an error
+  v.resize(keep);
+}
+ttn_ttv_s::~ttn_ttv_s() {
+  if (ready) { cudaStreamWaitEvent(ttn::ctx().stream, ready, 0); cudaEventDestroy(ready); }
+  if (busy) {
+    if (cudaEventQuery(busy) == cudaSuccess) {
+      cudaEventDestroy(busy);
+    } else {
+      cudaGetLastError();
+      DeferredRelease d;
+      d.ev = busy;
+      d.bufs = std::move(dtype == TTN_F64 ? r.cores : c.cores);
+      deferred().v.push_back(std::move(d));
+    }
+  }
+  ttn::drain_deferred_releases(false);
+}
+
 static void await_ready(ttn_ttv x) {
   if (x && x->ready) {
     TTN_CUDA(cudaStreamWaitEvent(ctx().stream, x->ready, 0));
@@ -204,6 +255,7 @@ int ttn_ttv_upload_async(int dtype, int d, const int64_t* dims, const int64_t* r
   need_init();
   ttn_assert(d >= 1 && batch >= 1 && out, TTN_EARG, "upload: bad arguments");
   ttn_assert(dtype == TTN_F64 || dtype == TTN_C128, TTN_EARG, "upload: bad dtype");
+  drain_deferred_releases(false);
   ttn_ttv h = new ttn_ttv_s();
   h->dtype = dtype;
   try {
@@ -264,6 +316,7 @@ int ttn_copy_synchronize(void) {
   API_BEGIN
   need_init();
   if (ctx().copy_stream) TTN_CUDA(cudaStreamSynchronize(ctx().copy_stream));
+  drain_deferred_releases(true);
   API_END
 }
 

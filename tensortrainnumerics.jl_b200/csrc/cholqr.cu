@@ -362,8 +362,7 @@ bool cholqr2_impl(const T* A, int m, int k, int64_t lda, int64_t bA, T* R, T* Q,
     ctx().launches++;
   }
   std::vector<double> h(2 * (size_t)batch);
-  TTN_CUDA(cudaMemcpyAsync(h.data(), st.p, sizeof(double) * 2 * batch, cudaMemcpyDeviceToHost, ctx().stream));
-  TTN_CUDA(cudaStreamSynchronize(ctx().stream));
+  read_back(h.data(), st.p, sizeof(double) * 2 * batch);
   double worst = 1.0;
   for (int b = 0; b < batch; ++b) {
     const double v = h[2 * b];
@@ -419,8 +418,7 @@ bool cholqr2_impl(const T* A, int m, int k, int64_t lda, int64_t bA, T* R, T* Q,
   }
   // min/max diag(R1) only bounds cond(A) from below.  The second Gram matrix is the direct evidence: Q1^H Q1 = I + O(eps cond^2),
   // so diag(R2) must sit at 1; a spread means the first pass lost orthogonality (cond(A) >~ 1e7) and the result is rejected.
-  TTN_CUDA(cudaMemcpyAsync(h.data(), st.p, sizeof(double) * 2 * batch, cudaMemcpyDeviceToHost, ctx().stream));
-  TTN_CUDA(cudaStreamSynchronize(ctx().stream));
+  read_back(h.data(), st.p, sizeof(double) * 2 * batch);
   for (int b = 0; b < batch; ++b) {
     const double v = h[2 * b];
     if (!(v >= 0.9)) {

@@ -5,6 +5,7 @@
 // drivers (dmrg.jl:170,245; tdvp.jl:75).  All of them are coalesced along the fastest index and sized
 // as a multiple of the SM count with a grid-stride loop.
 #include "ttn_internal.h"
+#include <cstring>
 
 namespace ttn {
 
@@ -59,6 +60,32 @@ BlockCache& cache() {
 }  // namespace
 
 void devbuf_cache_trim() { cache().trim(); }
+
+void read_back(void* dst, const void* src, size_t bytes) {
+  if (bytes == 0) return;
+  if (bytes > ((size_t)1 << 20)) {                   // bulk results: straight into the caller's memory
+    TTN_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx().stream));
+    TTN_CUDA(cudaStreamSynchronize(ctx().stream));
+    return;
+  }
+  void* st = host_stage(bytes);
+  TTN_CUDA(cudaMemcpyAsync(st, src, bytes, cudaMemcpyDeviceToHost, ctx().stream));
+  TTN_CUDA(cudaStreamSynchronize(ctx().stream));
+  memcpy(dst, st, bytes);
+}
+
+void* host_stage(size_t bytes) {
+  Context& c = ctx();
+  if (bytes > c.host_stage_bytes) {
+    if (c.host_stage) cudaFreeHost(c.host_stage);
+    c.host_stage = nullptr;
+    c.host_stage_bytes = 0;
+    size_t want = bytes < (size_t)(1 << 16) ? (size_t)(1 << 16) : bytes * 2;
+    TTN_CUDA(cudaHostAlloc(&c.host_stage, want, cudaHostAllocPortable));
+    c.host_stage_bytes = want;
+  }
+  return c.host_stage;
+}
 
 void DevBuf::alloc(size_t b) {
   release();
@@ -316,8 +343,7 @@ void multi_dot(int64_t n, int nv, const T* X, int64_t ldx, const T* y, T* host_o
   multi_dot_stage2<T><<<nv, 32, 0, ctx().stream>>>(nblocks, partial.as<T>(), out.as<T>());
   TTN_CHECK_LAUNCH();
   ctx().launches += 2;
-  TTN_CUDA(cudaMemcpyAsync(host_out, out.p, sizeof(T) * nv, cudaMemcpyDeviceToHost, ctx().stream));
-  TTN_CUDA(cudaStreamSynchronize(ctx().stream));
+  read_back(host_out, out.p, sizeof(T) * nv);
 }
 
 template <class T>

@@ -439,8 +439,7 @@ int jacobi_orth(T* X, int m, int n, int64_t ldx, double* norms, int batch, int64
   const double fk = ctx().jacobi_noise_floor ? JAC_FLOOR2 : 0.0;
   if (ctx().use_cluster_jacobi && jacobi_cluster<T>(X, m, n, ldx, batch, bX, tol, fr, fk, dsw_cl.as<int>())) {
     int hsw = 0;
-    TTN_CUDA(cudaMemcpyAsync(&hsw, dsw_cl.p, sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
-    TTN_CUDA(cudaStreamSynchronize(ctx().stream));
+    read_back(&hsw, dsw_cl.p, sizeof(int));
     sweeps_used = hsw;
   } else if ((size_t)n * col_bytes <= budget) {
     // whole matrix in one SM: iterate to convergence inside the kernel
@@ -458,8 +457,7 @@ int jacobi_orth(T* X, int m, int n, int64_t ldx, double* norms, int batch, int64
       ctx().launches++;
     }
     int hsw = 0;   // sweeps of batch element 0 (diagnostics; one 4-byte D2H, overlapped with the norms read-back sync)
-    TTN_CUDA(cudaMemcpyAsync(&hsw, dsw.p, sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
-    TTN_CUDA(cudaStreamSynchronize(ctx().stream));
+    read_back(&hsw, dsw.p, sizeof(int));
     sweeps_used = hsw;
   } else if (n >= 128 && m >= 64 && std::min(m, n) >= ctx().gram_jacobi_min) {
     // large matrices: Gram-block Jacobi, O(m n^2) work on the FP64 tensor pipe (jacobi_gram.cu)
@@ -533,8 +531,7 @@ int jacobi_orth(T* X, int m, int n, int64_t ldx, double* norms, int batch, int64
         ctx().launches++;
       }
       unsigned int rotated = 0;
-      TTN_CUDA(cudaMemcpyAsync(&rotated, dmax.p, sizeof(rotated), cudaMemcpyDeviceToHost, ctx().stream));
-      TTN_CUDA(cudaStreamSynchronize(ctx().stream));
+      read_back(&rotated, dmax.p, sizeof(rotated));
       sweeps_used = sw + 1;
       if (!rotated) break;
     }

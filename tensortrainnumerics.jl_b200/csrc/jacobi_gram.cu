@@ -442,8 +442,7 @@ int jacobi_gram(T* X, int m, int n, int64_t ldx, double tol, const double* frob2
       if (cnt > 0) step(gA.as<int>() + off[st], gB.as<int>() + off[st], cnt, 1);
     }
     unsigned int rotated = 0;
-    TTN_CUDA(cudaMemcpyAsync(&rotated, rot.p, sizeof(rotated), cudaMemcpyDeviceToHost, ctx().stream));
-    TTN_CUDA(cudaStreamSynchronize(ctx().stream));
+    read_back(&rotated, rot.p, sizeof(rotated));
     sweeps = sw + 1;
     // bit 1 = some rotation of this sweep was not yet of second order; without one, what is left after the sweep is below the
     // tolerance and the confirming sweep (6 ms at 2048^2) is skipped, as in the cluster kernel

@@ -294,8 +294,7 @@ void matvec2_host(int w_l, int w_r, int chi_l, int chi_r, int nn, const void* G,
   DevBuf Vd(sizeof(T) * (size_t)op.size()), Yd(sizeof(T) * (size_t)op.size());
   TTN_CUDA(cudaMemcpyAsync(Vd.p, V, Vd.bytes, cudaMemcpyHostToDevice, ctx().stream));
   op.apply(Vd.as<T>(), Yd.as<T>());
-  TTN_CUDA(cudaMemcpyAsync(Y, Yd.p, Yd.bytes, cudaMemcpyDeviceToHost, ctx().stream));
-  TTN_CUDA(cudaStreamSynchronize(ctx().stream));
+  read_back(Y, Yd.p, Yd.bytes);
 }
 
 template <class T>
@@ -311,8 +310,7 @@ void env_host(bool left, int n, int w_l, int w_r, int r_l, int r_r, const void* 
   env_update<T>(left, Ec.as<T>(), chi_in, w_in, xd.as<T>(), n, r_l, r_r, Ad.as<T>(), w_l, w_r, Eo);
   DevBuf Er(sizeof(T) * (size_t)w_out * chi_out * chi_out);
   env_ref_to_canon<T>(Eo.as<T>(), Er.as<T>(), w_out, chi_out, true);
-  TTN_CUDA(cudaMemcpyAsync(Eout, Er.p, Er.bytes, cudaMemcpyDeviceToHost, ctx().stream));
-  TTN_CUDA(cudaStreamSynchronize(ctx().stream));
+  read_back(Eout, Er.p, Er.bytes);
 }
 
 ttn_matvec matvec2_create(int dtype, int w_l, int w_r, int chi_l, int chi_r, int nn, const void* G, const void* Amid,

@@ -386,8 +386,7 @@ static double shard_eig_t(ShardOp<T>& op, T* x, int krylovdim, int maxiter, doub
   if (matvecs) *matvecs = info.matvecs;
   if (op.bound && op.nranks > 1) {
     int e = 0;
-    TTN_CUDA(cudaMemcpyAsync(&e, op.err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
-    TTN_CUDA(cudaStreamSynchronize(ctx().stream));
+    read_back(&e, op.err.p, sizeof(int));
     if (e) throw Error(6, "sharded matvec: a peer did not publish its slice within the epoch timeout (TTN_SHARD_TIMEOUT_S); "
                           "the gathered vector and the eigenpair are invalid");
   }
@@ -405,8 +404,7 @@ double shard_eigsolve(ttn_shard_matvec mv, void* x, int krylovdim, int maxiter, 
 int shard_error(ttn_shard_matvec mv) {
   int e = 0;
   void* p = mv->dtype == TTN_F64 ? mv->r.err.p : mv->c.err.p;
-  TTN_CUDA(cudaMemcpyAsync(&e, p, sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
-  TTN_CUDA(cudaStreamSynchronize(ctx().stream));
+  read_back(&e, p, sizeof(int));
   return e;
 }
 
@@ -462,8 +460,7 @@ int shard_ctx_error(ttn_shard_ctx c) {
   int e = 0, tot = 0;
   for (int t = 0; t < 2; ++t) {
     void* p = c->dtype == TTN_F64 ? c->r.op[t].err.p : c->c.op[t].err.p;
-    TTN_CUDA(cudaMemcpyAsync(&e, p, sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
-    TTN_CUDA(cudaStreamSynchronize(ctx().stream));
+    read_back(&e, p, sizeof(int));
     tot |= e;
   }
   return tot;

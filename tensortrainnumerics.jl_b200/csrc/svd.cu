@@ -81,8 +81,7 @@ void svd_left(const T* Theta, int p, int q, int64_t rs, int64_t cs, bool conj, S
       TTN_CHECK_LAUNCH();
       ctx().launches++;
       std::vector<double> hn(p);
-      TTN_CUDA(cudaMemcpyAsync(hn.data(), n2.p, sizeof(double) * p, cudaMemcpyDeviceToHost, ctx().stream));
-      TTN_CUDA(cudaStreamSynchronize(ctx().stream));
+      read_back(hn.data(), n2.p, sizeof(double) * p);
       for (double& v : hn)
         if (!std::isfinite(v)) v = 0.0;   // keeps the comparator a strict weak order; the Jacobi stage reports the NaN
       std::vector<int> perm(p);
@@ -152,8 +151,7 @@ void svd_left(const T* Theta, int p, int q, int64_t rs, int64_t cs, bool conj, S
   if (debug_svd()) fprintf(stderr, "[ttn] svd_left %d x %d batch %d: %d Jacobi sweeps\n", p, q, batch, out.sweeps);
   // singular values to the host, sorted descending per batch element
   std::vector<double> h((size_t)k * batch);
-  TTN_CUDA(cudaMemcpyAsync(h.data(), out.norms.p, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, ctx().stream));
-  TTN_CUDA(cudaStreamSynchronize(ctx().stream));
+  read_back(h.data(), out.norms.p, sizeof(double) * h.size());
   for (double v : h)
     if (!std::isfinite(v)) throw Error(5, "svd_left: the Jacobi SVD produced a non-finite singular value (non-finite input?)");
   out.sigma.resize(h.size());

@@ -64,8 +64,7 @@ void tt_dot(const TT<T>& A, const TT<T>& B, std::vector<T>& out) {
   }
   ttn_assert(A.rks[A.d] == 1 && B.rks[B.d] == 1, 1, "dot: boundary ranks must be 1");
   out.resize(batch);
-  TTN_CUDA(cudaMemcpyAsync(out.data(), M.p, sizeof(T) * batch, cudaMemcpyDeviceToHost, ctx().stream));
-  TTN_CUDA(cudaStreamSynchronize(ctx().stream));
+  read_back(out.data(), M.p, sizeof(T) * batch);
 }
 
 // src/tt_operations.jl:10-35 (block-diagonal concatenation)
@@ -708,8 +707,7 @@ bool tt_compress_gram(TT<T>& x, int64_t max_bond, int sweeps, double* sigma_out,
       gs.gram_steps.push_back((int)step); ++ngram;
       if (dbg) {   // debugging only: a flag read per step shows which bond declined
         std::vector<int> f(x.batch);
-        TTN_CUDA(cudaMemcpyAsync(f.data(), gs.flags.p, gs.flags.bytes, cudaMemcpyDeviceToHost, ctx().stream));
-        TTN_CUDA(cudaStreamSynchronize(ctx().stream));
+        read_back(f.data(), gs.flags.p, gs.flags.bytes);
         int a = 0;
         for (int v : f) a |= v;
         if (a != dbg_prev) {
@@ -741,12 +739,19 @@ bool tt_compress_gram(TT<T>& x, int64_t max_bond, int sweeps, double* sigma_out,
   ctx().gram_calls++;
   std::vector<int> hf(x.batch);
   std::vector<double> hs;
-  TTN_CUDA(cudaMemcpyAsync(hf.data(), gs.flags.p, gs.flags.bytes, cudaMemcpyDeviceToHost, ctx().stream));
-  if (gs.sigdev.p) {
-    hs.resize((size_t)nsteps * sigma_stride);
-    TTN_CUDA(cudaMemcpyAsync(hs.data(), gs.sigdev.p, gs.sigdev.bytes, cudaMemcpyDeviceToHost, ctx().stream));
+  {   // one read per call, through the context's pinned staging area (a pageable destination serialises in the driver)
+    const size_t fb = (gs.flags.bytes + 15) & ~(size_t)15;
+    const size_t sb = gs.sigdev.p ? gs.sigdev.bytes : 0;
+    char* st = (char*)host_stage(fb + sb);
+    TTN_CUDA(cudaMemcpyAsync(st, gs.flags.p, gs.flags.bytes, cudaMemcpyDeviceToHost, ctx().stream));
+    if (sb) TTN_CUDA(cudaMemcpyAsync(st + fb, gs.sigdev.p, sb, cudaMemcpyDeviceToHost, ctx().stream));
+    TTN_CUDA(cudaStreamSynchronize(ctx().stream));
+    memcpy(hf.data(), st, sizeof(int) * hf.size());
+    if (sb) {
+      hs.resize((size_t)nsteps * sigma_stride);
+      memcpy(hs.data(), st + fb, sb);
+    }
   }
-  TTN_CUDA(cudaStreamSynchronize(ctx().stream));
   int any = threw ? 32 : 0;
   for (int f : hf) any |= f;
   ctx().gram_last_flags = any;

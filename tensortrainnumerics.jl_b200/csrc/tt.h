@@ -93,11 +93,14 @@ struct ttn_ttv_s {
   // asynchronous host <-> device traffic on the library's copy stream (ttn_ttv_upload_async / ttn_ttv_download_async):
   cudaEvent_t ready = nullptr;   // recorded after the H2D copies: the compute stream must wait for it before the first use
   cudaEvent_t busy = nullptr;    // recorded after the D2H copies: the cores must not be released before it
-  ~ttn_ttv_s() {
-    if (ready) { cudaStreamWaitEvent(ttn::ctx().stream, ready, 0); cudaEventDestroy(ready); }
-    if (busy) { cudaStreamWaitEvent(ttn::ctx().stream, busy, 0); cudaEventDestroy(busy); }
-  }
+  // A handle freed while its D2H copies are still in flight parks its cores on the calling thread's deferred list (api.cu) and
+  // they go back to the block cache once the event has completed, so the compute stream never waits for the copy engine.
+  ~ttn_ttv_s();
 };
+namespace ttn {
+/// returns the cores of freed handles whose asynchronous downloads have completed to the block cache (`block`: wait for all)
+void drain_deferred_releases(bool block);
+}
 struct ttn_tto_s {
   int dtype = 0;
   ttn::TTO<double> r;

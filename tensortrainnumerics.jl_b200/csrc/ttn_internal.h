@@ -64,10 +64,16 @@ struct Context {
   int gram_last_flags = 0;
   bool gemm_bulk = true;            // TMA-staged (cp.async.bulk + mbarrier) big-tile GEMM when the operands allow it; TTN_GEMM_BULK=0 disables
   bool gram_compress = true;        // Gram path of tt_compress! for truncerr == 0 (heig.cu); TTN_GRAM_COMPRESS=0 disables
+  void* host_stage = nullptr;       // pinned staging area of the small device -> host reads (flags, singular values): a pageable
+  size_t host_stage_bytes = 0;      // destination would make the read a staged, driver-serialised copy that stalls other host threads
   int gram_jacobi_min = 640;        // Gram-block Jacobi (DMMA, two streams) for matrices with min(m, n) >= this (measured crossover);
                                     // TTN_GRAM_JACOBI=1: from 128 columns up, TTN_GRAM_JACOBI=0: never
 };
 Context& ctx();
+/// pinned host scratch of at least `bytes` bytes owned by the calling thread's context (valid until the next call)
+void* host_stage(size_t bytes);
+/// blocking device -> host read on the library stream; small reads go through the pinned staging area
+void read_back(void* dst, const void* src, size_t bytes);
 // brackets the launches of one kernel family with CUDA events on the library stream when profiling is enabled
 struct ProfScope {
   bool on;
