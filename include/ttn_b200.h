@@ -98,6 +98,10 @@ int ttn_ttv_complex(ttn_ttv x, ttn_ttv* out);                    /* Base.complex
 int ttn_ttv_free(ttn_ttv x);
 int ttn_tto_upload(int dtype, int d, const int64_t* dims, const int64_t* rks, const void* const* cores, ttn_tto* out);
 int ttn_tto_complex(ttn_tto A, ttn_tto* out);                    /* Base.complex, src/tt_tools.jl:59-61 */
+int ttn_tto_info(ttn_tto A, int* dtype, int* d);
+int ttn_tto_ranks(ttn_tto A, int64_t* rks /* d+1 */);            /* tto_rks, src/tt_tools.jl:52 */
+int ttn_tto_dims(ttn_tto A, int64_t* dims /* d */);              /* tto_dims, src/tt_tools.jl:51 */
+int ttn_tto_download(ttn_tto A, void* const* cores);             /* cores back as (n_k, n_k, R_{k-1}, R_k) column-major, src/tt_tools.jl:50 */
 int ttn_tto_free(ttn_tto A);
 
 /* ---- TT algebra -------------------------------------------------------------------------------------- */

@@ -75,6 +75,8 @@ def load():
         "ttn_ttv_ot": [vp, i64p], "ttn_ttv_download": [vp, vpp], "ttn_ttv_copy": [vp, vpp],
         "ttn_ttv_complex": [vp, vpp], "ttn_ttv_free": [vp],
         "ttn_tto_upload": [C.c_int, C.c_int, i64p, i64p, vpp, vpp], "ttn_tto_complex": [vp, vpp], "ttn_tto_free": [vp],
+        "ttn_tto_info": [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)], "ttn_tto_ranks": [vp, i64p], "ttn_tto_dims": [vp, i64p],
+        "ttn_tto_download": [vp, vpp],
         "ttn_apply": [vp, vp, vpp], "ttn_dot": [vp, vp, dp], "ttn_norm": [vp, dp], "ttn_add": [vp, vp, vpp],
         "ttn_scale": [vp, C.c_double, C.c_double, vpp], "ttn_orthogonalize": [vp, C.c_int, vpp],
         "ttn_compress": [vp, C.c_int64, C.c_double, C.c_int, dp, C.c_int64],

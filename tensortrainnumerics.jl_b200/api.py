@@ -321,6 +321,26 @@ class DeviceTTO:
         check(_lib.lib().ttn_tto_complex(self._h, C.byref(out)))
         return DeviceTTO(out, TTN_C128, self.N)
 
+    @property
+    def tto_rks(self):
+        buf = (C.c_int64 * (self.N + 1))()
+        check(_lib.lib().ttn_tto_ranks(self._h, buf))
+        return [int(v) for v in buf]
+
+    @property
+    def tto_dims(self):
+        buf = (C.c_int64 * self.N)()
+        check(_lib.lib().ttn_tto_dims(self._h, buf))
+        return tuple(int(v) for v in buf)
+
+    def download(self):
+        """device -> host TToperator (cores (n_k, n_k, R_{k-1}, R_k), Fortran order, as src/tt_tools.jl:48-54 stores them)"""
+        dims, rks = self.tto_dims, self.tto_rks
+        cores = [np.zeros((dims[k], dims[k], rks[k], rks[k + 1]), dtype=self.dtype, order="F") for k in range(self.N)]
+        ptrs = (C.c_void_p * self.N)(*[c.ctypes.data for c in cores])
+        check(_lib.lib().ttn_tto_download(self._h, ptrs))
+        return TToperator(self.N, cores, dims, rks)
+
     def free(self):
         if self._h is not None and self._h.value:
             _lib.load().ttn_tto_free(self._h)

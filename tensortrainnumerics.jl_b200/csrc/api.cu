@@ -433,6 +433,39 @@ int ttn_tto_complex(ttn_tto A, ttn_tto* out) {
   *out = h;
   API_END
 }
+int ttn_tto_info(ttn_tto A, int* dtype, int* d) {
+  API_BEGIN
+  ttn_assert(A != nullptr, TTN_EARG, "null handle");
+  if (dtype) *dtype = A->dtype;
+  if (d) *d = A->dtype == TTN_F64 ? A->r.d : A->c.d;
+  API_END
+}
+int ttn_tto_ranks(ttn_tto A, int64_t* rks) {
+  API_BEGIN
+  ttn_assert(A && rks, TTN_EARG, "null handle");
+  const auto& v = A->dtype == TTN_F64 ? A->r.rks : A->c.rks;
+  std::copy(v.begin(), v.end(), rks);
+  API_END
+}
+int ttn_tto_dims(ttn_tto A, int64_t* dims) {
+  API_BEGIN
+  ttn_assert(A && dims, TTN_EARG, "null handle");
+  const auto& v = A->dtype == TTN_F64 ? A->r.dims : A->c.dims;
+  std::copy(v.begin(), v.end(), dims);
+  API_END
+}
+int ttn_tto_download(ttn_tto A, void* const* cores) {
+  API_BEGIN
+  need_init();
+  ttn_assert(A && cores, TTN_EARG, "null handle");
+  const int d = A->dtype == TTN_F64 ? A->r.d : A->c.d;
+  for (int k = 0; k < d; ++k) {
+    const DevBuf& b = A->dtype == TTN_F64 ? A->r.cores[k] : A->c.cores[k];
+    TTN_CUDA(cudaMemcpyAsync(cores[k], b.p, b.bytes, cudaMemcpyDeviceToHost, ctx().stream));
+  }
+  TTN_CUDA(cudaStreamSynchronize(ctx().stream));
+  API_END
+}
 int ttn_tto_free(ttn_tto A) {
   API_BEGIN
   delete A;

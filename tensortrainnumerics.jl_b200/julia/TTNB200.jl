@@ -84,6 +84,20 @@ function upload(A::TToperator{T, M}) where {T <: Union{Float64, ComplexF64}, M}
     return DevTTO(out[])
 end
 
+function download(A::DevTTO)
+    dt, d = Ref{Cint}(0), Ref{Cint}(0)
+    check(ccall((:ttn_tto_info, LIB[]), Cint, (Ptr{Cvoid}, Ptr{Cint}, Ptr{Cint}), A.h, dt, d))
+    N = Int(d[])
+    T = dt[] == F64 ? Float64 : ComplexF64
+    dims, rks = zeros(Int64, N), zeros(Int64, N + 1)
+    check(ccall((:ttn_tto_dims, LIB[]), Cint, (Ptr{Cvoid}, Ptr{Int64}), A.h, dims))
+    check(ccall((:ttn_tto_ranks, LIB[]), Cint, (Ptr{Cvoid}, Ptr{Int64}), A.h, rks))
+    vec = [zeros(T, dims[k], dims[k], rks[k], rks[k + 1]) for k in 1:N]
+    cores = [pointer(c) for c in vec]
+    GC.@preserve vec check(ccall((:ttn_tto_download, LIB[]), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), A.h, cores))
+    return TToperator{T, N}(N, vec, Tuple(dims), rks, zeros(Int64, N))
+end
+
 function download(x::DevTT)
     dt, d, b = Ref{Cint}(0), Ref{Cint}(0), Ref{Cint}(0)
     check(ccall((:ttn_ttv_info, LIB[]), Cint, (Ptr{Cvoid}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}), x.h, dt, d, b))

@@ -403,3 +403,20 @@ def test_distances_and_add_inplace(cplx):
     assert y is x and list(x.ttv_rks) == [1] + [p + q for p, q in zip(a.ttv_rks[1:-1], b.ttv_rks[1:-1])] + [1]
     assert all(v == 0 for v in x.ttv_ot)
     assert np.allclose(o.ttv_to_tensor(x), A + B, atol=1e-12)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128])
+def test_tto_round_trip(dtype):
+    # TToperator storage (src/tt_tools.jl:48-54): upload -> metadata -> download is bit-exact, Base.complex promotes (tt_tools.jl:59-61)
+    import ttn_b200 as t
+    rng = np.random.default_rng(41)
+    dims = (2, 3, 2, 4)
+    A = o.rand_tto(dims, 3, rng=rng, dtype=dtype)
+    Ad = t.DeviceTTO.upload(A)
+    assert Ad.tto_dims == tuple(dims) and Ad.tto_rks == list(A.tto_rks)
+    B = Ad.download()
+    for a, b in zip(A.tto_vec, B.tto_vec):
+        assert a.shape == b.shape and np.array_equal(np.asarray(a, dtype=dtype), b)
+    C = Ad.complex().download()
+    for a, c in zip(A.tto_vec, C.tto_vec):
+        assert c.dtype == np.complex128 and np.array_equal(np.asarray(a, dtype=np.complex128), c)
