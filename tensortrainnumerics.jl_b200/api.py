@@ -32,7 +32,7 @@ __all__ = [
     "euclidean_distance_normalized",
     "orthogonalize", "tt_compress_", "tt_bond_truncate_", "als_linsolve", "als_eigsolve", "als_gen_eigsolv", "mals_linsolve",
     "mals_eigsolve", "dmrg_linsolve", "dmrg_eigsolve", "tdvp", "tdvp2", "matvec2", "env_left", "env_right",
-    "shard_range", "shard_batch", "assemble_slices", "ShardedMatvec", "ShardContext", "apply_compress", "svdtrunc", "heig_top", "set_option", "get_option", "copy_synchronize", "qr_thin", "gemm_host", "launch_count", "reset_launch_count", "synchronize", "library_path", "profile", "profile_read", "stream_handle",
+    "shard_range", "shard_batch", "assemble_slices", "ShardedMatvec", "ShardContext", "apply_compress", "increase_ranks", "rand_orthogonal", "r_and_d_to_rks", "svdtrunc", "heig_top", "set_option", "get_option", "copy_synchronize", "qr_thin", "gemm_host", "launch_count", "reset_launch_count", "synchronize", "library_path", "profile", "profile_read", "stream_handle",
     "KERNEL_FAMILIES",
 ]
 
@@ -603,11 +603,82 @@ def als_linsolve(A, b, tt_start, sweep_count=2, it_solver=False, r_itsolver=5000
     return (x, {"residual": res}) if return_info else x
 
 
+def r_and_d_to_rks(rks, dims, rmax=1024):
+    """src/tt_tools.jl:407-425 (library host code, `ttn_r_and_d_to_rks`)."""
+    d = len(dims)
+    out = (C.c_int64 * (d + 1))()
+    check(_lib.load().ttn_r_and_d_to_rks(_i64(rks), _i64(dims), d, int(rmax), out))
+    return [int(v) for v in out]
+
+
+def rand_orthogonal(n, m, rng=None, dtype=np.float64):
+    """src/tt_tools.jl:80-84: the leading n x m block of the Q factor of a uniform random square matrix (NumPy RNG, so the
+    stream differs from Julia's; the distribution is the same)."""
+    rng = np.random.default_rng() if rng is None else rng
+    N = max(n, m)
+    a = rng.random((N, N))
+    if np.dtype(dtype) == np.complex128:
+        a = a + 1j * rng.random((N, N))
+    q, _ = np.linalg.qr(a)
+    return q[:n, :m]
+
+
+def increase_ranks(x, max_bond, rks=None, noise=0.0, rng=None):
+    """src/tt_tools.jl:443-489: pad every core to the ranks `r_and_d_to_rks(rks, dims; rmax = max_bond)`; with `noise != 0` the new
+    block of a core whose left / right / both ranks grew is `noise` x a slice of a random orthogonal matrix (the three branches of
+    `increase_ranks_noise`, tt_tools.jl:443-460).  Host function on TTvector (a DeviceTT is downloaded first)."""
+    x = x.download() if isinstance(x, DeviceTT) else x
+    d = x.N
+    if not max_bond > max(x.ttv_rks):
+        raise AssertionError("New bond dimension too low")
+    if rks is None:
+        rks = [1] + [int(max_bond)] * (d - 1) + [1]
+    rks = r_and_d_to_rks(rks, x.ttv_dims, rmax=max_bond)
+    T = np.result_type(*[c.dtype for c in x.ttv_vec])
+    out, ot = [], [0] * d
+    for i in range(d):
+        c = x.ttv_vec[i]
+        n, a, b = c.shape
+        rkm, rk = rks[i], rks[i + 1]
+        v = np.zeros((n, rkm, rk), dtype=T, order="F")
+        v[:, :a, :b] = c
+        if noise != 0.0:
+            if rkm == a and rk > b:
+                Q = rand_orthogonal(n * rkm, rk - b, rng, T)
+                v[:, :, b:] = noise * Q.reshape((n, rkm, rk - b), order="F")
+            elif rk == b and rkm > a:
+                Q = rand_orthogonal(rkm - a, n * rk, rng, T)
+                v[:, a:, :] = noise * Q.reshape((n, rkm - a, rk), order="F")
+            elif rk > b and rkm > a:
+                Q = rand_orthogonal((rkm - a) * n, rk - b, rng, T)
+                v[:, a:, b:] = noise * Q.reshape((n, rkm - a, rk - b), order="F")
+        out.append(v)
+    return TTvector(d, out, x.ttv_dims, rks, ot)
+
+
 def als_eigsolve(A, tt_start, sweep_schedule=(2,), rmax_schedule=None, noise_schedule=None, it_solver=False,
-                 itslv_thresh=1024, maxiter=200, linsolv_tol=1e-8, krylovdim=30):
-    """src/solvers/als.jl:251-321 → (E, tt_opt).  Only noise_schedule == 0 is supported on the device path."""
+                 itslv_thresh=1024, maxiter=200, linsolv_tol=1e-8, krylovdim=30, rng=None):
+    """src/solvers/als.jl:251-321 → (E, tt_opt).  With a non-zero `noise_schedule` the rank increases between the stages of the
+    schedule (als.jl:289-291) are done on the host by `increase_ranks(...; noise)` with the NumPy generator `rng` — the one step of
+    the solver that draws random numbers — and every stage's sweeps run on the device."""
     if noise_schedule is not None and any(float(v) != 0.0 for v in noise_schedule):
-        raise NotImplementedError("noise_schedule != 0 draws from the host RNG and is not on the device path")
+        sched = [int(v) for v in sweep_schedule]
+        if rmax_schedule is None or not (len(rmax_schedule) == len(sched) == len(noise_schedule)):
+            raise AssertionError("Sweep schedule error")
+        kw = dict(it_solver=it_solver, itslv_thresh=itslv_thresh, maxiter=maxiter, linsolv_tol=linsolv_tol, krylovdim=krylovdim)
+        host = not isinstance(tt_start, DeviceTT)
+        x, Es = tt_start, []
+        for j, ns in enumerate(sched):
+            if j > 0:       # als.jl:289-291: increase_ranks + orthogonalize + init_H (the last two open every device call)
+                x = increase_ranks(x, int(rmax_schedule[j]), noise=float(noise_schedule[j]), rng=rng)
+            # stage j runs the sweeps sched[j-1] .. sched[j] - 1 of the reference's counter (the first stage starts at 1)
+            nsw = ns - (sched[j - 1] if j > 0 else 1)
+            if nsw > 0:
+                E, x = als_eigsolve(A, x, sweep_schedule=(nsw + 1,), rmax_schedule=(max(x.ttv_rks),), **kw)
+                Es.append(E)
+        if host and isinstance(x, DeviceTT):
+            x = x.download()
+        return (np.concatenate(Es) if Es else np.zeros(0)), x
     xd, host = _dev(tt_start)
     if rmax_schedule is None:
         rmax_schedule = [max(xd.ttv_rks)]

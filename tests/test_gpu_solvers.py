@@ -69,6 +69,26 @@ def test_als_eigsolve_vs_dense():
         t.als_eigsolve(A, x0, sweep_schedule=[2, 3], rmax_schedule=[4])     # als.jl:263
 
 
+def test_als_eigsolve_noise_schedule():
+    # als.jl:289-291: a rank-1 start cannot leave its manifold under one-site ALS; the noisy rank increase of the second stage gives it
+    # the directions the ground state needs.  E is the concatenation of the stages' histories: 2 (d-1) entries per sweep, als.jl:299-311
+    import ttn_b200 as t
+    d = 6
+    A = spd_op(d, 1.0)
+    x0 = o.rand_tt((2,) * d, 1, rng=np.random.default_rng(3))
+    lam = sla.eigvalsh(o.tto_to_matrix(A))[0]
+    E1, _ = t.als_eigsolve(A, x0, sweep_schedule=[8], rmax_schedule=[1], linsolv_tol=1e-13)
+    E, x = t.als_eigsolve(A, x0, sweep_schedule=[3, 9], rmax_schedule=[1, 6], noise_schedule=[0.0, 1e-2], linsolv_tol=1e-13,
+                          rng=np.random.default_rng(4))
+    assert len(E) == 2 * (d - 1) * (9 - 1)                     # sweeps 1..8 of the reference's counter
+    assert max(x.ttv_rks) == 6
+    assert abs(E[-1] - lam) < 1e-9 < abs(E1[-1] - lam)         # rank 1 alone stays away from the ground state
+    v = dv(x)
+    assert abs(v @ o.tto_to_matrix(A) @ v / (v @ v) - lam) < 1e-9
+    with pytest.raises(AssertionError):
+        t.als_eigsolve(A, x0, sweep_schedule=[2, 3], rmax_schedule=[4], noise_schedule=[0.0, 0.1])     # als.jl:263
+
+
 def test_mals_linsolve_vs_dense():
     import ttn_b200 as t
     d = 6

@@ -60,6 +60,44 @@ def test_bubble_sort_swaps_and_qttvector_wrapper():
         t.QTTvector(x, 4, 2, "serial")
 
 
+def test_increase_ranks_zero_padding_and_noise_branches():
+    """increase_ranks (src/tt_tools.jl:443-489) in the host mirror: noise = 0 equals the oracle's zero padding bit for bit and
+    leaves the represented tensor unchanged; noise != 0 fills exactly the new blocks of the three branches of
+    increase_ranks_noise with `noise` x (orthonormal columns or rows), the old block untouched (tt_tools.jl:446-458)."""
+    rng = np.random.default_rng(5)
+    dims = (2, 3, 2, 2)
+    x = o.rand_tt(dims, 2, rng=rng)
+    xm = t.TTvector(x.N, x.ttv_vec, x.ttv_dims, x.ttv_rks, x.ttv_ot)
+    z = t.increase_ranks(xm, 4)
+    zo = o.increase_ranks(x, 4)
+    assert z.ttv_rks == zo.ttv_rks == o.r_and_d_to_rks([1, 4, 4, 4, 1], dims, rmax=4)
+    for a, b in zip(z.ttv_vec, zo.ttv_vec):
+        assert np.array_equal(a, b)
+    with pytest.raises(AssertionError):
+        t.increase_ranks(xm, 2)                               # "New bond dimension too low", tt_tools.jl:483
+    eps = 1e-3
+    y = t.increase_ranks(xm, 4, noise=eps, rng=np.random.default_rng(7))
+    assert y.ttv_rks == z.ttv_rks and y.ttv_ot == [0] * x.N
+    for i, (c, c0) in enumerate(zip(y.ttv_vec, x.ttv_vec)):
+        n, a, b = c0.shape
+        _, rkm, rk = c.shape
+        assert np.array_equal(c[:, :a, :b], c0)
+        if rkm == a and rk > b:                               # new right block: orthonormal columns of an (n rkm) x (rk - b) matrix
+            Q = c[:, :, b:].reshape((n * rkm, rk - b), order="F") / eps
+            assert np.allclose(Q.T @ Q, np.eye(rk - b), atol=1e-12)
+        elif rk == b and rkm > a:                             # new left block: orthonormal rows
+            Q = np.reshape(np.asfortranarray(c[:, a:, :]), (rkm - a, n * rk), order="F") / eps      # undoes Julia's column-major reshape
+            assert np.allclose(Q @ Q.T, np.eye(rkm - a), atol=1e-12)
+        elif rk > b and rkm > a:                              # corner block only; the off-diagonal new blocks stay zero
+            assert np.all(c[:, :a, b:] == 0) and np.all(c[:, a:, :b] == 0)
+            Q = c[:, a:, b:].reshape(((rkm - a) * n, rk - b), order="F") / eps
+            assert np.allclose(Q.T @ Q, np.eye(rk - b), atol=1e-12)
+    dz = o.ttv_to_tensor(o.TTvector(x.N, y.ttv_vec, dims, y.ttv_rks, [0] * x.N)) - o.ttv_to_tensor(x)
+    assert 0 < np.linalg.norm(dz) < 50 * eps * np.linalg.norm(o.ttv_to_tensor(x))
+    qz = t.rand_orthogonal(5, 3, np.random.default_rng(1), np.complex128)
+    assert qz.shape == (5, 3) and np.allclose(qz.conj().T @ qz, np.eye(3), atol=1e-12)
+
+
 def test_batch_sharding_helpers():
     # SURVEY.md section 8(e): vectors split evenly over the ranks, no data-path collective
     for n, world in ((4096, 8), (10, 3), (5, 8), (0, 2)):
