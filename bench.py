@@ -437,7 +437,21 @@ def run_ours(args, rank, local_rank, world):
         h2d, d2h = int(tb[0].item()), int(tb[1].item())
 
     # ---- roofline pass: per-kernel-family CUDA events over one step, with the FLOPs the kernels were asked to execute ------
-    ms_prof, pres = timed(1, profile=True)
+    # one worker at a time (the others idle), so that a family's event-bracketed time is that of its kernels alone on the GPU and not
+    # stretched by the other host thread's kernels sharing the SMs
+    ms_prof, pres = 0.0, []
+    for w in workers:
+        barrier()
+        g0 = torch.cuda.Event(enable_timing=True)
+        g0.record()
+        w.cmd.put(("device", 1, True))
+        r = w.done.get()
+        if isinstance(r, Exception):
+            raise r
+        torch.cuda.synchronize()
+        ms_prof += g0.elapsed_time(r["end"])
+        pres.append(r)
+    barrier()
     fam_ms, fam_cnt, executed = {}, {}, {"gemm": 0.0, "jacobi": 0.0}
     for r in pres:
         for k, v in r["fam"].items():
@@ -462,8 +476,9 @@ def run_ours(args, rank, local_rank, world):
                 "unit": "TFLOP/s", "frac": fams.get(dom, {}).get("frac", 0.0), "traffic": None,
                 "flop_accounting": "FLOPs the dominant kernel family was asked to execute in the step (GEMM: 8MNK per complex product; "
                                    "eigensolver: LAPACK counts 4/3 n^3 + 2 n^2 nev, x4 complex), counted inside the library, / the summed "
-                                   "CUDA-event time of that family on its streams (with 2 host threads the families of different chunks "
-                                   "overlap, so the per-family times add up to more than the step)",
+                                   "CUDA-event time of that family in a profiling pass that runs the host threads one after the other (kernels "
+                                   "timed without the other thread's kernels sharing the SMs; the timed region itself overlaps the threads, "
+                                   "which is why profiled_ms_per_step exceeds ms_per_step)",
                 "traffic_note": "bond matrices stream through L2 / shared memory; dram__bytes of the kernels: profiles/ncu_*_r02.txt",
                 "peak_source": "measured cuBLAS FP64 GEMM 8192^3 burst on this pool's B200 (profiles/fp64_peak_r01.json; builder-"
                                "measured fallback: MEASURED_PEAKS.json carries no FP64 figure)",

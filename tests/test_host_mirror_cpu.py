@@ -140,3 +140,37 @@ def test_committed_bench_line_follows_the_contract():
     assert c["kind"] in ("port", "reference") and c["cores"] >= 1 and c["sample"] and c["value"] > 0
     assert d["gpu_launches"] > 0
     assert d["clocks"]["samples"] >= 1 and not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+def test_committed_round2_bench_line_follows_the_contract():
+    """`profiles/bench_end_of_round_r02.json`: the line `python bench.py --steps 20 --warmup 5` printed on one B200 at the end of
+    round 2.  Headline = cfg5 (4096 ComplexF64 QTT vectors, apply + tt_compress!), strong scaling over the ranks; value and
+    ms_per_step must agree, the end-to-end leg must move every step's inputs and results over PCIe, the roofline must name its
+    dominant kernel family with achieved / peak, and no Gram-path fallback may hide inside the timed region."""
+    import json
+    d = json.load(open(os.path.join(ROOT, "profiles", "bench_end_of_round_r02.json")))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "e2e", "roofline", "cpu_baseline", "clocks", "gpu_launches", "extras"):
+        assert k in d, k
+    assert d["metric"] == "tt_rounding sweeps/s" and d["unit"] == "sweeps/s"
+    assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["dtype"] == "c128" and d["data"] == "synthetic" and d["scaling"] == "strong"
+    c = d["config"]
+    assert "cfg5" in c["workload"] and "model" not in c and c["total_vectors"] == 4096 and c["d"] == 30 and c["rank"] == 64
+    assert c["gram_path_fallbacks_in_timed_region"] == 0 and c["out_max_rank"] == 64
+    assert abs(d["value"] - 4096 / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] > 1e10 and e["d2h_bytes_per_step"] > 1e10 and 0 < e["value"] <= d["value"] * 1.02
+    assert abs(e["value"] - 4096 / (e["ms_per_step"] * 1e-3)) < 1e-6 * e["value"]
+    r = d["roofline"]
+    assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert set(r["families"]) == {"gemm", "jacobi"} and all(0 < f["frac"] < 1 for f in r["families"].values())
+    assert 0 < r["whole_step"]["executed"]["frac"] < 1
+    b = d["cpu_baseline"]
+    assert b["kind"] == "port" and b["cores"] >= 1 and b["sample"] and 0 < b["reference_faithful_value"] < b["value"] < d["value"]
+    assert d["gpu_launches"] > 1000
+    assert d["clocks"]["samples"] >= 1 and not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    x = d["extras"]
+    for k in ("cfg2_sweeps_per_s", "matvec_cfg4_tflops", "dmrg_sweep_s", "mals_cfg3_heat_s", "mals_cfg3_heat_max_rank"):
+        assert k in x, k
+    assert x["mals_cfg3_heat_max_rank"] == 128
