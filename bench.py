@@ -337,7 +337,31 @@ class ChunkWorker(threading.Thread):
                 "d2h": int(sum(sum(a.nbytes for a in self.res_bufs[c[0].shape[3]][0]) for c in hc))}
 
 
+def bind_to_gpu_numa(local_rank):
+    """one process per GPU, bound to the CPUs the GPU hangs off (NVML's ideal CPU set intersected with what the container allows):
+    the pinned buffers are then first-touched on that socket and the host <-> device copies of the end-to-end leg do not cross the
+    socket interconnect.  Returns the number of CPUs bound, or None when NVML has no answer."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[local_rank]) if vis else local_rank      # NVML numbers the physical devices
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        allowed = os.sched_getaffinity(0)
+        nwords = (max(allowed) + 64) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, nwords)
+        ideal = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1}
+        cpus = ideal & allowed
+        if not cpus or cpus == allowed:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return None
+
+
 def run_ours(args, rank, local_rank, world):
+    bound = bind_to_gpu_numa(local_rank) if world > 1 and not args.no_numa_bind else None
     import torch
     import ttn_b200 as t
     torch.cuda.set_device(local_rank)
@@ -427,7 +451,7 @@ def run_ours(args, rank, local_rank, world):
         return (time.perf_counter() - w0) / max(1, nsteps), r
 
     e2e(min(W, 1))
-    e2e_steps = max(1, min(K, args.e2e_steps))
+    e2e_steps = max(1, min(K, args.e2e_steps * world))     # about the same bytes over PCIe per rank at every N
     e2e_s, er = e2e(e2e_steps)
     e2e_s = allmax(e2e_s)
     h2d, d2h = sum(r["h2d"] for r in er), sum(r["d2h"] for r in er)
@@ -572,7 +596,8 @@ def run_ours(args, rank, local_rank, world):
         line = {"metric": "tt_rounding sweeps/s", "value": value, "unit": "sweeps/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "c128",
                 "data": "synthetic", "config": dict(cfg5_config(world, chunk), out_max_rank=int(max(out_rks)),
-                                                    gram_path_fallbacks_in_timed_region=fallbacks, host_threads_per_rank=nw),
+                                                    gram_path_fallbacks_in_timed_region=fallbacks, host_threads_per_rank=nw,
+                                                    cpus_bound_per_rank=bound),
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": TOTAL5 / e2e_s, "unit": "sweeps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "mode": os.environ.get("TTN_BENCH_E2E_MODE", "full"),
@@ -756,6 +781,7 @@ def main():
     ap.add_argument("--host-threads", type=int, default=2, help="library contexts (host threads) per rank: chunks in flight")
     ap.add_argument("--e2e-steps", type=int, default=5, help="upper bound on the end-to-end steps (each moves 2 x 10 GB over PCIe at N=1)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-numa-bind", action="store_true", help="N > 1: do not bind each rank to its GPU's CPU set")
     ap.add_argument("--no-extras", action="store_true", help="skip the cfg2 / cfg4 matvec / DMRG sweep / cfg3 extras")
     ap.add_argument("--dmrg-chi", type=int, default=1024, help="bond cap of the DMRG sweep extra (cfg4: 1024)")
     ap.add_argument("--dmrg-all", action="store_true", help="run the DMRG sweep extra at N > 1 as well")

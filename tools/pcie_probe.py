@@ -7,6 +7,14 @@ import torch
 
 
 def main():
+    import os
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    dist = None
+    if world > 1:                      # all ranks copy at the same time: what the host can feed to N GPUs at once
+        import torch.distributed as dist
+        dist.init_process_group("gloo")
     n = 1 << 30
     h_in = torch.empty(n, dtype=torch.uint8).pin_memory()
     h_out = torch.empty(n, dtype=torch.uint8).pin_memory()
@@ -15,9 +23,11 @@ def main():
     s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
     out = {}
 
-    def timed(fn, reps=5):
+    def timed(fn, reps=10):
         fn()
         torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
         t0 = time.perf_counter()
         for _ in range(reps):
             fn()
@@ -49,6 +59,17 @@ def main():
     tm = timed(lambda: torch.matmul(a, a))
     out["duplex_with_fp64_gemm_s"] = tb
     out["fp64_gemm_alone_s"] = tm
+    out["rank"], out["world"], out["cpus"] = rank, world, len(os.sched_getaffinity(0))
+    if dist is not None:
+        allo = [None] * world
+        dist.all_gather_object(allo, out)
+        if rank == 0:
+            print(json.dumps({"world": world, "cpus": out["cpus"],
+                              "h2d_GBps_per_gpu": [round(o["h2d_GBps"], 1) for o in allo],
+                              "d2h_GBps_per_gpu": [round(o["d2h_GBps"], 1) for o in allo],
+                              "duplex_GBps_each_way_per_gpu": [round(o["duplex_GBps_each_way"], 1) for o in allo]}))
+        dist.destroy_process_group()
+        return
     print(json.dumps(out))
 
 
