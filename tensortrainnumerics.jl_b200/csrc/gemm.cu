@@ -28,8 +28,16 @@ constexpr int NSTAGE = 4;       // cp.async pipeline depth (k-slabs in flight)
 template <class T> struct Pad { static constexpr int v = 4; };
 template <> struct Pad<zc> { static constexpr int v = 2; };
 
-template <class T, int BM, int BN, int WM, int WN, bool AMAJ, bool BMAJ>
-__global__ void __launch_bounds__(NT) gemm_kernel(const GemmArgs g) {
+// tiles with at most 64 KB of accumulators whose pipeline fits in ~110 KB of shared memory are compiled for two CTAs per SM
+// (<= 128 registers per thread): 16 resident warps hide the DMMA / shared-memory latency that 8 warps leave exposed
+template <class T, int BM, int BN, int NS>
+struct MinBlocks {
+  static constexpr size_t smem = sizeof(T) * NS * BK * (BM + BN + 2 * Pad<T>::v);
+  static constexpr int v = (sizeof(T) * BM * BN <= 65536 && smem <= 112 * 1024) ? 2 : 1;
+};
+
+template <class T, int BM, int BN, int WM, int WN, bool AMAJ, bool BMAJ, int NS = NSTAGE>
+__global__ void __launch_bounds__(NT, MinBlocks<T, BM, BN, NS>::v) gemm_kernel(const GemmArgs g) {
   constexpr int PAD = Pad<T>::v;
   constexpr int PA = BM + PAD, PB = BN + PAD;
   constexpr int EA = BM * BK / NT, EB = BN * BK / NT;
@@ -40,7 +48,7 @@ __global__ void __launch_bounds__(NT) gemm_kernel(const GemmArgs g) {
   static_assert(BM * BK % NT == 0 && BN * BK % NT == 0, "tile loads must divide evenly");
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* Sm = reinterpret_cast<T*>(smem_raw);            // [NSTAGE][ A: [BK][PA] | B: [BK][PB] ]
+  T* Sm = reinterpret_cast<T*>(smem_raw);            // [NS][ A: [BK][PA] | B: [BK][PB] ]
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -83,7 +91,7 @@ __global__ void __launch_bounds__(NT) gemm_kernel(const GemmArgs g) {
   }
   auto issue = [&](int kt) {
     if (kt < nkt) {
-      T* as = Sm + (size_t)(kt % NSTAGE) * STAGE;
+      T* as = Sm + (size_t)(kt % NS) * STAGE;
       T* bs = as + BK * PA;
       const int k0 = kt * BK;
 #pragma unroll
@@ -101,14 +109,14 @@ __global__ void __launch_bounds__(NT) gemm_kernel(const GemmArgs g) {
   };
 
 #pragma unroll
-  for (int s = 0; s < NSTAGE - 1; ++s) issue(s);
+  for (int s = 0; s < NS - 1; ++s) issue(s);
 
   const bool cja = g.conjA, cjb = g.conjB;
   for (int kt = 0; kt < nkt; ++kt) {
-    cp_async_wait<NSTAGE - 2>();      // slab kt has landed (for this thread's copies) ...
+    cp_async_wait<NS - 2>();      // slab kt has landed (for this thread's copies) ...
     __syncthreads();                  // ... and for everyone; slab kt-1 is no longer being read
-    issue(kt + NSTAGE - 1);           // refills the buffer of slab kt-1
-    const T* as = Sm + (size_t)(kt % NSTAGE) * STAGE;
+    issue(kt + NS - 1);           // refills the buffer of slab kt-1
+    const T* as = Sm + (size_t)(kt % NS) * STAGE;
     const T* bs = as + BK * PA;
 #pragma unroll
     for (int kk = 0; kk < BK; kk += 4) {
@@ -167,7 +175,7 @@ __global__ void __launch_bounds__(NT) gemm_kernel(const GemmArgs g) {
 // Requirements (checked by the host dispatcher): unit stride along the tile rows, full tiles, 16-byte aligned rows.
 // ---------------------------------------------------------------------------------------------------------------------
 template <class T, int BM, int BN, int WM, int WN, bool BMAJ>
-__global__ void __launch_bounds__(NT) gemm_bulk_kernel(const GemmArgs g) {
+__global__ void __launch_bounds__(NT, MinBlocks<T, BM, BN, NSTAGE>::v) gemm_bulk_kernel(const GemmArgs g) {
   constexpr int PAD = Pad<T>::v;
   constexpr int PA = BM + PAD, PB = BN + PAD;
   constexpr int EB = BN * BK / NT;
@@ -315,11 +323,11 @@ bool try_bulk(const GemmArgs& g) {
   return false;
 }
 
-template <class T, int BM, int BN, int WM, int WN, bool AMAJ, bool BMAJ>
+template <class T, int BM, int BN, int WM, int WN, bool AMAJ, bool BMAJ, int NS = NSTAGE>
 void launch_cfg(const GemmArgs& g) {
   constexpr int PAD = Pad<T>::v;
-  const size_t smem = sizeof(T) * NSTAGE * BK * ((BM + PAD) + (BN + PAD));
-  auto kern = gemm_kernel<T, BM, BN, WM, WN, AMAJ, BMAJ>;
+  const size_t smem = sizeof(T) * NS * BK * ((BM + PAD) + (BN + PAD));
+  auto kern = gemm_kernel<T, BM, BN, WM, WN, AMAJ, BMAJ, NS>;
   static int attr_dev = -1;   // function attributes are per device (ttn_init may re-bind)
   if (attr_dev != ctx().device) {
     TTN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -347,25 +355,41 @@ void launch_cfg(const GemmArgs& g) {
   (void)nb;
 }
 
-template <class T, int BM, int BN, int WM, int WN>
+template <class T, int BM, int BN, int WM, int WN, int NS = NSTAGE>
 void launch_major(const GemmArgs& g) {
   const bool amaj = std::llabs(g.sAm) <= std::llabs(g.sAk);   // m is the faster index of A in memory
   const bool bmaj = std::llabs(g.sBn) < std::llabs(g.sBk);    // n is the faster index of B in memory
-  if (amaj && bmaj) launch_cfg<T, BM, BN, WM, WN, true, true>(g);
-  else if (amaj && !bmaj) launch_cfg<T, BM, BN, WM, WN, true, false>(g);
-  else if (!amaj && bmaj) launch_cfg<T, BM, BN, WM, WN, false, true>(g);
-  else launch_cfg<T, BM, BN, WM, WN, false, false>(g);
+  if (amaj && bmaj) launch_cfg<T, BM, BN, WM, WN, true, true, NS>(g);
+  else if (amaj && !bmaj) launch_cfg<T, BM, BN, WM, WN, true, false, NS>(g);
+  else if (!amaj && bmaj) launch_cfg<T, BM, BN, WM, WN, false, true, NS>(g);
+  else launch_cfg<T, BM, BN, WM, WN, false, false, NS>(g);
 }
 
 template <class T> struct Tiles;
 template <> struct Tiles<double> {
   static void big(const GemmArgs& g) { launch_major<double, 128, 128, 64, 32>(g); }
   static void small(const GemmArgs& g) { launch_major<double, 64, 64, 32, 16>(g); }
+  static void compact(const GemmArgs& g) {
+    const int v = ctx().gemm_real_tile;
+    if (v == 1) launch_major<double, 128, 64, 32, 32, 3>(g);
+    else if (v == 2) launch_major<double, 128, 64, 32, 32, 2>(g);
+    else if (v == 4) launch_major<double, 128, 64, 32, 32, 4>(g);
+    else if (v == 5) { if (!try_bulk<double, 128, 64, 32, 32>(g)) launch_major<double, 128, 64, 32, 32, 3>(g); }
+    else launch_major<double, 64, 64, 32, 16, 2>(g);
+  }
   static constexpr int BIGM = 128, BIGN = 128;
 };
 template <> struct Tiles<zc> {
   static void big(const GemmArgs& g) { launch_major<zc, 64, 128, 32, 32>(g); }
   static void small(const GemmArgs& g) { launch_major<zc, 64, 64, 32, 16>(g); }
+  // 64 x 64 tile, two pipeline stages: 68 KB of shared memory and 32 K registers per CTA, so that one such CTA fits on an SM next
+  // to a CTA of the (latency-bound, 132 KB) ComplexF64 tridiagonalisation kernel of another stream (ctx().gemm_compact)
+  static void compact(const GemmArgs& g) {
+    const int v = ctx().gemm_compact;
+    if (v == 2) launch_major<zc, 64, 64, 32, 16, 3>(g);
+    else if (v == 3) launch_major<zc, 64, 64, 32, 16, 4>(g);
+    else launch_major<zc, 64, 64, 32, 16, 2>(g);
+  }
   static constexpr int BIGM = 64, BIGN = 128;
 };
 
@@ -380,6 +404,10 @@ void gemm(const GemmArgs& g) {
                            ((g.N + Tiles<T>::BIGN - 1) / Tiles<T>::BIGN) * g.batch1 * g.batch2;
   const bool big = g.M >= (Tiles<T>::BIGM * 3) / 4 && g.N >= (Tiles<T>::BIGN * 3) / 4 &&
                    ctas_big >= (int64_t)(ctx().sm_count * 3) / 4;
+  if (g.npeer == 0 && (is_cplx<T>::value ? ctx().gemm_compact != 0 : (ctx().gemm_real_tile != 0 && big))) {
+    Tiles<T>::compact(g);
+    return;
+  }
   if (big) {
     if (!is_cplx<T>::value && try_bulk<double, 128, 128, 64, 32>(g)) return;
     Tiles<T>::big(g);
