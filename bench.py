@@ -778,7 +778,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chunk", type=int, default=296, help="vectors per device batch (cfg5); 296 = two full waves of one matrix per SM")
-    ap.add_argument("--host-threads", type=int, default=2, help="library contexts (host threads) per rank: chunks in flight")
+    ap.add_argument("--host-threads", type=int, default=3, help="library contexts (host threads) per rank: chunks in flight")
     ap.add_argument("--e2e-steps", type=int, default=5, help="upper bound on the end-to-end steps (each moves 2 x 10 GB over PCIe at N=1)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-numa-bind", action="store_true", help="N > 1: do not bind each rank to its GPU's CPU set")
