@@ -89,6 +89,7 @@ int ttn_set_option(const char* key, double value) {
   else if (k == "gemm_bulk") c.gemm_bulk = value != 0.0;
   else if (k == "gemm_compact") c.gemm_compact = (int)value;
   else if (k == "gemm_real_tile") c.gemm_real_tile = (int)value;
+  else if (k == "gemm_thin") c.gemm_thin = value != 0.0;
   else if (k == "gram_jacobi_min") c.gram_jacobi_min = (int)value;
   else if (k == "use_cholqr") c.use_cholqr = value != 0.0;
   else if (k == "use_cluster_jacobi") c.use_cluster_jacobi = value != 0.0;
@@ -106,6 +107,7 @@ int ttn_get_option(const char* key, double* value) {
   else if (k == "gemm_bulk") *value = c.gemm_bulk;
   else if (k == "gemm_compact") *value = c.gemm_compact;
   else if (k == "gemm_real_tile") *value = c.gemm_real_tile;
+  else if (k == "gemm_thin") *value = c.gemm_thin;
   else if (k == "gram_jacobi_min") *value = c.gram_jacobi_min;
   else if (k == "use_cholqr") *value = c.use_cholqr;
   else if (k == "use_cluster_jacobi") *value = c.use_cluster_jacobi;

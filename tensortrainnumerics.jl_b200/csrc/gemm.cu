@@ -365,6 +365,84 @@ void launch_major(const GemmArgs& g) {
   else launch_cfg<T, BM, BN, WM, WN, false, false, NS>(g);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Thin right-multiplication  C_b (M x N) = alpha A_b (M x K) W (K x N) + beta C_b  with N, K <= 32 and one W for the whole batch:
+// the middle contraction of the three-GEMM effective operator (T2 = T1 . W, K = w n^2 = 20 at cfg4) and of the environment
+// updates.  It is a streaming operation (2 x 8 bytes moved per 2 K flop): a DMMA tile would idle on 20 of its 64 columns, so each
+// thread keeps one row of A_b in registers (loads coalesced along M), W sits in shared memory (broadcast reads) and the row of C
+// goes back coalesced.  Bound: HBM bandwidth.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int THIN_MAX = 32;
+// KT = compile-time bound on K (registers), ROWS = rows of A per thread (every W value read from shared memory is used ROWS times)
+template <class T, int KT, int ROWS>
+__global__ void __launch_bounds__(256) gemm_thin_kernel(const GemmArgs g) {
+  __shared__ __align__(16) T Ws[THIN_MAX * KT];
+  const int K = g.K, N = g.N;
+  const T* __restrict__ Bp = reinterpret_cast<const T*>(g.B);
+  for (int idx = threadIdx.x; idx < KT * N; idx += blockDim.x) {
+    const int k = idx % KT, n = idx / KT;
+    T w = t_zero<T>();
+    if (k < K) {
+      w = Bp[k * g.sBk + n * g.sBn];
+      if (g.conjB) w = t_conj(w);
+    }
+    Ws[n * KT + k] = w;                      // zero padding up to KT: the inner loop needs no bound checks
+  }
+  __syncthreads();
+  const int m0 = blockIdx.x * (256 * ROWS) + threadIdx.x;
+  const int b = blockIdx.y, b1 = b % g.batch1, b2 = b / g.batch1;
+  const T* __restrict__ A = reinterpret_cast<const T*>(g.A) + b1 * g.bA1 + b2 * g.bA2;
+  T* __restrict__ C = reinterpret_cast<T*>(g.C) + b1 * g.bC1 + b2 * g.bC2;
+  T x[ROWS][KT];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    const int m = m0 + 256 * r;
+#pragma unroll
+    for (int k = 0; k < KT; ++k) x[r][k] = (k < K && m < g.M) ? A[m + k * g.sAk] : t_zero<T>();
+  }
+  for (int n = 0; n < N; ++n) {
+    T acc[ROWS][2];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) acc[r][0] = acc[r][1] = t_zero<T>();
+    const T* w = Ws + n * KT;
+#pragma unroll
+    for (int k = 0; k < KT; k += 2) {
+      const T w0 = w[k], w1 = w[k + 1];      // 16-byte aligned pair: one LDS.128 for Float64
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) { t_fma(acc[r][0], x[r][k], w0); t_fma(acc[r][1], x[r][k + 1], w1); }
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const int m = m0 + 256 * r;
+      if (m >= g.M) continue;
+      T v = t_scale(t_add(acc[r][0], acc[r][1]), g.alpha);
+      if (g.beta != 0.0) v = t_add(v, t_scale(C[m + n * g.sCn], g.beta));
+      C[m + n * g.sCn] = v;
+    }
+  }
+}
+
+template <class T, int KT, int ROWS>
+void launch_thin(const GemmArgs& g) {
+  dim3 grid((g.M + 256 * ROWS - 1) / (256 * ROWS), (unsigned)((int64_t)g.batch1 * g.batch2));
+  gemm_thin_kernel<T, KT, ROWS><<<grid, 256, 0, ctx().stream>>>(g);
+  TTN_CHECK_LAUNCH();
+  ctx().launches++;
+}
+
+template <class T>
+bool try_thin(const GemmArgs& g) {
+  if (g.N > THIN_MAX || g.K > THIN_MAX || g.M < 256 || g.npeer != 0 || g.conjA) return false;
+  if (g.sAm != 1 || g.sCm != 1 || g.bB1 != 0 || g.bB2 != 0) return false;
+  if ((int64_t)g.batch1 * g.batch2 > 65535) return false;
+  constexpr int R = is_cplx<T>::value ? 1 : 2;      // register budget: ROWS * KT values of T per thread
+  if (g.K <= 8) launch_thin<T, 8, R>(g);
+  else if (g.K <= 16) launch_thin<T, 16, R>(g);
+  else if (g.K <= 24) launch_thin<T, 24, R>(g);
+  else launch_thin<T, 32, 1>(g);
+  return true;
+}
+
 template <class T> struct Tiles;
 template <> struct Tiles<double> {
   static void big(const GemmArgs& g) { launch_major<double, 128, 128, 64, 32>(g); }
@@ -404,6 +482,7 @@ void gemm(const GemmArgs& g) {
                            ((g.N + Tiles<T>::BIGN - 1) / Tiles<T>::BIGN) * g.batch1 * g.batch2;
   const bool big = g.M >= (Tiles<T>::BIGM * 3) / 4 && g.N >= (Tiles<T>::BIGN * 3) / 4 &&
                    ctas_big >= (int64_t)(ctx().sm_count * 3) / 4;
+  if (ctx().gemm_thin && try_thin<T>(g)) return;
   if (g.npeer == 0 && (is_cplx<T>::value ? ctx().gemm_compact != 0 : (ctx().gemm_real_tile != 0 && big))) {
     Tiles<T>::compact(g);
     return;

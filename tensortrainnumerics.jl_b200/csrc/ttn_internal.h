@@ -63,6 +63,7 @@ struct Context {
   long long gram_calls = 0, gram_fallbacks = 0;   // tt_compress! calls that took the Gram path / were redone by the Jacobi path
   int gram_last_flags = 0;
   bool gemm_bulk = true;            // TMA-staged (cp.async.bulk + mbarrier) big-tile GEMM when the operands allow it; TTN_GEMM_BULK=0 disables
+  bool gemm_thin = true;            // streaming kernel for thin right-multiplications (N, K <= 32, shared B): the middle contraction of the local operators
   int gemm_real_tile = 5;           // Float64 big GEMMs: 5 = 128x64 tile, two CTAs per SM, TMA-staged when the operands allow it (else 3-stage LDGSTS);
                                     // 0 = the 128x128 one-CTA-per-SM tile of round 1; 1/2/4 = 128x64 with 3/2/4 LDGSTS stages; 3 = 64x64 (A/B timing)
   int gemm_compact = 1;        // ComplexF64 GEMMs: 1 = 64x64 tile with 2 stages (68 KB, two CTAs per SM, fits next to an eigensolver CTA of another stream); 2/3 = 3/4 stages; 0 = the 64x128 / 64x64 4-stage tiles of round 1

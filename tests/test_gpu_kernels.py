@@ -322,3 +322,30 @@ def test_gemm_tma_staged_big_tile(shape, transB):
         t.set_option("gemm_bulk", 1)
     assert relerr(plain, ref) < 1e-13
     assert relerr(got, plain) < 1e-14
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("shape", [(1024, 20, 20), (777, 10, 32), (4096, 32, 7), (256, 1, 1)])
+def test_gemm_thin_right_multiplication(shape, cplx):
+    """The streaming kernel for thin right-multiplications (csrc/gemm.cu::gemm_thin_kernel; the middle contraction T2 = T1 . W of
+    the effective operators, dmrg.jl:239-244, with K = w n^2 <= 32) against NumPy and against the DMMA tile path, with alpha / beta,
+    both B layouts and conj(B)."""
+    import ttn_b200 as t
+    M, N, K = shape
+    rng = np.random.default_rng(M + 3 * N + 7 * K + cplx)
+    A = rnd(rng, (M, K), cplx)
+    C0 = rnd(rng, (M, N), cplx)
+    assert t.get_option("gemm_thin") == 1.0
+    for transB, conjB in [(False, False), (True, False), (True, True)]:
+        B = rnd(rng, (N, K) if transB else (K, N), cplx)
+        Bm = B.T if transB else B
+        ref = 1.25 * (A @ (Bm.conj() if conjB else Bm)) + 0.5 * C0
+        got = t.gemm_host(A, B, transB=transB, conjB=conjB, alpha=1.25, beta=0.5, C0=C0)
+        assert relerr(got, ref) < 1e-14
+        t.set_option("gemm_thin", 0)
+        try:
+            tiles = t.gemm_host(A, B, transB=transB, conjB=conjB, alpha=1.25, beta=0.5, C0=C0)
+        finally:
+            t.set_option("gemm_thin", 1)
+        assert relerr(got, tiles) < 1e-14
+    assert relerr(t.gemm_host(A, rnd(rng, (K, N), cplx) * 0 + 1.0), A.sum(axis=1, keepdims=True) * np.ones((1, N))) < 1e-14
