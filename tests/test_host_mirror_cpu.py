@@ -174,3 +174,20 @@ def test_committed_round2_bench_line_follows_the_contract():
     for k in ("cfg2_sweeps_per_s", "matvec_cfg4_tflops", "dmrg_sweep_s", "mals_cfg3_heat_s", "mals_cfg3_heat_max_rank"):
         assert k in x, k
     assert x["mals_cfg3_heat_max_rank"] == 128
+
+
+def test_bench_helpers_without_a_gpu():
+    """Pieces of bench.py that do not need a device: the committed ncu capture feeds roofline.traffic, the NUMA binding is a no-op
+    without NVML, the cfg5 config names the workload and carries no model keys, and both arms describe the same config."""
+    sys.path.insert(0, ROOT)
+    import bench
+    tr = bench.captured_traffic()
+    assert tr is not None and 3e7 < tr < 2e8            # 296 lower triangles of 128 x 128 ComplexF64 = 39 MB + what L2 lets through
+    assert bench.bind_to_gpu_numa(0) is None or isinstance(bench.bind_to_gpu_numa(0), int)
+    c1, c8 = bench.cfg5_config(1, 296), bench.cfg5_config(8, 296)
+    assert "cfg5" in c1["workload"] and "model" not in c1 and c1["total_vectors"] == bench.TOTAL5 == 4096
+    assert {k for k in c1} == {k for k in c8}
+    rks, Rk = bench.cfg5_ranks()
+    assert max(rks) == 64 and max(Rk) == 4 and len(rks) == bench.D5 + 1 == 31
+    m = bench.cfg5_flop_model()
+    assert 1.3e10 < m["total"] < 1.5e10                 # SURVEY.md section 8(d)-5: ~13-14 GFLOP per vector
