@@ -11,14 +11,16 @@ the cfg4 matvec and the DMRG sweep stay in the line as compact extras (full deta
   value     device-timed (CUDA events on the library's stream, max over ranks): inputs resident in HBM (10.3 GB at N = 1,
             every chunk of 296 vectors is 0.74 GB, far larger than L2, and is touched once per step);
   e2e       the same step through the public host API on pinned host buffers: per chunk H2D of the input cores,
-            `apply_compress`, D2H of the rounded cores into pinned memory — wall clock, max over ranks;
-  roofline  the kernel family that dominates the step (per-family CUDA events over one step) against the measured FP64 GEMM
-            peak, plus the whole step against the 13.3 GFLOP/vector model of SURVEY.md §8(d)-5;
+            `apply_compress`, D2H of the rounded cores into pinned memory, software-pipelined over the chunks of all timed steps
+            (the copies of chunk i +- 1 run on the copy stream while chunk i computes) — wall clock, max over ranks;
+  roofline  the kernel family that dominates the step (per-family CUDA events over one step, the host threads profiled one after
+            the other) against the measured FP64 GEMM peak, plus the whole step against the 13.3 GFLOP/vector model of SURVEY.md
+            §8(d)-5; `traffic` = DRAM bytes per launch of the dominant kernel from the committed ncu capture;
   cpu_baseline  the NumPy restatement of the reference algorithm on the host cores (bounded sample, rank 0, N = 1).
 
 `--impl reference` times the reference's own CPU algorithm (oracle/, including the discarded `orthogonalize` of
 src/tt_tools.jl:769 that the Julia code executes in every bond step) on a bounded sample of the same workload: every step is
-ONE vector of the batch, fully measured (no extrapolation).
+ONE vector of the batch, fully measured (no extrapolation); the run stops after a time budget and reports the steps it measured.
 """
 import argparse
 import json
@@ -231,7 +233,7 @@ def pinned_chunks(torch, nvec, chunk, rank):
 
 class ChunkWorker(threading.Thread):
     """One host thread = one library context (compute stream + copy stream + allocation cache, include/ttn_b200.h).  Each worker
-    owns every `nw`-th chunk of this rank's vectors; two workers keep two chunks in flight, so the latency-bound eigensolver
+    owns every `nw`-th chunk of this rank's vectors; the workers keep one chunk each in flight, so the latency-bound eigensolver
     kernels of one chunk overlap the DMMA GEMMs of the other."""
 
     def __init__(self, idx, nw, host_chunks, Ad, rks, torch, keep):
